@@ -1,0 +1,190 @@
+/* kiltro_b200.h -- C ABI of libkiltro_b200.so (B200 / sm_100a implementation of Kiltro's FEM hot path).
+ *
+ * Conventions:
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (torch tensor storage, cudaMalloc, ...);
+ *     h_* is a HOST pointer; nothing is allocated behind the caller's back except where a function says so
+ *     (kb_pattern_build allocates its sort scratch with cudaMallocAsync and frees it before returning);
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered; functions that return a count or a
+ *     convergence record to the host synchronise that stream themselves and say so;
+ *   - return value: 0 on success, >0 a cudaError_t, <0 a KB_E* code; kb_error_string() decodes both;
+ *   - connectivity / CSR indices are int32 (the reference's native code is int32 too:
+ *     kiltro/FiniteElements/ComputeSparsityPattern.pyx:15-41, Assembly.py:26), values are fp64.
+ *
+ * Each entry point cites the reference interface it replaces as file:line under /root/reference.
+ */
+#ifndef KILTRO_B200_H
+#define KILTRO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_EINVAL     (-1)   /* bad argument (null pointer, unsupported element type, ...) */
+#define KB_ETOOBIG    (-2)   /* a count does not fit the int32 index space */
+#define KB_EWORKSPACE (-3)   /* caller-provided workspace too small */
+#define KB_EBREAKDOWN (-4)   /* Krylov breakdown (rho, omega or p.Ap vanished / non-finite) */
+#define KB_ENOTCONV   (-5)   /* maxiter reached without meeting the tolerance */
+
+/* advection term of the element matrix */
+#define KB_MODE_REFERENCE  0 /* scalar broadcast, what Temperature/TemperaturePG compute: VariationalPrinciple.py:152,156,164-173 */
+#define KB_MODE_CONSISTENT 1 /* W (x) (u.grad N): MaterialBase.py:42-58 (the examples' HeatAdvectionDiffusion) */
+
+/* material constants, MaterialBase.py:4-39 */
+typedef struct kb_material { double k, rho, c_v, area, q; } kb_material;
+
+/* result record of the Krylov solvers */
+typedef struct kb_solve_info {
+    int32_t iterations;      /* iterations performed */
+    int32_t status;          /* 0 converged, KB_ENOTCONV, KB_EBREAKDOWN */
+    double  residual;        /* final ||b - A x||_2 (recurrence residual of the preconditioned system, see krylov.cu) */
+    double  rhs_norm;        /* ||b||_2 of the system actually iterated on */
+    int64_t kernel_launches; /* kernels launched by the call */
+} kb_solve_info;
+
+const char *kb_error_string(int code);
+int kb_version(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
+int64_t kb_launch_count(void);
+void kb_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K8  mesh generators                       replaces kiltro/MeshGeneration/Mesh.py:14-30 (Line), :33-58 (Rectangle)
+ * points (nnode, ndim) fp64 row-major, bit-identical to numpy.linspace/meshgrid; elements (nelem, npe) int32.
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_mesh_line(double left, double right, int64_t n, double *d_points, int32_t *d_elements, void *stream);
+int kb_mesh_rectangle(double x0, double y0, double x1, double y1, int64_t nx, int64_t ny,
+                      double *d_points, int32_t *d_elements, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1  batched element matrices              replaces VariationalPrinciple.py:42-69 (GetLocalMass), :117-173
+ *     (Temperature.GetLocalConvection), :216-261,:311-342 (TemperaturePG), FunctionSpace.py:5-62 (tables)
+ * ndim 1 -> line-2 (npe 2, 2 Gauss points), ndim 2 -> quad-4 (npe 4, 2x2 Gauss points).
+ * d_velocity may be NULL (zero velocity).  d_Ke (nelem, npe*npe) row-major = convectionel.ravel();
+ * d_Fe (nelem, npe); d_Me (nelem, npe*npe) or NULL (steady: Me is not computed, VariationalPrinciple.py:104-107).
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_element_matrices(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem,
+                        const double *d_velocity, const kb_material *material, int mode, int petrov,
+                        double *d_Ke, double *d_Fe, double *d_Me, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K2  symbolic phase                        replaces FiniteElements/ComputeSparsityPattern.pyx:44-112 and
+ *     ComputeSparsityPattern.h:22-62 (_ComputeSparsityPattern_), :67-122 (_ComputeDataIndices_)
+ * COO keys of every element entry -> device LSD radix sort -> unique.  nent = nelem*(npe*nvar)^2.
+ * Outputs (all device, caller-allocated):
+ *   d_indptr (nnode*nvar+1), d_indices (capacity nent, first nnz valid; like .pyx:64,91),
+ *   d_data_local (nent), d_data_global (nent)          -- the reference's two scatter maps;
+ *   d_seg_ptr (nent+1, first nnz+1 valid), d_gather_src (nent) -- row-owner gather map: CSR entry u sums
+ *        Ke_flat[d_gather_src[p]] for p in [seg_ptr[u], seg_ptr[u+1]) ; contributors are in ascending element
+ *        order, the order of the reference's sequential += (Assembly.py:46,60-61);
+ *   d_diag_pos (nnode*nvar) position of the diagonal entry of each row (-1 if absent).
+ * *h_nnz receives nnz (the call synchronises `stream`).
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode, int nvar,
+                     int32_t *d_indptr, int32_t *d_indices, int32_t *d_data_local, int32_t *d_data_global,
+                     int32_t *d_seg_ptr, int32_t *d_gather_src, int32_t *d_diag_pos, int64_t *h_nnz, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K3  numeric assembly                      replaces FiniteElements/Assembly.py:46-72 (element loop, scatter-add)
+ * (a) two-step seam: CSR values from materialised element matrices through the gather map (deterministic segmented
+ *     reduction, no atomics).  d_Me/d_M may be NULL.  d_Flux (nnode) from d_Fe through the diagonal's segment.
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_assemble_from_elements(int npe, int64_t nnode, int64_t nnz, const int32_t *d_seg_ptr,
+                              const int32_t *d_gather_src, const int32_t *d_diag_pos,
+                              const double *d_Ke, const double *d_Me, const double *d_Fe,
+                              double *d_K, double *d_M, double *d_Flux, void *stream);
+
+/* (b) fused path: element matrices are computed on chip and never written to HBM.  A "tile plan" built once per
+ *     mesh (symbolic) assigns to each CTA a set of CSR rows and the elements incident to them.
+ *     kb_tile_plan_build sizes/fills the plan; see assemble.cu for the layout.  h_sizes[0..3] receive
+ *     {ntiles, total tile elements, total pairs, reserved}.  Pass d_* = NULL to only obtain the sizes. */
+int kb_tile_plan_sizes(int64_t nnode, int64_t nelem, int npe, int64_t nx_nodes, int64_t ny_nodes, int64_t *h_sizes);
+int kb_tile_plan_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode,
+                       const int32_t *d_indptr, const int32_t *d_seg_ptr, const int32_t *d_gather_src,
+                       const int32_t *d_diag_pos, int64_t nx_nodes, int64_t ny_nodes,
+                       int32_t *d_tile_rows, int32_t *d_tile_row_ptr, int32_t *d_tile_elems, int32_t *d_tile_elem_ptr,
+                       uint16_t *d_pairs, int32_t *d_pair_ptr, void *stream);
+int kb_assemble_fused(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem, int64_t nnode,
+                      const double *d_velocity, const kb_material *material, int mode, int petrov,
+                      const int32_t *d_indptr, const int32_t *d_indices,
+                      int64_t ntiles, const int32_t *d_tile_rows, const int32_t *d_tile_row_ptr,
+                      const int32_t *d_tile_elems, const int32_t *d_tile_elem_ptr,
+                      const uint16_t *d_pairs, const int32_t *d_pair_ptr,
+                      double *d_K, double *d_M, double *d_Flux, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K4  boundary conditions                   replaces kiltro/BoundaryCondition.py
+ * ------------------------------------------------------------------------------------------------------- */
+/* :100-122 GetDirichletBoundaryConditions.  flags (ndof) fp64, NaN = free.  d_renum[i] = index of DOF i in the reduced
+ * system if free, -1 - (index among the fixed DOFs) otherwise.  d_columns_in / d_columns_out (capacity ndof each, int64
+ * like the reference), d_applied (capacity ndof).  h_counts[0]=n_free, h_counts[1]=n_fixed (synchronises). */
+int kb_dirichlet_split(const double *d_flags, int64_t ndof, int32_t *d_renum, int64_t *d_columns_in,
+                       int64_t *d_columns_out, double *d_applied, int64_t *h_counts, void *stream);
+/* :125-140 ComputeNeumannFluxes: F[i] = flag[i] if not NaN else 0 */
+int kb_neumann_fluxes(const double *d_flags, int64_t ndof, double *d_F, void *stream);
+/* :169-200 ApplyDirichletGetReducedMatrices.  d_applied (n_fixed): prescribed values in columns_out order (what
+ * kb_dirichlet_split wrote, possibly scaled by the caller's load increment).  In place:
+ *   F[free] -= (sum_{j fixed, !isclose(T_j,0)} K_ij T_j, ascending j) * load_factor
+ * Reduced CSR (K_b = K[in,:][:,in]) is written to d_Kb_* (d_Kb_indptr n_free+1; capacity nnz for data/indices);
+ * d_Mb_data optional (same pattern, from d_M).  d_Fb (n_free) = F[in].  h_nnz_b receives nnz(K_b) (synchronises). */
+int kb_apply_dirichlet_reduce(int64_t ndof, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
+                              const double *d_M, const int32_t *d_renum, const double *d_applied, double load_factor,
+                              double *d_F, int64_t n_free, int32_t *d_Kb_indptr, int32_t *d_Kb_indices,
+                              double *d_Kb_data, double *d_Mb_data, double *d_Fb, int64_t *h_nnz_b, void *stream);
+/* :203-241 TotalComponentSol / UpdateFixDoFs / UpdateFreeDoFs: T[i] = sol[renum[i]] if free (or 0 when d_sol NULL),
+ * applied[-1-renum[i]] if fixed (or 0 when d_applied NULL) */
+int kb_total_component_sol(int64_t ndof, const int32_t *d_renum, const double *d_sol, const double *d_applied,
+                           double *d_T, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K5  CSR SpMV y = A x                      (building block of K6; replaces nothing 1:1 -- the reference's only
+ *     mat-vec is the dense np.dot in FEMSolver.py:281)
+ * d_rowblk (nblk+1): row partition with ~equal nnz per CTA from kb_spmv_partition (nblk = kb_spmv_num_blocks).
+ * d_dot_x / d_dot_out: optional fused dot products: out[0] = <w, y>, out[1] = <y, y> where w = d_dot_w (may be NULL).
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t kb_spmv_num_blocks(int64_t nnz);
+int kb_spmv_partition(int64_t nrows, int64_t nnz, const int32_t *d_indptr, int32_t *d_rowblk, void *stream);
+int kb_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+            const int32_t *d_rowblk, const double *d_x, double *d_y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K6  Krylov solvers                        replace LinearSolver.Solve -> scipy spsolve, FEMSolver.py:350-364
+ * Jacobi preconditioning is applied as an explicit diagonal scaling of a private copy of the values
+ * (CG: D^-1/2 A D^-1/2, BiCGSTAB: A D^-1), which is algebraically the Jacobi-preconditioned method.
+ * workspace: kb_krylov_workspace_bytes(nrows, nnz) bytes of device memory.  x: initial guess in, solution out.
+ * The calls synchronise `stream` every `check_every` iterations to test convergence ||r|| <= rtol*||b||.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t kb_krylov_workspace_bytes(int64_t nrows, int64_t nnz);
+int kb_cg_solve(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+                const double *d_b, double *d_x, double rtol, int maxiter, int check_every,
+                void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream);
+int kb_bicgstab_solve(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                      const double *d_vals, const double *d_b, double *d_x, double rtol, int maxiter, int check_every,
+                      void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K7  transient step                        replaces FEMSolver.TransientSolver, FEMSolver.py:253-297 (+ :138-145)
+ * One theta-step on the FULL system with the reference's (M^-1)[in,in] convention:
+ *     rhs_i = (K T^n + F)_i for free i, 0 for fixed i ;  solve (M + theta dt Kff) y = rhs ;  T^{n+1}_free = T^n - dt y
+ * kb_time_step_rule: dt = factor * min_e rho c_v |X1-X0|^2 / (2k)   (FEMSolver.py:138-144); result in *d_dt (device).
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_time_step_rule(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem,
+                      const kb_material *material, double factor, double *d_dt, void *stream);
+/* rhs = mask_free .* (K T + F) */
+int kb_transient_rhs(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
+                     const int32_t *d_rowblk, const int32_t *d_renum, const double *d_F, const double *d_T,
+                     double *d_rhs, void *stream);
+/* A = M + theta*dt*Kff  (Kff: rows and columns of fixed DOFs zeroed) on the shared pattern */
+int kb_transient_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                        const double *d_K, const double *d_M, const int32_t *d_renum, double theta_dt,
+                        double *d_A, void *stream);
+/* T_next = fixed ? td : T - dt*y */
+int kb_transient_update(int64_t ndof, const int32_t *d_renum, const double *d_td, const double *d_T,
+                        const double *d_y, double dt, double *d_Tnext, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KILTRO_B200_H */

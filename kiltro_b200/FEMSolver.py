@@ -1,0 +1,231 @@
+"""Driver + linear solver, mirroring kiltro/FEMSolver.py (reference file:line cited per method).
+
+FEMSolver.Solve(formulation, mesh, material, boundary_condition) keeps the reference's signature and return type
+(a PostProcess whose .sol is (nnodes, nvar, nincr) float64).  Every stage runs on the GPU through libkiltro_b200.so:
+symbolic pattern (K2) -> numeric assembly (K1+K3) -> Dirichlet/Neumann (K4) -> Jacobi-preconditioned CG / BiCGSTAB
+(K5+K6) -> solution scatter (K4); the transient branch, which the reference ships broken, runs the
+theta-method loop (K7) on device with theta = 0 reproducing the reference's intended forward Euler."""
+from copy import deepcopy
+from time import time
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+from .MeshGeneration import Mesh
+from .FiniteElements.Assembly import Assemble
+from .PostProcess import PostProcess
+from .sparse import DeviceCSR, issparse
+
+_quiet = [False]
+
+
+def _say(*a):
+    if not _quiet[0]:
+        print(*a)
+
+
+class FEMSolver(object):
+
+    def __init__(self, analysis_type="steady", analysis_nature="linear",
+                 number_of_load_increments=1, print_incremental_log=False,
+                 memory_store_frequency=1, recompute_sparsity_pattern=False,
+                 squeeze_sparsity_pattern=False, number_of_increments=None, theta=0.0, time_step=None,
+                 time_step_factor=0.1, include_heat_source=False, assembly="auto", verbose=True):
+        # FEMSolver.py:14-28 (+ the examples' number_of_increments=, examples/transient_2d.py:73-74)
+        self.analysis_type = analysis_type
+        self.analysis_nature = analysis_nature
+        self.number_of_load_increments = number_of_load_increments
+        self.save_frequency = int(memory_store_frequency)
+        self.print_incremental_log = print_incremental_log
+        self.recompute_sparsity_pattern = recompute_sparsity_pattern
+        self.squeeze_sparsity_pattern = squeeze_sparsity_pattern
+        self.is_sparsity_pattern_computed = False
+        # extensions (all default to the reference's behaviour)
+        self.number_of_increments = number_of_increments
+        self.theta = float(theta)
+        self.time_step = time_step
+        self.time_step_factor = float(time_step_factor)          # FEMSolver.py:144 uses 0.1
+        self.include_heat_source = include_heat_source           # the reference drops Flux from the RHS
+        self.assembly = assembly                                  # "auto" | "fused" | "two_pass"
+        self.verbose = verbose
+        self.sparsity = None
+        self.timings = {}
+        self.solver_info = None
+
+    # ------------------------------------------------------------------------------------------ FEMSolver.py:31-62
+    def __checkdata__(self, material, boundary_condition, formulation, mesh, function_spaces, solver):
+        if mesh is None:
+            raise ValueError("No mesh detected for the analysis")
+        elif not isinstance(mesh, Mesh):
+            raise ValueError("mesh has to be an instance of Kiltro.Mesh")
+        if boundary_condition is None:
+            raise ValueError("No boundary conditions detected for the analysis")
+        if material is None:
+            raise ValueError("No material model chosen for the analysis")
+        if formulation is None:
+            raise ValueError("No variational formulation specified")
+        if function_spaces is None:
+            if formulation.function_spaces is None:
+                raise ValueError("No interpolation functions specified")
+            else:
+                function_spaces = formulation.function_spaces
+        if solver is None:
+            solver = LinearSolver(linear_solver="iterative", linear_solver_type="auto")
+        if boundary_condition.initial_field is None and self.analysis_type == "transient":
+            raise ValueError("The problem is TRANSIENT but there are not initial conditions.")
+        return function_spaces, solver
+
+    def __makeoutput__(self, mesh, TotalSol, formulation):       # FEMSolver.py:65-70
+        post_process = PostProcess(formulation.ndim, formulation.nvar)
+        post_process.SetMesh(mesh)
+        post_process.SetSolution(TotalSol)
+        post_process.solver_info = self.solver_info
+        return post_process
+
+    # ------------------------------------------------------------------------------------------ FEMSolver.py:73-153
+    def Solve(self, formulation=None, mesh=None, material=None,
+              boundary_condition=None, function_spaces=None, solver=None):
+        _quiet[0] = not self.verbose
+        function_spaces, solver = self.__checkdata__(material, boundary_condition, formulation, mesh,
+                                                     function_spaces, solver)
+        self.PrintPreAnalysisInfo(mesh, formulation)
+        self.ComputeSparsityFEM(mesh, formulation)
+
+        _say('Assembling the system and acquiring neccessary information for the analysis...')
+        boundary_condition.GetDirichletBoundaryConditions(formulation, mesh, material, self)
+        NeumannFluxes = boundary_condition.ComputeNeumannFluxes(mesh, material)
+
+        if self.analysis_nature == "nonlinear":
+            raise ValueError("nonlinear analysis is not available (the reference's branch is unreachable too)")
+        if self.analysis_type == "steady":
+            if self.save_frequency != 1:
+                raise ValueError("memory_store_frequency != 1 is not supported for steady analyses")
+            TotalSol = self.SteadyLinearDiffusionSolver(function_spaces, formulation, mesh, material,
+                                                        boundary_condition, solver, None, NeumannFluxes)
+            return self.__makeoutput__(mesh, TotalSol, formulation)
+        return self.TransientSolver(function_spaces, formulation, solver, mesh, material, boundary_condition,
+                                    NeumannFluxes)
+
+    # ------------------------------------------------------------------------------------------ FEMSolver.py:156-228
+    def SteadyLinearDiffusionSolver(self, function_spaces, formulation, omesh, material,
+                                    boundary_condition, solver, TotalSol, NeumannFluxes):
+        mesh = omesh                                             # the reference deep-copies (:165) but never edits it
+        LoadIncrement = int(self.number_of_load_increments)
+        LoadFactor = 1. / LoadIncrement
+        nnodes, nvar = mesh.nnodes, formulation.nvar
+        if TotalSol is None:
+            TotalSol = D.zeros((nnodes, nvar, LoadIncrement))
+        NodalFluxes = -LoadFactor * NeumannFluxes                                            # :171
+        AppliedDirichletInc = LoadFactor * boundary_condition.applied_dirichlet_device       # :172
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for Increment in range(LoadIncrement):
+            ev[0].record()
+            K, Flux, _ = Assemble(self, function_spaces, formulation, mesh, material, boundary_condition)   # :183
+            Residual = NodalFluxes.clone()                                                   # :179,186
+            if self.include_heat_source:
+                Residual += LoadFactor * Flux          # opt-in: the reference computes Flux and drops it
+            ev[1].record()
+            K_b, F_b = boundary_condition.ApplyDirichletGetReducedMatrices(K, Residual, AppliedDirichletInc)[:2]   # :190
+            ev[2].record()
+            sol = solver.Solve(K_b, F_b)                                                     # :193
+            ev[3].record()
+            dphi = boundary_condition.TotalComponentSol(sol, AppliedDirichletInc, 0, K.shape[0], nvar)   # :196
+            TotalSol[:, :, Increment] += dphi                                                # :199
+            torch.cuda.synchronize()
+            self.timings = {"assemble_ms": ev[0].elapsed_time(ev[1]), "bc_ms": ev[1].elapsed_time(ev[2]),
+                            "solve_ms": ev[2].elapsed_time(ev[3])}
+            self.solver_info = getattr(solver, "info", None)
+            _say("Finished load increment " + str(Increment) + " for linear problem. Solver time is",
+                 self.timings["solve_ms"] * 1e-3)
+        if LoadIncrement > 1:                                                                # :225-226
+            TotalSol = torch.cumsum(TotalSol, dim=2)
+        return TotalSol
+
+    # ------------------------------------------------------------------------------------------ FEMSolver.py:253-297
+    def TransientSolver(self, function_spaces, formulation, solver, mesh, material, boundary_condition,
+                        NeumannFluxes):
+        from .transient import run_transient
+        return run_transient(self, function_spaces, formulation, solver, mesh, material, boundary_condition,
+                             NeumannFluxes)
+
+    def PrintPreAnalysisInfo(self, mesh, formulation):           # FEMSolver.py:300-304
+        _say('Pre-processing the information. Getting paths, solution parameters, mesh info, interpolation info etc...')
+        _say('Number of nodes is', mesh.nnodes, 'number of DoFs is', mesh.nnodes * formulation.nvar)
+        _say('Number of elements is', mesh.nelem)
+
+    def ComputeSparsityFEM(self, mesh, formulation):             # FEMSolver.py:313-330
+        if self.is_sparsity_pattern_computed is False:
+            if self.recompute_sparsity_pattern is False:
+                t_sp = time()
+                from .FiniteElements.ComputeSparsityPattern import ComputeSparsityPatternDevice
+                if self.squeeze_sparsity_pattern:
+                    raise ValueError("Not implemented yet")
+                sp = ComputeSparsityPatternDevice(mesh, formulation.nvar)
+                self.sparsity = sp
+                self.indices, self.indptr = sp.indices, sp.indptr
+                self.data_local_indices, self.data_global_indices = sp.data_local_indices, sp.data_global_indices
+                self.is_sparsity_pattern_computed = True
+                torch.cuda.synchronize()
+                self.timings["pattern_s"] = time() - t_sp
+                _say("Computed sparsity pattern for the mesh. Time elapsed is {} seconds".format(time() - t_sp))
+            else:
+                raise ValueError("recompute_sparsity_pattern=True is not implemented (neither is it upstream: "
+                                 "Assembly.py:54)")
+        return self.sparsity
+
+
+class LinearSolver(object):
+    """Replaces kiltro/FEMSolver.py:335-364 (scipy spsolve) with device Krylov solvers (csrc/krylov.cu).
+
+    linear_solver_type: "auto" (CG when the matrix is known symmetric, BiCGSTAB otherwise), "cg", "bicgstab".
+    The reference's ("direct", "lapack") arguments are accepted and mapped to "auto" with the default tolerance."""
+
+    def __init__(self, linear_solver="iterative", linear_solver_type="auto", tol=1.0e-12, maxiter=None,
+                 check_every=50, raise_on_failure=False):
+        self.is_sparse = True
+        self.solver_type = linear_solver
+        self.solver_subtype = linear_solver_type if linear_solver_type in ("cg", "bicgstab") else "auto"
+        self.has_umfpack = False
+        self.tol = float(tol)
+        self.maxiter = maxiter
+        self.check_every = int(check_every)
+        self.raise_on_failure = raise_on_failure
+        self.info = None
+        self.x0 = None
+
+    def Solve(self, A, b):
+        if not issparse(A):
+            raise ValueError("Linear system is not of sparse type")          # FEMSolver.py:355-356
+        lib = _lib.load()
+        b = D.to_device(b, torch.float64).reshape(-1)
+        n = A.shape[0]
+        if n == 0 and b.shape[0] == 0:
+            warn("Empty linear system!!! Nothing to solve!!!")               # FEMSolver.py:358-360
+            return b.clone()
+        if b.shape[0] != n:
+            raise ValueError("dimension mismatch between A and b")
+        method = self.solver_subtype
+        if method == "auto":
+            method = "cg" if A.symmetric else "bicgstab"
+        maxiter = int(self.maxiter) if self.maxiter is not None else max(1000, 20 * int(np.sqrt(n)) + 200)
+        x = D.zeros(n) if self.x0 is None else D.to_device(self.x0, torch.float64).reshape(-1).clone()
+        nbytes = lib.kb_krylov_workspace_bytes(n, A.nnz)
+        ws = D.empty(nbytes, torch.uint8)
+        info = _lib.kb_solve_info()
+        fn = lib.kb_cg_solve if method == "cg" else lib.kb_bicgstab_solve
+        _lib.check(fn(n, A.nnz, D.ptr(A.indptr), D.ptr(A.indices), D.ptr(A.data), D.ptr(b), D.ptr(x), self.tol,
+                      maxiter, self.check_every, D.ptr(ws), nbytes, info, D.stream_ptr()))
+        self.info = {"method": method, "iterations": int(info.iterations), "status": int(info.status),
+                     "residual": float(info.residual), "rhs_norm": float(info.rhs_norm),
+                     "relative_residual": float(info.residual) / float(info.rhs_norm) if info.rhs_norm > 0 else 0.0,
+                     "kernel_launches": int(info.kernel_launches)}
+        if info.status != 0:
+            msg = "%s stopped after %d iterations with relative residual %.3e (status %d: %s)" % (
+                method, info.iterations, self.info["relative_residual"], info.status,
+                lib.kb_error_string(int(info.status)).decode())
+            if self.raise_on_failure:
+                raise _lib.KiltroB200Error(msg)
+            warn(msg)
+        return x

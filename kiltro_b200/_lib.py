@@ -1,0 +1,85 @@
+"""ctypes binding of libkiltro_b200.so (include/kiltro_b200.h).  There is NO CPU fallback: if the library is missing
+or a call is made without a CUDA device the caller gets an exception, never a silently different code path."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkiltro_b200.so")
+
+c_i32p = ctypes.c_void_p      # all device/host buffers are passed as raw addresses
+c_vp = ctypes.c_void_p
+I64 = ctypes.c_int64
+I32 = ctypes.c_int
+F64 = ctypes.c_double
+
+
+class kb_material(ctypes.Structure):
+    _fields_ = [("k", F64), ("rho", F64), ("c_v", F64), ("area", F64), ("q", F64)]
+
+
+class kb_solve_info(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("residual", F64), ("rhs_norm", F64),
+                ("kernel_launches", I64)]
+
+
+KB_MODE_REFERENCE = 0
+KB_MODE_CONSISTENT = 1
+KB_ENOTCONV = -5
+KB_EBREAKDOWN = -4
+
+# name -> (restype, argtypes); mirrors include/kiltro_b200.h one to one
+SIGNATURES = {
+    "kb_error_string": (ctypes.c_char_p, [I32]),
+    "kb_version": (I32, []),
+    "kb_launch_count": (I64, []),
+    "kb_launch_count_reset": (None, []),
+    "kb_mesh_line": (I32, [F64, F64, I64, c_vp, c_vp, c_vp]),
+    "kb_mesh_rectangle": (I32, [F64, F64, F64, F64, I64, I64, c_vp, c_vp, c_vp]),
+    "kb_element_matrices": (I32, [I32, c_vp, c_vp, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, c_vp, c_vp,
+                                  c_vp]),
+    "kb_pattern_build": (I32, [c_vp, I64, I32, I64, I32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               ctypes.POINTER(I64), c_vp]),
+    "kb_assemble_from_elements": (I32, [I32, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
+    "kb_neumann_fluxes": (I32, [c_vp, I64, c_vp, c_vp]),
+    "kb_apply_dirichlet_reduce": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, I64, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
+    "kb_total_component_sol": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_num_blocks": (I64, [I64]),
+    "kb_spmv_partition": (I32, [I64, I64, c_vp, c_vp, c_vp]),
+    "kb_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_krylov_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
+    "kb_cg_solve": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, I32, I32, c_vp, ctypes.c_size_t,
+                          ctypes.POINTER(kb_solve_info), c_vp]),
+    "kb_bicgstab_solve": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, I32, I32, c_vp, ctypes.c_size_t,
+                                ctypes.POINTER(kb_solve_info), c_vp]),
+}
+
+_LIB = None
+
+
+class KiltroB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the CUDA library; raises (loudly) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise KiltroB200Error(
+                "libkiltro_b200.so is missing (%s). Build it with `python -m kiltro_b200.build` or "
+                "__graft_entry__.build(); kiltro_b200 has no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().kb_error_string(int(rc))
+        raise KiltroB200Error("libkiltro_b200 call failed (%d): %s" % (rc, msg.decode() if msg else "?"))

@@ -1,0 +1,271 @@
+// K2: symbolic phase -- CSR sparsity pattern and scatter/gather maps, entirely on device.
+//
+// Replaces kiltro/FiniteElements/ComputeSparsityPattern.pyx:44-112 (NumPy argsort/unique preparation + prefix sum)
+// and ComputeSparsityPattern.h:22-62 (_ComputeSparsityPattern_: per-node sort+unique of neighbour lists) and
+// :67-122 (_ComputeDataIndices_: per-entry binary search of the CSR slot).
+//
+// B200 formulation: every element entry (local row i, local col b; nodes visited in ascending node id as the
+// reference does, .pyx:51-52) becomes a 64-bit key (row << cbits | col) with its entry id as payload; one stable LSD
+// radix sort orders all entries by (row, col) and -- because the sort is stable and entry ids start ascending -- by
+// ascending element inside each (row, col) group.  Group heads give the CSR pattern (rows strictly ascending, explicit
+// zeros kept, exactly the reference's std::sort+std::unique result), the running head count gives
+// data_global_indices, and the sorted payload is the deterministic row-owner gather map used by the numeric phase.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------- key generation
+// one thread per element entry idx = e*cap + i*ndof + b  (ndof = npe*nvar, cap = ndof^2)
+template <int NPE>
+__global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ elements, int64_t nent, int nvar,
+                                                   int cbits, uint64_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ payload, int32_t *__restrict__ data_local) {
+    const int ndof = NPE * nvar, cap = ndof * ndof;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nent; idx += stride) {
+        const int64_t e = idx / cap;
+        const int r = (int)(idx - e * cap);
+        const int i = r / ndof, b = r - i * ndof;
+        // stable insertion argsort of the element's nodes ("sorter", .pyx:51)
+        int node[NPE], sorter[NPE];
+#pragma unroll
+        for (int a = 0; a < NPE; ++a) { node[a] = __ldg(elements + e * NPE + a); sorter[a] = a; }
+#pragma unroll
+        for (int a = 1; a < NPE; ++a) {
+#pragma unroll
+            for (int c = a; c > 0; --c) {
+                if (node[c - 1] > node[c]) {
+                    int t = node[c]; node[c] = node[c - 1]; node[c - 1] = t;
+                    t = sorter[c]; sorter[c] = sorter[c - 1]; sorter[c - 1] = t;
+                }
+            }
+        }
+        // DOF (sorted-node rank, component) of local row i and local column b                       .h:86-98
+        const int in_ = i / nvar, ic = i - in_ * nvar, bn = b / nvar, bc = b - bn * nvar;
+        int rn = 0, rs = 0, cn = 0, cs = 0;
+#pragma unroll
+        for (int a = 0; a < NPE; ++a) {        // register-friendly select instead of dynamic indexing
+            if (a == in_) { rn = node[a]; rs = sorter[a]; }
+            if (a == bn) { cn = node[a]; cs = sorter[a]; }
+        }
+        const uint64_t row = (uint64_t)rn * nvar + ic, col = (uint64_t)cn * nvar + bc;
+        keys[idx] = (row << cbits) | col;
+        payload[idx] = (uint32_t)idx;
+        data_local[idx] = (rs * nvar + ic) * ndof + (cs * nvar + bc);                               // .h:114
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- LSD radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+// per-tile digit histogram -> hist[digit * ntiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys, int64_t n, int shift,
+                                                        int64_t ntiles, int *__restrict__ hist) {
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 0xff)], 1);     // integer, shared memory: order-free
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter.  Warp w owns the contiguous items [w*512, (w+1)*512) of the tile, visited in 16 chunks of 32.
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ keys_in,
+                                                           const uint32_t *__restrict__ vals_in, int64_t n, int shift,
+                                                           int64_t ntiles, const int *__restrict__ hist_scanned,
+                                                           uint64_t *__restrict__ keys_out,
+                                                           uint32_t *__restrict__ vals_out) {
+    __shared__ int cnt[RS_WARPS][256];
+    __shared__ int dbase[256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    dbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (32 * RS_ITEMS) + lane;
+    uint64_t key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+    int rank[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const int64_t i = base + c * 32;
+        const bool ok = i < n;
+        key[c] = ok ? keys_in[i] : ~0ull;
+        val[c] = ok ? vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const int d = (int)((key[c] >> shift) & 0xff);
+        const uint32_t peers = __match_any_sync(KB_FULL, d);
+        const int before = __popc(peers & lt);
+        const int old = cnt[w][d];                  // same value for every peer (read before the leader's update)
+        __syncwarp();
+        if (before == 0) cnt[w][d] = old + __popc(peers);
+        __syncwarp();
+        rank[c] = old + before;
+    }
+    __syncthreads();
+    {   // exclusive scan over warps for digit = threadIdx.x
+        int run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) { const int t = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const int64_t i = base + c * 32;
+        if (i < n) {
+            const int d = (int)((key[c] >> shift) & 0xff);
+            const int64_t pos = (int64_t)dbase[d] + cnt[w][d] + rank[c];
+            keys_out[pos] = key[c];
+            vals_out[pos] = val[c];
+        }
+    }
+}
+
+struct HistIn {
+    const int *h;
+    __device__ int operator()(int64_t i) const { return h[i]; }
+};
+struct HistOut {
+    int *h;
+    __device__ void operator()(int64_t i, int ex, int) const { h[i] = ex; }
+};
+
+// ----------------------------------------------------------------------------------------------- heads -> CSR
+struct HeadIn {
+    const uint64_t *keys;
+    __device__ int operator()(int64_t p) const { return (p == 0 || keys[p] != keys[p - 1]) ? 1 : 0; }
+};
+
+struct HeadOut {
+    const uint64_t *keys;
+    const uint32_t *payload;
+    const int32_t *data_local;
+    int cbits, cap;
+    int32_t *indptr, *indices, *data_global, *seg_ptr, *gather_src, *diag_pos;
+    __device__ void operator()(int64_t p, int ex, int head) const {
+        const int uid = ex + head - 1;                       // index of this entry's (row, col) group = CSR slot
+        const uint32_t idx = payload[p];
+        data_global[idx] = uid;                              // .h:113
+        gather_src[p] = (int32_t)((idx / (uint32_t)cap) * (uint32_t)cap) + data_local[idx];
+        if (head) {
+            const uint64_t key = keys[p];
+            const int64_t row = (int64_t)(key >> cbits);
+            const int64_t col = (int64_t)(key & ((1ull << cbits) - 1ull));
+            indices[uid] = (int32_t)col;
+            seg_ptr[uid] = (int32_t)p;
+            if (row == col) diag_pos[row] = uid;
+            const int64_t prev_row = p == 0 ? -1 : (int64_t)(keys[p - 1] >> cbits);
+            for (int64_t r = prev_row + 1; r <= row; ++r) indptr[r] = uid;      // also covers empty rows
+        }
+    }
+};
+
+__global__ void k_pattern_tail(const uint64_t *__restrict__ keys, int64_t nent, int cbits, int64_t nrows,
+                               const int *__restrict__ total, int32_t *__restrict__ indptr,
+                               int32_t *__restrict__ seg_ptr) {
+    const int nnz = *total;
+    const int64_t last_row = nent > 0 ? (int64_t)(keys[nent - 1] >> cbits) : -1;
+    for (int64_t r = last_row + 1 + threadIdx.x; r <= nrows; r += blockDim.x) indptr[r] = nnz;
+    if (threadIdx.x == 0) seg_ptr[nnz] = (int32_t)nent;
+}
+
+__global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ p, int64_t n, int32_t v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+int bits_for(uint64_t maxval) {     // number of bits needed to represent values in [0, maxval]
+    int b = 1;
+    while (b < 63 && (maxval >> b) != 0) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode, int nvar,
+                                int32_t *d_indptr, int32_t *d_indices, int32_t *d_data_local, int32_t *d_data_global,
+                                int32_t *d_seg_ptr, int32_t *d_gather_src, int32_t *d_diag_pos, int64_t *h_nnz,
+                                void *stream) {
+    if (!d_elements || !d_indptr || !d_indices || !d_data_local || !d_data_global || !d_seg_ptr || !d_gather_src ||
+        !d_diag_pos || !h_nnz)
+        return KB_EINVAL;
+    if (nelem < 0 || nnode < 1 || nvar < 1 || (npe != 2 && npe != 4)) return KB_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ndof = (int64_t)npe * nvar, cap = ndof * ndof, nent = nelem * cap, nrows = nnode * nvar;
+    if (nent >= INT32_MAX || nrows >= INT32_MAX) return KB_ETOOBIG;
+    const int cbits = bits_for((uint64_t)(nrows - 1)), rbits = cbits;
+    const int keybits = cbits + rbits;
+
+    k_fill_i32<<<kb_grid(nrows, 256, 8), 256, 0, s>>>(d_diag_pos, nrows, -1);
+    KB_LAUNCH_CHECK();
+    if (nent == 0) {
+        k_fill_i32<<<kb_grid(nrows + 1, 256, 8), 256, 0, s>>>(d_indptr, nrows + 1, 0);
+        KB_LAUNCH_CHECK();
+        k_fill_i32<<<1, 32, 0, s>>>(d_seg_ptr, 1, 0);
+        KB_LAUNCH_CHECK();
+        KB_CUDA(cudaStreamSynchronize(s));
+        *h_nnz = 0;
+        return 0;
+    }
+
+    // scratch: double-buffered keys/payload, per-tile histograms, scan spine
+    const int64_t ntiles = kb_cdiv(nent, RS_TILE);
+    const int64_t nhist = 256 * ntiles;
+    const int64_t scan_ws = kbscan::workspace_ints(nent > nhist ? nent : nhist);
+    uint64_t *keys[2];
+    uint32_t *vals[2];
+    int *hist, *scanws;
+    KB_CUDA(cudaMallocAsync((void **)&keys[0], sizeof(uint64_t) * nent, s));
+    KB_CUDA(cudaMallocAsync((void **)&keys[1], sizeof(uint64_t) * nent, s));
+    KB_CUDA(cudaMallocAsync((void **)&vals[0], sizeof(uint32_t) * nent, s));
+    KB_CUDA(cudaMallocAsync((void **)&vals[1], sizeof(uint32_t) * nent, s));
+    KB_CUDA(cudaMallocAsync((void **)&hist, sizeof(int) * nhist, s));
+    KB_CUDA(cudaMallocAsync((void **)&scanws, sizeof(int) * scan_ws, s));
+
+    const int g = kb_grid(nent, 256, 8);
+    if (npe == 4) k_make_keys<4><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, keys[0], vals[0], d_data_local);
+    else k_make_keys<2><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, keys[0], vals[0], d_data_local);
+    KB_LAUNCH_CHECK();
+
+    int cur = 0;
+    for (int shift = 0; shift < keybits; shift += 8) {
+        k_rs_hist<<<(unsigned)ntiles, RS_THREADS, 0, s>>>(keys[cur], nent, shift, ntiles, hist);
+        KB_LAUNCH_CHECK();
+        int rc = kbscan::exclusive_scan(HistIn{hist}, HistOut{hist}, nhist, scanws, s);
+        if (rc) return rc;
+        k_rs_scatter<<<(unsigned)ntiles, RS_THREADS, 0, s>>>(keys[cur], vals[cur], nent, shift, ntiles, hist,
+                                                             keys[cur ^ 1], vals[cur ^ 1]);
+        KB_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+
+    HeadOut out{keys[cur], vals[cur], d_data_local, cbits, (int)cap,
+                d_indptr, d_indices, d_data_global, d_seg_ptr, d_gather_src, d_diag_pos};
+    int rc = kbscan::exclusive_scan(HeadIn{keys[cur]}, out, nent, scanws, s);
+    if (rc) return rc;
+    const int64_t nt = kbscan::num_tiles(nent);
+    k_pattern_tail<<<1, 256, 0, s>>>(keys[cur], nent, cbits, nrows, scanws + nt, d_indptr, d_seg_ptr);
+    KB_LAUNCH_CHECK();
+    int nnz32 = 0;
+    KB_CUDA(cudaMemcpyAsync(&nnz32, scanws + nt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KB_CUDA(cudaFreeAsync(keys[0], s));
+    KB_CUDA(cudaFreeAsync(keys[1], s));
+    KB_CUDA(cudaFreeAsync(vals[0], s));
+    KB_CUDA(cudaFreeAsync(vals[1], s));
+    KB_CUDA(cudaFreeAsync(hist, s));
+    KB_CUDA(cudaFreeAsync(scanws, s));
+    KB_CUDA(cudaStreamSynchronize(s));
+    *h_nnz = nnz32;
+    return 0;
+}

@@ -1,0 +1,50 @@
+"""Device-buffer plumbing.  PyTorch is used ONLY to own device memory and name the current stream; every computation
+goes through libkiltro_b200.so (kiltro_b200/_lib.py).  Nothing here computes on the CPU on behalf of the hot path."""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.KiltroB200Error("kiltro_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Raw device address of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def empty(shape, dtype=torch.float64):
+    return torch.empty(shape, dtype=dtype, device=require_cuda())
+
+
+def zeros(shape, dtype=torch.float64):
+    return torch.zeros(shape, dtype=dtype, device=require_cuda())
+
+
+def to_device(a, dtype):
+    """NumPy array / torch tensor -> contiguous device tensor of `dtype` (host->device copy if needed)."""
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a).to(device=dev, dtype=dtype, non_blocking=False).contiguous()
+
+
+def to_numpy(a):
+    """Device tensor (or anything array-like) -> NumPy array on the host."""
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    if hasattr(a, "to_numpy"):
+        return a.to_numpy()
+    return np.asarray(a)

@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python API) against the CPU oracle and
+the reference-generated golden fixtures.  Integer/index outputs must be bit-exact; matrix values <= 1e-12 relative;
+solutions <= 1e-8 relative L2 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import Golden, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+PAT = Golden("pattern")
+ASM = Golden("asm")
+STE = Golden("steady")
+
+VAL_TOL = 1e-12
+SOL_TOL = 1e-8
+
+
+def _K():
+    import kiltro_b200 as K
+    return K
+
+
+def make_mesh(points, elements):
+    K = _K()
+    m = K.Mesh(element_type="quad" if elements.shape[1] == 4 else "line")
+    m.points = points
+    m.elements = elements
+    return m
+
+
+def formulation_for(name, mesh, velocity):
+    K = _K()
+    if name.endswith("_pg"):
+        return K.TemperaturePG(mesh, velocity=velocity)
+    tail = name.split("_")[-1]
+    if tail in ("cons", "consistent"):
+        return K.HeatAdvectionDiffusion(mesh, velocity=velocity)
+    return K.Temperature(mesh, velocity=velocity)
+
+
+def material_for(vec, ndim):
+    K = _K()
+    k, rho, cv, area, q = [float(v) for v in vec]
+    return K.FourierConduction(ndim, k=k, area=area, density=rho, heat_capacity_v=cv, q=q)
+
+
+# ------------------------------------------------------------------------------------------------- K8 mesh
+@pytest.mark.parametrize("args", [((0.0, 0.0), (1.0, 1.0), 2, 2), ((0, 0), (0.5, 0.01), 5, 3), ((-1.5, 0.25), (3.7, 9.1), 37, 23),
+                                  ((0, 0), (1, 1), 1, 1), ((0.0, 0.0), (1.0, 1.0), 300, 7)])
+def test_mesh_rectangle_bit_exact(args):
+    from oracle import kiltro_oracle as O
+    ll, ur, nx, ny = args
+    m = _K().Mesh(element_type="quad"); m.Rectangle(lower_left_point=ll, upper_right_point=ur, nx=nx, ny=ny)
+    pts, el = O.mesh_rectangle(ll, ur, nx, ny)
+    assert m.nnodes == pts.shape[0] and m.nelem == el.shape[0] and m.ndim == 2
+    assert m.elements.dtype == np.int64 and np.array_equal(m.elements, el)
+    assert np.array_equal(m.points, pts)
+
+
+@pytest.mark.parametrize("args", [(0.0, 0.5, 5), (-1.0, 2.0, 17), (0.0, 1.0, 1), (3.0, 3.5, 1000)])
+def test_mesh_line_bit_exact(args):
+    from oracle import kiltro_oracle as O
+    m = _K().Mesh(element_type="line"); m.Line(*args)
+    pts, el = O.mesh_line(*args)
+    assert np.array_equal(m.points, pts) and np.array_equal(m.elements, el) and m.ndim == 1
+
+
+# ------------------------------------------------------------------------------------------------- K2 pattern
+@pytest.mark.parametrize("name", [c for c in PAT.cases() if "nvar2" not in c])
+def test_pattern_golden(name):
+    c = PAT.case(name)
+    el = c["elements"]
+    m = make_mesh(np.zeros((int(c["nnodes"]), 2 if el.shape[1] == 4 else 1)), el)
+    ind, ptr, dl, dg = _K().ComputeSparsityPattern(m, 1)
+    assert ind.dtype == np.int32 and ptr.dtype == np.int32 and dl.dtype == np.int32 and dg.dtype == np.int32
+    assert np.array_equal(ptr, c["indptr"]) and np.array_equal(ind, c["indices"])
+    assert np.array_equal(dl, c["data_local"]) and np.array_equal(dg, c["data_global"])
+
+
+def test_pattern_nvar2_golden():
+    c = PAT.case("rect2x2_nvar2")
+    m = make_mesh(np.zeros((9, 2)), PAT.case("rect2x2")["elements"])
+    ind, ptr, dl, dg = _K().ComputeSparsityPattern(m, 2)
+    assert np.array_equal(ptr, c["indptr"]) and np.array_equal(ind, c["indices"])
+    assert np.array_equal(dl, c["data_local"]) and np.array_equal(dg, c["data_global"])
+
+
+@pytest.mark.parametrize("nx,ny,scramble", [(40, 31, False), (64, 64, True), (257, 129, False)])
+def test_pattern_vs_oracle_c(nx, ny, scramble):
+    from oracle import kiltro_oracle as O, native as ON
+    pts, el = O.mesh_rectangle((0, 0), (1, 1), nx, ny)
+    if scramble:
+        rng = np.random.default_rng(3)
+        el = el[rng.permutation(el.shape[0])]
+        for e in range(0, el.shape[0], 3):
+            el[e] = np.roll(el[e], e % 4)
+    m = make_mesh(pts, el)
+    got = _K().ComputeSparsityPattern(m, 1)
+    want = ON.c_sparsity_pattern(el, pts.shape[0], 1)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert got[0].shape[0] == (3 * (nx + 1) - 2) * (3 * (ny + 1) - 2)
+
+
+def test_pattern_line_vs_oracle():
+    from oracle import kiltro_oracle as O, native as ON
+    pts, el = O.mesh_line(0, 1, 5000)
+    got = _K().ComputeSparsityPattern(make_mesh(pts, el), 1)
+    want = ON.c_sparsity_pattern(el, pts.shape[0], 1)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert got[0].shape[0] == 3 * 5001 - 2
+
+
+# ------------------------------------------------------------------------------------------------- K1 + K3
+@pytest.mark.parametrize("name", ASM.cases())
+def test_element_matrices_and_assembly_golden(name):
+    K = _K()
+    c = ASM.case(name)
+    m = make_mesh(c["points"], c["elements"])
+    form = formulation_for(name, m, c["velocity"])
+    mat = material_for(c["material"], m.ndim)
+    Ke, Fe, Me = form.GetAllElementalMatrices(m, mat, want_mass=True)
+    assert rel_max(K.to_numpy(Ke), c["Ke"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Fe), c["Fe"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Me), c["Me"]) < VAL_TOL
+    transient = "M_data" in c
+    fs = K.FEMSolver(analysis_type="transient" if transient else "steady", verbose=False)
+    Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, mat, K.BoundaryCondition())
+    assert np.array_equal(K.to_numpy(Kc.indices), c["K_indices"]) and np.array_equal(K.to_numpy(Kc.indptr), c["K_indptr"])
+    assert rel_max(K.to_numpy(Kc.data), c["K_data"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Flux).ravel(), c["Flux"]) < VAL_TOL
+    if transient:
+        assert rel_max(K.to_numpy(Mm.data), c["M_data"]) < VAL_TOL
+    # the reference's per-element seam
+    I, J, V, f, Im, Jm, Vm = form.GetElementalMatrices(3, form.function_spaces[0], m, mat, fs)
+    assert rel_max(V, c["Ke"][3]) < VAL_TOL and rel_max(f.ravel(), c["Fe"][3]) < VAL_TOL
+
+
+@pytest.mark.parametrize("mode,pg", [("reference", False), ("reference", True), ("consistent", False), ("consistent", True)])
+def test_assembly_vs_oracle_medium(mode, pg):
+    from oracle import kiltro_oracle as O
+    K = _K()
+    rng = np.random.default_rng(11)
+    nx, ny = 61, 47
+    pts, el = O.mesh_rectangle((0, 0), (2.0, 1.0), nx, ny)
+    hx, hy = 2.0 / nx, 1.0 / ny
+    inner = (pts[:, 0] > 0) & (pts[:, 0] < 2.0) & (pts[:, 1] > 0) & (pts[:, 1] < 1.0)
+    pts[inner] += 0.2 * np.array([hx, hy]) * rng.uniform(-1, 1, (inner.sum(), 2))
+    vel = np.array([3.0, -1.0]) + rng.standard_normal(pts.shape)
+    matv = (1.3, 0.9, 1.7, 1.1, 2.5)
+    A = O.assemble(pts, el, vel, matv, mode, pg, True)
+    m = make_mesh(pts, el)
+    cls = {("reference", False): K.Temperature, ("reference", True): K.TemperaturePG,
+           ("consistent", False): K.HeatAdvectionDiffusion, ("consistent", True): K.HeatAdvectionDiffusionPG}[(mode, pg)]
+    form = cls(m, velocity=vel)
+    fs = K.FEMSolver(analysis_type="transient", verbose=False)
+    Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
+    assert np.array_equal(K.to_numpy(Kc.indices), A["indices"]) and np.array_equal(K.to_numpy(Kc.indptr), A["indptr"])
+    assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Flux).ravel(), A["Flux"]) < VAL_TOL
+    # determinism: a second assembly is bitwise identical
+    K2 = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())[0]
+    assert torch.equal(K2.data, Kc.data)
+
+
+# ------------------------------------------------------------------------------------------------- K4 + K6 (steady)
+@pytest.mark.parametrize("name", STE.cases())
+def test_steady_golden(name):
+    K = _K()
+    c = STE.case(name)
+    m = make_mesh(c["points"], c["elements"])
+    form = formulation_for(name, m, c["velocity"])
+    mat = material_for(c["material"], m.ndim)
+    bc = K.BoundaryCondition()
+    bc.SetDirichletCriteria(lambda: c["dirichlet_flags"].copy())
+    if "neumann_flags" in c:
+        bc.SetNeumannCriteria(lambda: c["neumann_flags"].copy())
+    fs = K.FEMSolver(analysis_type="steady", verbose=False)
+    solver = K.LinearSolver(tol=1e-13, check_every=10)
+    sol = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=solver)
+    assert np.array_equal(bc.columns_in, c["columns_in"]) and np.array_equal(bc.columns_out, c["columns_out"])
+    assert bc.columns_out.dtype == np.int64
+    # seam: reduced system
+    Kc = K.Assemble(fs, form.function_spaces, form, m, mat, bc)[0]
+    Res = -bc.ComputeNeumannFluxes(m, mat)
+    K_b, F_b, F = bc.ApplyDirichletGetReducedMatrices(Kc, Res, bc.applied_dirichlet)
+    assert np.array_equal(K.to_numpy(K_b.indices), c["Kb_indices"]) and np.array_equal(K.to_numpy(K_b.indptr), c["Kb_indptr"])
+    assert rel_max(K.to_numpy(K_b.data), c["Kb_data"]) < VAL_TOL
+    assert rel_max(K.to_numpy(F_b), c["F_b"]) < 1e-11
+    assert sol.sol.shape == c["sol"].shape
+    assert solver.info["status"] == 0, solver.info
+    assert rel_l2(sol.sol, c["sol"]) < SOL_TOL, solver.info
+
+
+def test_spmv_vs_scipy():
+    from oracle import kiltro_oracle as O
+    K = _K()
+    rng = np.random.default_rng(5)
+    pts, el = O.mesh_rectangle((0, 0), (1, 1), 150, 97)
+    vel = rng.standard_normal(pts.shape)
+    m = make_mesh(pts, el)
+    form = K.HeatAdvectionDiffusion(m, velocity=vel)
+    fs = K.FEMSolver(verbose=False)
+    Kc = K.Assemble(fs, form.function_spaces, form, m, material_for((1, 1, 1, 1, 0), 2), K.BoundaryCondition())[0]
+    x = rng.standard_normal(pts.shape[0])
+    y = K.to_numpy(Kc.dot(x))
+    assert rel_max(y, Kc.tocsr() @ x) < 1e-13
+
+
+@pytest.mark.parametrize("n,mode", [(127, "consistent"), (255, "diffusion"), (200, "reference_pg")])
+def test_steady_vs_oracle_spsolve(n, mode):
+    """Synthetic structured case of BASELINE config 4 at oracle-sized n: Dirichlet x=0 -> 100, x=1 -> 500."""
+    from oracle import kiltro_oracle as O
+    K = _K()
+    pts, el = O.mesh_rectangle((0, 0), (1, 1), n, n)
+    h = 1.0 / n
+    rng = np.random.default_rng(0)
+    U = 0.45 * 2.0 / h                                         # cell Peclet 0.45
+    vel = np.zeros(pts.shape); vel[:, 0] = U; vel += 0.1 * U * rng.standard_normal(pts.shape)
+    d = np.full((pts.shape[0], 1), np.nan); d[pts[:, 0] == 0.0] = 100.0; d[pts[:, 0] == 1.0] = 500.0
+    matv = (1.0, 1.0, 1.0, 1.0, 0.0)
+    m = make_mesh(pts, el)
+    if mode == "consistent":
+        form = K.HeatAdvectionDiffusion(m, velocity=vel); ref = O.steady_solve(pts, el, vel, matv, d, None, "consistent", False)
+    elif mode == "diffusion":
+        form = K.HeatDiffusion(m); ref = O.steady_solve(pts, el, None, matv, d, None, "reference", False)
+    else:
+        form = K.TemperaturePG(m, velocity=vel * 1e-3); ref = O.steady_solve(pts, el, vel * 1e-3, matv, d, None, "reference", True)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d.copy())
+    solver = K.LinearSolver(tol=1e-13, maxiter=20000)
+    sol = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=material_for(matv, 2), boundary_condition=bc,
+                                           solver=solver)
+    assert solver.info["status"] == 0, solver.info
+    assert rel_l2(sol.sol.ravel(), ref) < SOL_TOL, solver.info
+
+
+def test_closed_form_galerkin_advection():
+    """1D-like 2D problem: consistent Galerkin advection has the discrete solution T_i = T_0 + dT (r^i-1)/(r^n-1),
+    r = (1+Pe)/(1-Pe)."""
+    K = _K()
+    nx, ny = 64, 8
+    m = K.Mesh(element_type="quad"); m.Rectangle((0, 0), (1.0, 0.125), nx, ny)
+    h = 1.0 / nx; Pe = 0.45
+    vel = np.zeros((m.nnodes, 2)); vel[:, 0] = Pe * 2.0 / h
+    pts = m.points
+    d = np.full((m.nnodes, 1), np.nan); d[pts[:, 0] == 0.0] = 100.0; d[pts[:, 0] == 1.0] = 500.0
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d)
+    sol = K.FEMSolver(verbose=False).Solve(formulation=K.HeatAdvectionDiffusion(m, velocity=vel), mesh=m,
+                                           material=K.FourierConduction(2, k=1.0, area=1.0, density=1.0, c_v=1.0),
+                                           boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    r = (1 + Pe) / (1 - Pe)
+    exact = 100.0 + 400.0 * (r ** np.arange(nx + 1) - 1) / (r ** nx - 1)
+    got = sol.sol.reshape(ny + 1, nx + 1)
+    assert np.abs(got - exact[None, :]).max() / 500.0 < 1e-8
