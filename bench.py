@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (BASELINE.json: assembly+solve DOF/s, 2D conv-diff at 16M DOF).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over the synthetic workload S16 (BASELINE configs[3]):
+numeric assembly (K1+K3) + Dirichlet/Neumann (K4) + Jacobi-BiCGSTAB solve (K5+K6) + solution scatter, i.e. exactly
+FEMSolver.Solve() with the sparsity pattern cached on the solver (the reference caches it the same way and times it
+separately: FEMSolver.py:313-325).  `value` is measured with every input already resident in HBM; `e2e` runs the same
+step from pinned HOST buffers (reference array formats: float64 points/velocity/flags, int64 connectivity) with the
+host->device copies and the device->host read of the solution inside the timed region.
+
+--impl reference times the CPU oracle port of the reference's algorithm (oracle/kiltro_oracle.py: batched NumPy element
+matrices + scatter-add + scipy spsolve; the reference itself is pure Python/SciPy and cannot travel to the GPU box) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "assembly+solve DOF/s, 2D conv-diff at 16M DOF"
+UNIT = "DOF/s"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_problem(K, torch, nps, seed=0, peclet=0.45):
+    """S16-style synthetic case, generated on device: unit square, nps x nps nodes, k=rho=c_v=area=1, q=0, Dirichlet
+    x=0 -> 100, x=1 -> 500, nodal velocity U(1,0) + 0.1 U N(0,1) with cell Peclet U h / 2k = 0.45."""
+    mesh = K.Mesh(element_type="quad")
+    mesh.Rectangle(lower_left_point=(0.0, 0.0), upper_right_point=(1.0, 1.0), nx=nps - 1, ny=nps - 1)
+    nn = mesh.nnodes
+    h = 1.0 / (nps - 1)
+    U = peclet * 2.0 / h
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    vel = torch.zeros((nn, 2), dtype=torch.float64, device="cuda")
+    vel[:, 0] = U
+    vel += 0.1 * U * torch.randn((nn, 2), dtype=torch.float64, device="cuda", generator=g)
+    flags = torch.full((nn, 1), float("nan"), dtype=torch.float64, device="cuda")
+    left = torch.arange(nps, device="cuda") * nps
+    flags[left, 0] = 100.0
+    flags[left + nps - 1, 0] = 500.0
+    material = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+    return mesh, vel, flags, material
+
+
+def algorithmic_bytes_spmv(nrows, nnz):
+    return 12 * nnz + 20 * nrows
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_run(nps, steps, warmup):
+    """The reference's algorithm on the host (oracle port), same synthetic workload at nps x nps nodes."""
+    import numpy as np
+    from oracle import kiltro_oracle as O
+    pts, el = O.mesh_rectangle((0.0, 0.0), (1.0, 1.0), nps - 1, nps - 1)
+    h = 1.0 / (nps - 1)
+    U = 0.45 * 2.0 / h
+    rng = np.random.default_rng(0)
+    vel = np.zeros(pts.shape); vel[:, 0] = U; vel += 0.1 * U * rng.standard_normal(pts.shape)
+    d = np.full((pts.shape[0], 1), np.nan); d[::nps] = 100.0; d[nps - 1::nps] = 500.0
+    mat = (1.0, 1.0, 1.0, 1.0, 0.0)
+    nn = pts.shape[0]
+    ind, ptr = O.sparsity_pattern_fast(el, nn)
+    dl, dg = O.data_indices_fast(el, ind, ptr)                  # pattern cached, like the GPU arm
+
+    def step():
+        A = O.assemble(pts, el, vel, mat, "consistent", False, False, (ind, ptr, dl, dg))
+        cin, cout, td = O.dirichlet_split(d)
+        kb = O.apply_dirichlet_reduce(ind, ptr, A["K"], np.zeros(nn), cin, cout, td)
+        sol = O.linear_solve(kb[0], kb[1], kb[2], kb[3])
+        return O.total_component_sol(sol, cin, cout, td, nn)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return nn, dt / steps
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    nps = args.cpu_nodes_per_side
+    steps = max(1, min(args.steps, 3)); warmup = min(args.warmup, 1)
+    nn, sec = cpu_oracle_run(nps, steps, warmup)
+    val = nn / sec
+    sample = "%dx%d nodes (%d DOF) of the same synthetic conv-diff case; %d timed step(s); oracle port: batched NumPy " \
+             "element matrices + np.add.at + scipy spsolve, pattern cached" % (nps, nps, nn, steps)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "S16-style steady 2D conv-diff (consistent Galerkin, cell Pe 0.45), bounded CPU sample",
+                       "nodes_per_side": nps, "ndof": nn},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nodes-per-side", type=int, default=4000)
+    ap.add_argument("--rtol", type=float, default=1.0e-10)
+    ap.add_argument("--check-every", type=int, default=100)
+    ap.add_argument("--maxiter", type=int, default=None, help="cap Krylov iterations (profiling runs only)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-nodes-per-side", type=int, default=384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import kiltro_b200 as K
+    from kiltro_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kiltro_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nps = args.nodes_per_side
+    mesh, vel, flags, material = make_problem(K, torch, nps, seed=rank)
+    nn = mesh.nnodes
+    form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    fs = K.FEMSolver(analysis_type="steady", verbose=False)
+    solver = K.LinearSolver(linear_solver="iterative", linear_solver_type="bicgstab", tol=args.rtol,
+                            check_every=args.check_every, maxiter=args.maxiter)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    sp = fs.ComputeSparsityFEM(mesh, form)                       # symbolic phase: once per mesh, reported separately
+    torch.cuda.synchronize(); t_symbolic = time.perf_counter() - t0
+
+    def step():
+        return fs.Solve(formulation=form, mesh=mesh, material=material, boundary_condition=bc, solver=solver)
+
+    for _ in range(args.warmup):
+        out = step()
+    iters = solver.info["iterations"]
+    # ---- timed region: inputs resident in HBM
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.check(lib.kb_profile_spmv_begin(8))
+    barrier()
+    launches0 = lib.kb_launch_count()
+    e0.record()
+    phase = {"assemble_ms": 0.0, "bc_ms": 0.0, "solve_ms": 0.0}
+    for _ in range(args.steps):
+        out = step()
+        for k in phase:
+            phase[k] += fs.timings[k]
+    e1.record()
+    barrier()
+    launches = lib.kb_launch_count() - launches0
+    ns, tot = _lib.I64(0), _lib.F64(0.0)
+    lib.kb_profile_spmv_end(ns, tot)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * nn * args.steps / (ms * 1e-3)
+    info = dict(solver.info)
+
+    # ---- roofline of the dominant kernel (k_spmv inside the BiCGSTAB loop), timed live with CUDA events
+    peaks, peak_src = None, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak = float(peaks["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    nfree = bc.n_free
+    nnz_b = None
+    roof = None
+    if ns.value > 0:
+        # the solver iterates on the reduced system K_b; its nnz is known from the last BC pass
+        nnz_b = int(fs.last_reduced_nnz) if hasattr(fs, "last_reduced_nnz") else sp.nnz
+        spmv_ms = tot.value / ns.value
+        achieved = algorithmic_bytes_spmv(nfree, nnz_b) / (spmv_ms * 1e-3) * 1e-9
+        roof = {"bound": "hbm", "kernel": "k_spmv (CSR-stream SpMV + fused dots, inside BiCGSTAB)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": spmv_ms, "launches_timed": int(ns.value),
+                "algorithmic_bytes_per_launch": algorithmic_bytes_spmv(nfree, nnz_b)}
+
+    # ---- e2e: same step from pinned host buffers in the reference's array formats
+    e2e = None
+    if args.e2e_steps > 0:
+        h_pts = mesh._points_d.cpu().pin_memory()
+        h_el = mesh._elements_d.to(torch.int64).cpu().pin_memory()
+        h_vel = vel.cpu().pin_memory()
+        h_flags = flags.cpu().pin_memory()
+        h_sol = torch.empty((nn, 1, 1), dtype=torch.float64).pin_memory()
+        h2d = h_pts.numel() * 8 + h_el.numel() * 8 + h_vel.numel() * 8 + h_flags.numel() * 8
+        d2h = h_sol.numel() * 8
+
+        def e2e_step():
+            m = K.Mesh(element_type="quad")
+            m.set_arrays(h_pts, h_el)                            # host -> device inside
+            f = K.HeatAdvectionDiffusion(m, velocity=h_vel)
+            b = K.BoundaryCondition(); b.SetDirichletCriteria(lambda: h_flags)
+            o = fs.Solve(formulation=f, mesh=m, material=material, boundary_condition=b, solver=solver)
+            h_sol.copy_(o.sol_device, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return o
+
+        e2e_step()                                               # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        ee1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max(ee0.elapsed_time(ee1), wall * 1e3)
+        t2 = torch.tensor([ems], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nn * args.e2e_steps / (float(t2.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "ms_per_step": float(t2.item()) / args.e2e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cn = args.cpu_nodes_per_side
+        cnn, csec = cpu_oracle_run(cn, 1, 0)
+        cpu = {"value": cnn / csec, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%dx%d nodes (%d DOF) of the same synthetic case, 1 timed step of oracle/kiltro_oracle.py "
+                         "(batched NumPy assembly + scipy spsolve), pattern cached" % (cn, cn, cnn)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "S16: synthetic 2D structured quad mesh %dx%d nodes (%d DOF per GPU), steady "
+                                       "convection-diffusion (consistent Galerkin, cell Pe 0.45 + 10%% noise), "
+                                       "Jacobi-BiCGSTAB rtol %.0e, pattern cached" % (nps, nps, nn, args.rtol),
+                           "ndof_per_gpu": nn, "nnz": sp.nnz, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                           "l2_policy": "inputs (CSR matrix %.2f GB + vectors) far larger than the 126 MB L2" % (sp.nnz * 12e-9),
+                           "rtol": args.rtol},
+                "solver": {"method": info["method"], "iterations": info["iterations"],
+                           "relative_residual": info["relative_residual"], "status": info["status"]},
+                "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+                "t_symbolic_ms": t_symbolic * 1e3,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

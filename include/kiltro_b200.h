@@ -57,6 +57,8 @@ void kb_launch_count_reset(void);
 int kb_mesh_line(double left, double right, int64_t n, double *d_points, int32_t *d_elements, void *stream);
 int kb_mesh_rectangle(double x0, double y0, double x1, double y1, int64_t nx, int64_t ny,
                       double *d_points, int32_t *d_elements, void *stream);
+/* Mesh.elements is int64 in the reference (Mesh.py:20,44); device connectivity is int32 */
+int kb_cast_i64_i32(const int64_t *d_in, int64_t n, int32_t *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K1  batched element matrices              replaces VariationalPrinciple.py:42-69 (GetLocalMass), :117-173
@@ -145,6 +147,11 @@ int kb_total_component_sol(int64_t ndof, const int32_t *d_renum, const double *d
  * d_dot_x / d_dot_out: optional fused dot products: out[0] = <w, y>, out[1] = <y, y> where w = d_dot_w (may be NULL).
  * ------------------------------------------------------------------------------------------------------- */
 int64_t kb_spmv_num_blocks(int64_t nnz);
+/* live timing of the SpMV launches inside kb_cg_solve / kb_bicgstab_solve: between begin and end, one SpMV launch of every
+ * `every`-th iteration is bracketed by CUDA events on the launching stream (bench.py's roofline leg). */
+void kb_spmv_force_simple(int on);   /* development switch: 1 = use the one-shot (non-TMA) SpMV kernel */
+int kb_profile_spmv_begin(int every);
+int kb_profile_spmv_end(int64_t *h_samples, double *h_total_ms);
 int kb_spmv_partition(int64_t nrows, int64_t nnz, const int32_t *d_indptr, int32_t *d_rowblk, void *stream);
 int kb_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
             const int32_t *d_rowblk, const double *d_x, double *d_y, void *stream);

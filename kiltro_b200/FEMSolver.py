@@ -129,6 +129,7 @@ class FEMSolver(object):
             ev[1].record()
             K_b, F_b = boundary_condition.ApplyDirichletGetReducedMatrices(K, Residual, AppliedDirichletInc)[:2]   # :190
             ev[2].record()
+            self.last_reduced_nnz = K_b.nnz
             sol = solver.Solve(K_b, F_b)                                                     # :193
             ev[3].record()
             dphi = boundary_condition.TotalComponentSol(sol, AppliedDirichletInc, 0, K.shape[0], nvar)   # :196

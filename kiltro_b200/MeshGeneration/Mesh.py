@@ -89,6 +89,16 @@ class Mesh(object):
             self.element_type = "quad"
         self.structured_shape = (nx + 1, ny + 1)
 
+    def set_arrays(self, points, elements):
+        """Adopt caller-provided arrays (NumPy, torch host/pinned or torch CUDA) by uploading them once: the device
+        copies become the source of truth (use the `points` / `elements` setters for host arrays you intend to edit)."""
+        pts = D.to_device(points, torch.float64)
+        el = D.to_device(elements, torch.int32)
+        self._set_device(pts, el, int(pts.shape[1]))
+        if self.element_type is None:
+            self.element_type = "quad" if el.shape[1] == 4 else "line"
+        self.structured_shape = None
+
     def _set_device(self, pts, el, ndim):
         self._points_d, self._elements_d = pts, el
         self._points_h = self._elements_h = None

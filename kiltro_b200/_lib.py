@@ -35,6 +35,7 @@ SIGNATURES = {
     "kb_launch_count_reset": (None, []),
     "kb_mesh_line": (I32, [F64, F64, I64, c_vp, c_vp, c_vp]),
     "kb_mesh_rectangle": (I32, [F64, F64, F64, F64, I64, I64, c_vp, c_vp, c_vp]),
+    "kb_cast_i64_i32": (I32, [c_vp, I64, c_vp, c_vp]),
     "kb_element_matrices": (I32, [I32, c_vp, c_vp, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, c_vp, c_vp,
                                   c_vp]),
     "kb_pattern_build": (I32, [c_vp, I64, I32, I64, I32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -46,6 +47,9 @@ SIGNATURES = {
                                         c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
     "kb_total_component_sol": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_spmv_num_blocks": (I64, [I64]),
+    "kb_spmv_force_simple": (None, [I32]),
+    "kb_profile_spmv_begin": (I32, [I32]),
+    "kb_profile_spmv_end": (I32, [ctypes.POINTER(I64), ctypes.POINTER(F64)]),
     "kb_spmv_partition": (I32, [I64, I64, c_vp, c_vp, c_vp]),
     "kb_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_krylov_workspace_bytes": (ctypes.c_size_t, [I64, I64]),

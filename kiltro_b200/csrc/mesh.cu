@@ -60,3 +60,17 @@ extern "C" int kb_mesh_rectangle(double x0, double y0, double x1, double y1, int
     KB_LAUNCH_CHECK();
     return 0;
 }
+
+// connectivity arrives from the reference's API as int64 (Mesh.py:20,44); the kernels use int32
+__global__ void __launch_bounds__(256) k_cast_i64_i32(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int32_t)in[i];
+}
+
+extern "C" int kb_cast_i64_i32(const int64_t *d_in, int64_t n, int32_t *d_out, void *stream) {
+    if (n < 0 || (n > 0 && (!d_in || !d_out))) return KB_EINVAL;
+    if (n == 0) return 0;
+    k_cast_i64_i32<<<kb_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(d_in, n, d_out);
+    KB_LAUNCH_CHECK();
+    return 0;
+}

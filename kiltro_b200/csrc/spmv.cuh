@@ -15,7 +15,7 @@
 namespace kbspmv {
 
 constexpr int THREADS = 256;
-constexpr int NNZ_TARGET = 2048;          // non-zeros per CTA aimed for by the partition
+constexpr int NNZ_TARGET = 2304;          // non-zeros per CTA aimed for by the partition (256 quad-4 rows)
 constexpr int NNZ_SMEM = 3072;            // staging capacity (24 KB): target + longest row that still takes the fast path
 
 static inline int64_t num_blocks(int64_t nnz) { return nnz > 0 ? (nnz + NNZ_TARGET - 1) / NNZ_TARGET : 1; }

@@ -35,10 +35,17 @@ def zeros(shape, dtype=torch.float64):
 def to_device(a, dtype):
     """NumPy array / torch tensor -> contiguous device tensor of `dtype` (host->device copy if needed)."""
     dev = require_cuda()
-    if isinstance(a, torch.Tensor):
+    if not isinstance(a, torch.Tensor):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if a.dtype == dtype or a.is_cuda and not (a.dtype == torch.int64 and dtype == torch.int32):
         return a.to(device=dev, dtype=dtype).contiguous()
-    a = np.ascontiguousarray(a)
-    return torch.from_numpy(a).to(device=dev, dtype=dtype, non_blocking=False).contiguous()
+    if a.dtype == torch.int64 and dtype == torch.int32:
+        # raw upload, then narrow on device with our own kernel (no host-side conversion pass)
+        raw = a.to(device=dev).contiguous()
+        out = torch.empty(raw.shape, dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().kb_cast_i64_i32(raw.data_ptr(), raw.numel(), out.data_ptr(), stream_ptr()))
+        return out
+    return a.to(dtype).to(device=dev).contiguous()
 
 
 def to_numpy(a):
