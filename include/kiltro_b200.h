@@ -98,22 +98,29 @@ int kb_assemble_from_elements(int npe, int64_t nnode, int64_t nnz, const int32_t
                               const double *d_Ke, const double *d_Me, const double *d_Fe,
                               double *d_K, double *d_M, double *d_Flux, void *stream);
 
-/* (b) fused path: element matrices are computed on chip and never written to HBM.  A "tile plan" built once per
- *     mesh (symbolic) assigns to each CTA a set of CSR rows and the elements incident to them.
- *     kb_tile_plan_build sizes/fills the plan; see assemble.cu for the layout.  h_sizes[0..3] receive
- *     {ntiles, total tile elements, total pairs, reserved}.  Pass d_* = NULL to only obtain the sizes. */
+/* (b) fused path: element matrices are computed on chip and never written to HBM.  A "tile plan" built once per mesh
+ *     (symbolic; layout in csrc/tileplan.cuh) assigns to each CTA a set of CSR rows and the elements incident to them.
+ *     kb_tile_plan_sizes -> h_sizes = {ntiles, capacity of d_tile_elems, capacity of d_pair_rec, structured?}.
+ *     nx_nodes/ny_nodes: node grid of a Mesh.Rectangle-numbered mesh (tiling hint; pass 0,0 for arbitrary meshes).
+ *     kb_tile_plan_build -> h_info = {ntiles, n tile elements, n pairs, max elements/tile, max rows/tile,
+ *     max entries/tile, fits (1 = usable by kb_assemble_fused), structured}; synchronises `stream`.
+ *     d_tile_rows (nnode), d_tile_row_ptr / d_tile_elem_ptr (ntiles+1), d_pair_ptr (nnode+1); d_tile_elems (element ids,
+ *     build scratch) and d_tile_conn (npe ints per tile element: tile-local copy of the connectivity, what the kernel
+ *     reads) have capacity h_sizes[1] and npe*h_sizes[1]. */
 int kb_tile_plan_sizes(int64_t nnode, int64_t nelem, int npe, int64_t nx_nodes, int64_t ny_nodes, int64_t *h_sizes);
 int kb_tile_plan_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode,
-                       const int32_t *d_indptr, const int32_t *d_seg_ptr, const int32_t *d_gather_src,
-                       const int32_t *d_diag_pos, int64_t nx_nodes, int64_t ny_nodes,
-                       int32_t *d_tile_rows, int32_t *d_tile_row_ptr, int32_t *d_tile_elems, int32_t *d_tile_elem_ptr,
-                       uint16_t *d_pairs, int32_t *d_pair_ptr, void *stream);
+                       const int32_t *d_indptr, const int32_t *d_indices, const int32_t *d_seg_ptr,
+                       const int32_t *d_gather_src, const int32_t *d_diag_pos, int64_t nx_nodes, int64_t ny_nodes,
+                       int32_t *d_tile_rows, int32_t *d_tile_row_ptr, int32_t *d_tile_elems, int32_t *d_tile_conn,
+                       int32_t *d_tile_elem_ptr, uint32_t *d_pair_rec, int32_t *d_pair_ptr, int64_t *h_info,
+                       void *stream);
+/* d_M may be NULL (steady).  d_velocity may be NULL. */
 int kb_assemble_fused(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem, int64_t nnode,
                       const double *d_velocity, const kb_material *material, int mode, int petrov,
                       const int32_t *d_indptr, const int32_t *d_indices,
                       int64_t ntiles, const int32_t *d_tile_rows, const int32_t *d_tile_row_ptr,
-                      const int32_t *d_tile_elems, const int32_t *d_tile_elem_ptr,
-                      const uint16_t *d_pairs, const int32_t *d_pair_ptr,
+                      const int32_t *d_tile_conn, const int32_t *d_tile_elem_ptr,
+                      const uint32_t *d_pair_rec, const int32_t *d_pair_ptr,
                       double *d_K, double *d_M, double *d_Flux, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -170,7 +170,8 @@ class FEMSolver(object):
                 self.is_sparsity_pattern_computed = True
                 torch.cuda.synchronize()
                 self.timings["pattern_s"] = time() - t_sp
-                _say("Computed sparsity pattern for the mesh. Time elapsed is {} seconds".format(time() - t_sp))
+                if self.verbose:
+                    print("Computed sparsity pattern for the mesh. Time elapsed is {} seconds".format(time() - t_sp))
             else:
                 raise ValueError("recompute_sparsity_pattern=True is not implemented (neither is it upstream: "
                                  "Assembly.py:54)")

@@ -28,8 +28,19 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
     M = D.empty(sp.nnz) if transient else None
     Flux = D.empty((nnode * formulation.nvar, 1))
     method = getattr(fem_solver, "assembly", "auto")
-    if method in ("auto", "fused") and hasattr(lib, "kb_assemble_fused") and getattr(fem_solver, "_fused_ok", False):
-        from .fused import assemble_fused
+    if method not in ("auto", "fused", "two_pass"):
+        raise ValueError("assembly must be 'auto', 'fused' or 'two_pass'")
+    use_fused = False
+    if method != "two_pass" and formulation.nvar == 1:
+        from .fused import assemble_fused, build_tile_plan
+        if sp.tile_plan is None:
+            sp.tile_plan = build_tile_plan(sp, mesh)             # symbolic, cached with the pattern
+        use_fused = sp.tile_plan.fits
+        if method == "fused" and not use_fused:
+            raise _lib.KiltroB200Error("the tile plan of this mesh does not fit the fused assembly kernel: %r"
+                                       % (sp.tile_plan.info,))
+    fem_solver.assembly_used = "fused" if use_fused else "two_pass"
+    if use_fused:
         assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux)
     else:
         Ke, Fe, Me = formulation.GetAllElementalMatrices(mesh, material, want_mass=transient)

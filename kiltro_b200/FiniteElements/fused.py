@@ -1,0 +1,66 @@
+"""Host side of the fused assembly (csrc/assemble_fused.cu): builds/caches the tile plan and launches the kernel."""
+import torch
+
+from .. import _lib, device as D
+
+
+class TilePlan(object):
+    def __init__(self):
+        self.ntiles = 0
+        self.tile_rows = self.tile_row_ptr = self.tile_conn = self.tile_elem_ptr = None
+        self.pair_rec = self.pair_ptr = None
+        self.info = {}
+        self.fits = False
+
+
+def build_tile_plan(sp, mesh):
+    """Symbolic phase, part 2 (once per mesh): tiles of rows + their incident elements + per-(row, element) records."""
+    lib = _lib.load()
+    el = mesh.device_elements()
+    nelem, npe = int(el.shape[0]), int(el.shape[1])
+    nnode = int(mesh.nnodes)
+    plan = TilePlan()
+    if nelem == 0 or sp.nvar != 1:
+        return plan
+    shape = mesh.structured_shape if (mesh.structured_shape is not None and not mesh.host_is_authoritative()) else None
+    nxn, nyn = (shape if shape is not None else (0, 0))
+    sizes = (_lib.I64 * 4)()
+    _lib.check(lib.kb_tile_plan_sizes(nnode, nelem, npe, nxn, nyn, sizes))
+    ntiles = int(sizes[0])
+    tile_rows = D.empty(nnode, torch.int32)
+    tile_row_ptr = D.empty(ntiles + 1, torch.int32)
+    tile_elems = D.empty(int(sizes[1]), torch.int32)
+    tile_conn = D.empty(int(sizes[1]) * npe, torch.int32)
+    tile_elem_ptr = D.empty(ntiles + 1, torch.int32)
+    pair_rec = D.empty(int(sizes[2]), torch.int32)          # uint32 payload, int32 storage
+    pair_ptr = D.empty(nnode + 1, torch.int32)
+    info = (_lib.I64 * 8)()
+    _lib.check(lib.kb_tile_plan_build(D.ptr(el), nelem, npe, nnode, D.ptr(sp.indptr), D.ptr(sp.indices),
+                                      D.ptr(sp.seg_ptr), D.ptr(sp.gather_src), D.ptr(sp.diag_pos), nxn, nyn,
+                                      D.ptr(tile_rows), D.ptr(tile_row_ptr), D.ptr(tile_elems), D.ptr(tile_conn), D.ptr(tile_elem_ptr),
+                                      D.ptr(pair_rec), D.ptr(pair_ptr), info, D.stream_ptr()))
+    plan.ntiles = ntiles
+    plan.tile_rows, plan.tile_row_ptr, plan.tile_elem_ptr, plan.pair_ptr = tile_rows, tile_row_ptr, tile_elem_ptr, pair_ptr
+    plan.tile_conn = tile_conn[:int(info[1]) * npe].clone()
+    plan.pair_rec = pair_rec[:int(info[2])].clone()
+    plan.info = {"ntiles": int(info[0]), "tile_elements": int(info[1]), "pairs": int(info[2]),
+                 "max_elements_per_tile": int(info[3]), "max_rows_per_tile": int(info[4]),
+                 "max_entries_per_tile": int(info[5]), "structured": bool(info[7]),
+                 "rim_factor": float(info[1]) / max(nelem, 1)}
+    plan.fits = bool(info[6])
+    return plan
+
+
+def assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux):
+    lib = _lib.load()
+    plan = sp.tile_plan
+    pts = mesh.device_points()
+    el = mesh.device_elements()
+    vel = formulation.device_velocity()
+    mat = material.as_struct()
+    _lib.check(lib.kb_assemble_fused(formulation.ndim, D.ptr(pts), D.ptr(el), int(el.shape[0]), int(mesh.nnodes),
+                                     D.ptr(vel), mat, int(formulation.mode), int(bool(formulation.petrov)),
+                                     D.ptr(sp.indptr), D.ptr(sp.indices), plan.ntiles, D.ptr(plan.tile_rows),
+                                     D.ptr(plan.tile_row_ptr), D.ptr(plan.tile_conn), D.ptr(plan.tile_elem_ptr),
+                                     D.ptr(plan.pair_rec), D.ptr(plan.pair_ptr), D.ptr(K), D.ptr(M), D.ptr(Flux),
+                                     D.stream_ptr()))

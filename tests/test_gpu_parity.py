@@ -257,3 +257,77 @@ def test_closed_form_galerkin_advection():
     exact = 100.0 + 400.0 * (r ** np.arange(nx + 1) - 1) / (r ** nx - 1)
     got = sol.sol.reshape(ny + 1, nx + 1)
     assert np.abs(got - exact[None, :]).max() / 500.0 < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------- fused assembly (K1+K3)
+@pytest.mark.parametrize("nx,ny,transient,cls", [(70, 53, True, "HeatAdvectionDiffusion"), (45, 31, False, "TemperaturePG"),
+                                                 (15, 15, True, "Temperature"), (16, 14, False, "HeatAdvectionDiffusionPG"),
+                                                 (3, 2, True, "HeatAdvectionDiffusion")])
+def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
+    """Device-generated Rectangle mesh (2-D node-patch tiles), nodes perturbed in place on device: fused == two-pass
+    bitwise, and both match the oracle."""
+    from oracle import kiltro_oracle as O
+    K = _K()
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (2.0, 1.0), nx, ny)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    P = m.device_points()
+    hx, hy = 2.0 / nx, 1.0 / ny
+    inner = (P[:, 0] > 0) & (P[:, 0] < 2.0) & (P[:, 1] > 0) & (P[:, 1] < 1.0)
+    noise = (torch.rand(P.shape, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * torch.tensor([hx, hy], dtype=torch.float64, device="cuda") * 0.2
+    P += noise * inner[:, None]
+    vel = torch.randn(P.shape, dtype=torch.float64, device="cuda", generator=g) * 3.0 + 2.0
+    matv = (1.3, 0.9, 1.7, 1.1, 2.5)
+    form = getattr(K, cls)(m, velocity=vel)
+    at = "transient" if transient else "steady"
+    res = {}
+    for method in ("fused", "two_pass"):
+        fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
+        Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
+        assert fs.assembly_used == method
+        res[method] = (Kc, Flux, Mm)
+        if method == "fused":
+            assert fs.sparsity.tile_plan.info["structured"]
+    # same device function, same accumulation order; the two kernels may contract FMAs differently in the tanh/PG branch
+    assert rel_max(K.to_numpy(res["fused"][0].data), K.to_numpy(res["two_pass"][0].data)) < 1e-14
+    assert torch.equal(res["fused"][1], res["two_pass"][1])
+    if transient:
+        assert torch.equal(res["fused"][2].data, res["two_pass"][2].data)
+    mode = "consistent" if cls.startswith("Heat") else "reference"
+    A = O.assemble(K.to_numpy(P), m.elements, K.to_numpy(vel), matv, mode, cls.endswith("PG"), transient)
+    assert np.array_equal(K.to_numpy(res["fused"][0].indices), A["indices"])
+    assert rel_max(K.to_numpy(res["fused"][0].data), A["K"]) < VAL_TOL
+    assert rel_max(K.to_numpy(res["fused"][1]).ravel(), A["Flux"]) < VAL_TOL
+    if transient:
+        assert rel_max(K.to_numpy(res["fused"][2].data), A["M"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("name", ["quad_cons", "quad_scrambled_pg", "line_pg", "line_cons"])
+def test_fused_assembly_row_chunk_tiles_golden(name):
+    """Host-provided connectivity (row-chunk tiles; scrambled meshes may fall back to the two-pass seam)."""
+    K = _K()
+    c = ASM.case(name)
+    m = make_mesh(c["points"], c["elements"])
+    form = formulation_for(name, m, c["velocity"])
+    mat = material_for(c["material"], m.ndim)
+    fs = K.FEMSolver(analysis_type="transient", verbose=False, assembly="auto")
+    Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, mat, K.BoundaryCondition())
+    assert rel_max(K.to_numpy(Kc.data), c["K_data"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Mm.data), c["M_data"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Flux).ravel(), c["Flux"]) < VAL_TOL
+    fs2 = K.FEMSolver(analysis_type="transient", verbose=False, assembly="two_pass")
+    K2 = K.Assemble(fs2, form.function_spaces, form, m, mat, K.BoundaryCondition())[0]
+    assert rel_max(K.to_numpy(K2.data), K.to_numpy(Kc.data)) < 1e-14
+
+
+def test_fused_assembly_line_mesh_large():
+    from oracle import kiltro_oracle as O
+    K = _K()
+    m = K.Mesh(element_type="line"); m.Line(0.0, 3.0, 5000)
+    vel = np.full((m.nnodes, 1), 7.0)
+    matv = (0.8, 1.1, 1.4, 2.0, -2.0)
+    form = K.TemperaturePG(m, velocity=vel)
+    fs = K.FEMSolver(analysis_type="transient", verbose=False, assembly="fused")
+    Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 1), K.BoundaryCondition())
+    A = O.assemble(m.points, m.elements, vel, matv, "reference", True, True)
+    assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL and rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Flux).ravel(), A["Flux"]) < VAL_TOL
