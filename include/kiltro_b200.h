@@ -179,24 +179,30 @@ int kb_bicgstab_solve(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const
                       void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * K7  transient step                        replaces FEMSolver.TransientSolver, FEMSolver.py:253-297 (+ :138-145)
- * One theta-step on the FULL system with the reference's (M^-1)[in,in] convention:
- *     rhs_i = (K T^n + F)_i for free i, 0 for fixed i ;  solve (M + theta dt Kff) y = rhs ;  T^{n+1}_free = T^n - dt y
- * kb_time_step_rule: dt = factor * min_e rho c_v |X1-X0|^2 / (2k)   (FEMSolver.py:138-144); result in *d_dt (device).
+ * K7  transient loop                        replaces FEMSolver.TransientSolver, FEMSolver.py:253-297 (+ :138-145)
+ * Every step solves, on the FULL system with the reference's (M^-1)[in,in] convention,
+ *     (M + theta dt Kff) y = Kff T^n + Fm ;   T^{n+1} = T^n - dt y at free DOFs, prescribed values at fixed DOFs
+ * (Kff: rows and columns of fixed DOFs zeroed; Fm: F zeroed at fixed DOFs).  theta = 0 is the reference's intended
+ * forward Euler; theta > 0 is new capability.
  * ------------------------------------------------------------------------------------------------------- */
+/* dt = factor * min_e rho c_v |X1-X0|^2 / (2k)   (FEMSolver.py:138-144); result written to *d_dt (device) */
 int kb_time_step_rule(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem,
                       const kb_material *material, double factor, double *d_dt, void *stream);
-/* rhs = mask_free .* (K T + F) */
-int kb_transient_rhs(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
-                     const int32_t *d_rowblk, const int32_t *d_renum, const double *d_F, const double *d_T,
-                     double *d_rhs, void *stream);
-/* A = M + theta*dt*Kff  (Kff: rows and columns of fixed DOFs zeroed) on the shared pattern */
+/* Kff and A = M + theta_dt*Kff on the shared pattern */
 int kb_transient_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
                         const double *d_K, const double *d_M, const int32_t *d_renum, double theta_dt,
-                        double *d_A, void *stream);
-/* T_next = fixed ? td : T - dt*y */
-int kb_transient_update(int64_t ndof, const int32_t *d_renum, const double *d_td, const double *d_T,
-                        const double *d_y, double dt, double *d_Tnext, void *stream);
+                        double *d_Kff, double *d_A, void *stream);
+/* out = in at free DOFs, 0 at fixed DOFs */
+int kb_mask_free(int64_t ndof, const int32_t *d_renum, const double *d_in, double *d_out, void *stream);
+/* The whole time loop on device.  d_T: T^0 in, T^nsteps out.  h_snap_steps: ascending step indices (0 = initial state)
+ * whose state is copied to d_snapshots (nsnap x ndof).  a_symmetric selects CG (1) or BiCGSTAB (0) for A.  h_info:
+ * iterations = total Krylov iterations, residual = worst relative residual over the steps.  Synchronises `stream`. */
+size_t kb_transient_workspace_bytes(int64_t ndof, int64_t nnz);
+int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_Kff,
+                     const double *d_A, int a_symmetric, const double *d_Fm, const int32_t *d_renum,
+                     const double *d_applied, double *d_T, double dt, int nsteps, const int32_t *h_snap_steps, int nsnap,
+                     double *d_snapshots, double rtol, int maxiter, void *d_workspace, size_t workspace_bytes,
+                     kb_solve_info *h_info, void *stream);
 
 #ifdef __cplusplus
 }

@@ -176,10 +176,12 @@ class BoundaryCondition(object):
     def _total(self, sol, applied, fsize, nvar):
         lib = _lib.load()
         T = D.empty(fsize)
-        _lib.check(lib.kb_total_component_sol(fsize, D.ptr(self.renum),
-                                              D.ptr(D.to_device(sol, torch.float64).reshape(-1)) if sol is not None else None,
-                                              D.ptr(self._applied(applied)) if applied is not False else None,
-                                              D.ptr(T), D.stream_ptr()))
+        # keep every buffer referenced by a local until the launch is enqueued (a temporary freed mid-expression could be
+        # handed out again by the caching allocator before the kernel reads it)
+        sol_d = D.to_device(sol, torch.float64).reshape(-1) if sol is not None else None
+        app_d = self._applied(applied) if applied is not False else None
+        _lib.check(lib.kb_total_component_sol(fsize, D.ptr(self.renum), D.ptr(sol_d), D.ptr(app_d), D.ptr(T),
+                                              D.stream_ptr()))
         return T.reshape(fsize // nvar, nvar)
 
     def UpdateFixDoFs(self, AppliedDirichletInc, fsize, nvar):   # :203-214

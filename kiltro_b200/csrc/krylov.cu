@@ -326,7 +326,7 @@ int read_state(const Work &w, HostState *h, cudaStream_t s) {
 template <int METHOD>
 int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                  const double *b, double *x, double rtol, int maxiter, int check_every, void *workspace,
-                 size_t workspace_bytes, kb_solve_info *info, cudaStream_t s) {
+                 size_t workspace_bytes, kb_solve_info *info, cudaStream_t s, bool reuse_setup = false) {
     if (!indptr || !indices || (!vals && nnz > 0) || !b || !x || !workspace || !info || n < 0 || nnz < 0) return KB_EINVAL;
     if (n >= INT32_MAX || nnz >= INT32_MAX) return KB_ETOOBIG;
     if (workspace_bytes < carve(nullptr, nullptr, n, nnz)) return KB_EWORKSPACE;
@@ -341,14 +341,16 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
 
     k_reset_state<<<1, 32, 0, s>>>(w.ticket, w.done, w.iter, w.sc);
     KB_LAUNCH_CHECK();
-    const int64_t nblk = num_blocks(nnz);
-    k_partition<<<(unsigned)kb_cdiv(nblk + 1, 256), 256, 0, s>>>(n, nblk, indptr, w.rowblk);
-    KB_LAUNCH_CHECK();
-    const int g = kb_grid(n, 256, 8);
-    k_diag_scale<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale);
-    KB_LAUNCH_CHECK();
-    k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat);
-    KB_LAUNCH_CHECK();
+    if (!reuse_setup) {      // row partition + Jacobi-scaled copy of the values (kept in the workspace between calls)
+        const int64_t nblk = num_blocks(nnz);
+        k_partition<<<(unsigned)kb_cdiv(nblk + 1, 256), 256, 0, s>>>(n, nblk, indptr, w.rowblk);
+        KB_LAUNCH_CHECK();
+        const int g = kb_grid(n, 256, 8);
+        k_diag_scale<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale);
+        KB_LAUNCH_CHECK();
+        k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat);
+        KB_LAUNCH_CHECK();
+    }
     int rc;
     // xh = x / scale ; bh = scaled rhs
     if ((rc = launch_vec<0>(n, BodyScaleIn{x, b, w.scale, xh, bh, METHOD == 0 ? 1 : 0}, NoFin{}, w, nullptr, s))) return rc;
@@ -420,6 +422,98 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------ K7 transient loop
+namespace {
+struct BodyRhs {            // rhs = (Kff T) + Fm   (both already zero at fixed DOFs)
+    const double *kt, *fm; double *rhs;
+    __device__ void operator()(int64_t i, double &, double &) const { rhs[i] = kt[i] + fm[i]; }
+};
+struct BodyStep {           // T = fixed ? td : T - dt*y
+    const int32_t *renum; const double *td, *y; double *T; double dt;
+    __device__ void operator()(int64_t i, double &, double &) const {
+        const int r = renum[i];
+        T[i] = r >= 0 ? T[i] - dt * y[i] : td[-1 - r];
+    }
+};
+}  // namespace
+
+extern "C" size_t kb_transient_workspace_bytes(int64_t ndof, int64_t nnz) {
+    return carve(nullptr, nullptr, ndof, nnz) + 4 * align256(sizeof(double) * (size_t)(ndof + 1)) +
+           align256(sizeof(int32_t) * (size_t)(num_blocks(nnz) + 1)) + align256(2 * sizeof(double) * 4096);
+}
+
+extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                                const double *d_Kff, const double *d_A, int a_symmetric, const double *d_Fm,
+                                const int32_t *d_renum, const double *d_applied, double *d_T, double dt, int nsteps,
+                                const int32_t *h_snap_steps, int nsnap, double *d_snapshots, double rtol, int maxiter,
+                                void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream) {
+    if (!d_indptr || !d_indices || !d_Kff || !d_A || !d_Fm || !d_renum || !d_applied || !d_T || !d_workspace || !h_info ||
+        ndof < 1 || nsteps < 0 || nsnap < 0 || (nsnap > 0 && (!h_snap_steps || !d_snapshots)))
+        return KB_EINVAL;
+    if (workspace_bytes < kb_transient_workspace_bytes(ndof, nnz)) return KB_EWORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t launches0 = g_kb_launches;
+    char *base = (char *)d_workspace;
+    const size_t kws = carve(nullptr, nullptr, ndof, nnz);
+    size_t off = kws;
+    const size_t vb = align256(sizeof(double) * (size_t)(ndof + 1));
+    double *kt = (double *)(base + off); off += vb;
+    double *rhs = (double *)(base + off); off += vb;
+    double *y = (double *)(base + off); off += vb;
+    off += vb;
+    int32_t *rowblk = (int32_t *)(base + off); off += align256(sizeof(int32_t) * (size_t)(num_blocks(nnz) + 1));
+    double *partials = (double *)(base + off);
+    Work wv;                               // only partials/ticket are used by launch_vec<0> (no dots): give valid pointers
+    carve(&wv, base, ndof, nnz);
+    const int64_t nblk = num_blocks(nnz);
+    k_partition<<<(unsigned)kb_cdiv(nblk + 1, 256), 256, 0, s>>>(ndof, nblk, d_indptr, rowblk);
+    KB_LAUNCH_CHECK();
+    KB_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)ndof, s));
+    int snap = 0, rc;
+    int64_t total_iters = 0;
+    double worst = 0.0;
+    int status = 0;
+    // snapshot of the initial state (step index 0)
+    while (snap < nsnap && h_snap_steps[snap] == 0) {
+        KB_CUDA(cudaMemcpyAsync(d_snapshots + (size_t)snap * ndof, d_T, sizeof(double) * (size_t)ndof,
+                                cudaMemcpyDeviceToDevice, s));
+        ++snap;
+    }
+    for (int step = 1; step <= nsteps; ++step) {
+        // rhs = Kff T^n + Fm
+        if ((rc = launch_spmv_raw<0, NoFinal>(ndof, nnz, d_indptr, d_indices, d_Kff, rowblk, partials, nullptr, d_T, kt,
+                                              nullptr, nullptr, NoFinal{}, s))) return rc;
+        if ((rc = launch_vec<0>(ndof, BodyRhs{kt, d_Fm, rhs}, NoFin{}, wv, nullptr, s))) return rc;
+        // A y = rhs  (A = M + theta dt Kff; y of the previous step is the initial guess)
+        kb_solve_info info;
+        if (a_symmetric)
+            rc = krylov_solve<0>(ndof, nnz, d_indptr, d_indices, d_A, rhs, y, rtol, maxiter, 8, d_workspace, kws, &info, s,
+                                 step > 1);
+        else
+            rc = krylov_solve<1>(ndof, nnz, d_indptr, d_indices, d_A, rhs, y, rtol, maxiter, 8, d_workspace, kws, &info, s,
+                                 step > 1);
+        if (rc) return rc;
+        total_iters += info.iterations;
+        if (info.status != 0) status = info.status;
+        if (info.rhs_norm > 0 && info.residual / info.rhs_norm > worst) worst = info.residual / info.rhs_norm;
+        // T^{n+1}
+        if ((rc = launch_vec<0>(ndof, BodyStep{d_renum, d_applied, y, d_T, dt}, NoFin{}, wv, nullptr, s))) return rc;
+        while (snap < nsnap && h_snap_steps[snap] == step) {
+            KB_CUDA(cudaMemcpyAsync(d_snapshots + (size_t)snap * ndof, d_T, sizeof(double) * (size_t)ndof,
+                                    cudaMemcpyDeviceToDevice, s));
+            ++snap;
+        }
+    }
+    KB_CUDA(cudaStreamSynchronize(s));
+    memset(h_info, 0, sizeof(*h_info));
+    h_info->iterations = (int32_t)(total_iters > INT32_MAX ? INT32_MAX : total_iters);
+    h_info->status = status;
+    h_info->residual = worst;           // worst relative residual of the per-step solves
+    h_info->rhs_norm = 1.0;
+    h_info->kernel_launches = g_kb_launches - launches0;
+    return 0;
+}
 
 extern "C" int kb_profile_spmv_begin(int every) {
     if (!g_prof.have_events) {

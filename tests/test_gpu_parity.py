@@ -331,3 +331,79 @@ def test_fused_assembly_line_mesh_large():
     A = O.assemble(m.points, m.elements, vel, matv, "reference", True, True)
     assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL and rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL
     assert rel_max(K.to_numpy(Flux).ravel(), A["Flux"]) < VAL_TOL
+
+
+# ------------------------------------------------------------------------------------------------- K7 transient
+TRA = Golden("transient")
+
+
+def _transient_setup(c, name, theta=0.0, snaps=None, nincr=None):
+    K = _K()
+    m = make_mesh(c["points"], c["elements"])
+    vel = c["velocity"] if np.any(c["velocity"]) else None
+    form = K.HeatAdvectionDiffusion(m, velocity=vel) if name.endswith("consistent") else K.Temperature(m, velocity=vel)
+    mat = material_for(c["material"], m.ndim)
+    bc = K.BoundaryCondition()
+    bc.SetInitialConditions(lambda: c["initial"].copy())
+    bc.SetDirichletCriteria(lambda: c["dirichlet_flags"].copy())
+    if "neumann_flags" in c:
+        bc.SetNeumannCriteria(lambda: c["neumann_flags"].copy())
+    fs = K.FEMSolver(analysis_type="transient", number_of_increments=int(c["nincr"]) if nincr is None else nincr,
+                     theta=theta, time_step=float(c["dt"]), verbose=False)
+    if snaps is not None:
+        fs.snapshot_increments = snaps
+    return K, m, form, mat, bc, fs
+
+
+@pytest.mark.parametrize("name", TRA.cases())
+def test_transient_golden(name):
+    """theta = 0: forward Euler with consistent mass and (M^-1)[in,in] -- the reference's intent (FEMSolver.py:253-297),
+    pinned by fixtures built on the reference's own Assemble and by its shipped figures."""
+    c = TRA.case(name)
+    K, m, form, mat, bc, fs = _transient_setup(c, name, snaps="all")
+    T = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    assert T.shape == c["T_all"].shape
+    assert fs.solver_info["status"] == 0, fs.solver_info
+    assert rel_l2(T, c["T_all"]) < SOL_TOL, fs.solver_info
+    K, m, form, mat, bc, fs = _transient_setup(c, name)
+    S = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    assert S.shape == c["snapshots"].shape and rel_l2(S, c["snapshots"]) < SOL_TOL
+
+
+def test_transient_time_step_rule():
+    c = TRA.case("ex2d_dt010")
+    K, m, form, mat, bc, fs = _transient_setup(c, "ex2d_dt010")
+    fs.time_step = None                                   # FEMSolver.py:138-144 with the upstream factor 0.1
+    fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    assert abs(fs.time_increment - float(c["dt"])) < 1e-12 * float(c["dt"])
+
+
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+def test_transient_theta_method(theta):
+    """theta > 0 (new capability): checked against a dense NumPy statement of the same scheme built on the oracle's
+    assembled matrices."""
+    from oracle import kiltro_oracle as O
+    from scipy.sparse import csr_matrix
+    c = TRA.case("distorted_consistent")
+    nincr, dt = 25, float(c["dt"]) * 6.0                  # beyond the explicit stability limit on purpose
+    K, m, form, mat, bc, fs = _transient_setup(c, "distorted_consistent", theta=theta, snaps="all", nincr=nincr)
+    fs.time_step = dt
+    T = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    A = O.assemble(c["points"], c["elements"], c["velocity"], tuple(c["material"]), "consistent", False, True)
+    nn = c["points"].shape[0]
+    Kd = csr_matrix((A["K"], A["indices"], A["indptr"]), shape=(nn, nn)).toarray()
+    Md = csr_matrix((A["M"], A["indices"], A["indptr"]), shape=(nn, nn)).toarray()
+    cin, cout, td = O.dirichlet_split(c["dirichlet_flags"])
+    Fn = O.neumann_fluxes(c["neumann_flags"], nn)
+    free = np.zeros(nn, bool); free[cin] = True
+    Kff = Kd * free[:, None] * free[None, :]
+    F = np.zeros(nn); F[cin] = Kd[np.ix_(cin, cout)] @ td; F -= Fn; F[~free] = 0.0
+    Tn = c["initial"].ravel().copy(); Tn[cout] += td
+    ref = [Tn.copy()]
+    Amat = Md + theta * dt * Kff
+    for _ in range(nincr - 1):
+        y = np.linalg.solve(Amat, Kff @ Tn + F)
+        Tn = np.where(free, Tn - dt * y, 0.0); Tn[cout] = td
+        ref.append(Tn.copy())
+    ref = np.array(ref).T
+    assert np.isfinite(T).all() and rel_l2(T, ref) < SOL_TOL, fs.solver_info
