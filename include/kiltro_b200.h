@@ -57,6 +57,9 @@ void kb_launch_count_reset(void);
 int kb_mesh_line(double left, double right, int64_t n, double *d_points, int32_t *d_elements, void *stream);
 int kb_mesh_rectangle(double x0, double y0, double x1, double y1, int64_t nx, int64_t ny,
                       double *d_points, int32_t *d_elements, void *stream);
+/* node rows [j_first, j_first+nrows) of the global Rectangle mesh as a local mesh (row-block partition, K9) */
+int kb_mesh_rectangle_strip(double x0, double y0, double x1, double y1, int64_t nx, int64_t ny, int64_t j_first,
+                            int64_t nrows, double *d_points, int32_t *d_elements, void *stream);
 /* Mesh.elements is int64 in the reference (Mesh.py:20,44); device connectivity is int32 */
 int kb_cast_i64_i32(const int64_t *d_in, int64_t n, int32_t *d_out, void *stream);
 
@@ -203,6 +206,37 @@ int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const i
                      const double *d_applied, double *d_T, double dt, int nsteps, const int32_t *h_snap_steps, int nsnap,
                      double *d_snapshots, double rtol, int maxiter, void *d_workspace, size_t workspace_bytes,
                      kb_solve_info *h_info, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K9  building blocks of the row-block partitioned (multi-GPU) solves           (new capability)
+ * The fused kernels of K6 exposed one by one, scalars as DEVICE pointers, local partial dots returned in d_out2 so the
+ * caller can all-reduce them (NCCL) between the dot and its use.  d_scratch: kb_blocks_scratch_bytes(nnz) bytes, zeroed
+ * once by the caller.  Row-range views of a local CSR are expressed by offsetting d_indptr / d_y / vector pointers.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t kb_blocks_scratch_bytes(int64_t nnz);
+int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+                 const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, double *d_out2,
+                 void *d_scratch, void *stream);                          /* y = A x ; out = {<w,y>, <y,y>} */
+int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream); /* {<a,b>,<b,b>} */
+int kb_residual(int64_t n, const double *d_b, const double *d_q, double *d_r, double *d_out2, void *d_scratch,
+                void *stream);                                            /* r = b - q ; out = {<r,r>, <b,b>} */
+int kb_axpy_neg(int64_t n, const double *d_alpha, const double *d_v, double *d_r, void *stream);      /* r -= alpha v */
+int kb_bicgstab_update(int64_t n, const double *d_alpha, const double *d_omega, const double *d_p, const double *d_t,
+                       const double *d_rhat, double *d_x, double *d_r, double *d_out2, void *d_scratch, void *stream);
+int kb_bicgstab_p(int64_t n, const double *d_beta, const double *d_omega, const double *d_r, const double *d_v,
+                  double *d_p, void *stream);                             /* p = r + beta (p - omega v) */
+int kb_cg_update(int64_t n, const double *d_alpha, const double *d_p, const double *d_q, double *d_x, double *d_r,
+                 double *d_out2, void *d_scratch, void *stream);          /* x += alpha p ; r -= alpha q ; out[0] = <r,r> */
+int kb_cg_p(int64_t n, const double *d_beta, const double *d_r, double *d_p, void *stream);           /* p = r + beta p */
+int kb_vec_mul(int64_t n, const double *d_a, const double *d_b, double *d_out, void *stream);         /* out = a .* b */
+int kb_diag_scale(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals, int mode,
+                  double *d_scale, void *stream);                         /* mode 0: 1/diag ; 1: 1/sqrt(diag) */
+int kb_scale_matrix(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals, int mode,
+                    const double *d_scale, double *d_out, void *stream);  /* mode 0: A D ; 1: D A D (D = diag(scale)) */
+/* out = c_k*Kff + c_m*M (M may be NULL) (+ 1 on the diagonal of fixed rows when identity_fixed) */
+int kb_masked_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
+                     const double *d_M, const int32_t *d_renum, double c_k, double c_m, int identity_fixed,
+                     double *d_out, void *stream);
 
 #ifdef __cplusplus
 }

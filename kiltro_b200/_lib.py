@@ -69,6 +69,20 @@ SIGNATURES = {
     "kb_transient_run": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, I32, c_vp, c_vp, c_vp, c_vp, F64, I32,
                                ctypes.POINTER(ctypes.c_int32), I32, c_vp, F64, I32, c_vp, ctypes.c_size_t,
                                ctypes.POINTER(kb_solve_info), c_vp]),
+    "kb_mesh_rectangle_strip": (I32, [F64, F64, F64, F64, I64, I64, I64, I64, c_vp, c_vp, c_vp]),
+    "kb_blocks_scratch_bytes": (ctypes.c_size_t, [I64]),
+    "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_dot2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_residual": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_axpy_neg": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),
+    "kb_bicgstab_update": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_bicgstab_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_cg_update": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_cg_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),
+    "kb_vec_mul": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),
+    "kb_diag_scale": (I32, [I64, c_vp, c_vp, c_vp, I32, c_vp, c_vp]),
+    "kb_scale_matrix": (I32, [I64, c_vp, c_vp, c_vp, I32, c_vp, c_vp, c_vp]),
+    "kb_masked_matrix": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, F64, I32, c_vp, c_vp]),
 }
 
 _LIB = None

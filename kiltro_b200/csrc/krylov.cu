@@ -515,6 +515,153 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ building blocks
+// The same fused kernels as above, exposed one by one with their scalars passed as DEVICE pointers, for solver loops
+// driven from the host side when a collective sits between a dot product and its use (row-block partitioned multi-GPU
+// solve, kiltro_b200/distributed.py): local partial dots come back in d_out2 (2 doubles) and are all-reduced by the caller.
+namespace {
+struct FinStore { double *out; __device__ void operator()(double a, double b) const { out[0] = a; out[1] = b; } };
+struct BodyDot2 { const double *a, *b; __device__ void operator()(int64_t i, double &d0, double &d1) const { const double bi = b[i]; d0 += a[i] * bi; d1 += bi * bi; } };
+struct BodyAxpyP {          // r -= alpha v
+    const double *alpha, *v; double *r;
+    __device__ void operator()(int64_t i, double &, double &) const { r[i] -= alpha[0] * v[i]; }
+};
+struct BodyBiUpdateP {      // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
+    const double *alpha, *omega, *p, *t, *rhat; double *x, *r;
+    __device__ void operator()(int64_t i, double &d0, double &d1) const {
+        const double a = alpha[0], om = omega[0], si = r[i];
+        x[i] += a * p[i] + om * si;
+        const double ri = si - om * t[i];
+        r[i] = ri;
+        d0 += rhat[i] * ri; d1 += ri * ri;
+    }
+};
+struct BodyBiPP {           // p = r + beta (p - omega v)
+    const double *beta, *omega, *r, *v; double *p;
+    __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * (p[i] - omega[0] * v[i]); }
+};
+struct BodyCgUpdateP {      // x += alpha p ; r -= alpha q ; d0 = <r,r>
+    const double *alpha, *p, *q; double *x, *r;
+    __device__ void operator()(int64_t i, double &d0, double &) const {
+        const double a = alpha[0];
+        x[i] += a * p[i];
+        const double ri = r[i] - a * q[i];
+        r[i] = ri;
+        d0 += ri * ri;
+    }
+};
+struct BodyCgPP {           // p = r + beta p
+    const double *beta, *r; double *p;
+    __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * p[i]; }
+};
+struct BodyMulP {           // out = a .* b
+    const double *a, *b; double *out;
+    __device__ void operator()(int64_t i, double &, double &) const { out[i] = a[i] * b[i]; }
+};
+struct BodyResidualP {      // r = b - q ; d0 = <r,r> ; d1 = <b,b>
+    const double *b, *q; double *r;
+    __device__ void operator()(int64_t i, double &d0, double &d1) const {
+        const double bi = b[i], ri = bi - q[i];
+        r[i] = ri; d0 += ri * ri; d1 += bi * bi;
+    }
+};
+
+// scratch for the partial sums of the building blocks: [2*(max grid)] doubles + ticket, carved from a caller buffer
+struct Scratch { double *partials; unsigned int *ticket; };
+Scratch scratch_of(void *d_scratch) {
+    Scratch sc;
+    sc.ticket = (unsigned int *)d_scratch;
+    sc.partials = (double *)((char *)d_scratch + 256);
+    return sc;
+}
+template <int DOTS, class Body, class Final>
+int launch_vec_s(int64_t n, Body body, Final fin, const Scratch &sc, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int grid = kb_grid(n, 256, 8);
+    k_vec<DOTS, Body, Final><<<grid, 256, 0, s>>>(n, body, sc.partials, sc.ticket, nullptr, fin);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace
+
+// bytes of device scratch the building blocks need for a system with nnz non-zeros (zero-initialise it once)
+extern "C" size_t kb_blocks_scratch_bytes(int64_t nnz) {
+    return 256 + sizeof(double) * (size_t)(2 * num_blocks(nnz) + 2 * 8 * (int64_t)kb_num_sms() + 64);
+}
+
+// y = A x over `nrows` rows + local partial dots d_out2 = {<w,y>, <y,y>}
+extern "C" int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                            const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y,
+                            const double *d_w, double *d_out2, void *d_scratch, void *stream) {
+    if (!d_indptr || !d_indices || (!d_vals && nnz > 0) || !d_rowblk || !d_x || !d_y || !d_w || !d_out2 || !d_scratch)
+        return KB_EINVAL;
+    if (nrows <= 0) return 0;
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_spmv_raw<1, FinStore>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
+                                        d_y, d_w, nullptr, FinStore{d_out2}, (cudaStream_t)stream);
+}
+extern "C" int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream) {
+    if (!d_a || !d_b || !d_out2 || !d_scratch) return KB_EINVAL;
+    return launch_vec_s<1>(n, BodyDot2{d_a, d_b}, FinStore{d_out2}, scratch_of(d_scratch), (cudaStream_t)stream);
+}
+extern "C" int kb_residual(int64_t n, const double *d_b, const double *d_q, double *d_r, double *d_out2, void *d_scratch,
+                           void *stream) {
+    if (!d_b || !d_q || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
+    return launch_vec_s<1>(n, BodyResidualP{d_b, d_q, d_r}, FinStore{d_out2}, scratch_of(d_scratch), (cudaStream_t)stream);
+}
+extern "C" int kb_axpy_neg(int64_t n, const double *d_alpha, const double *d_v, double *d_r, void *stream) {
+    if (!d_alpha || !d_v || !d_r) return KB_EINVAL;
+    return launch_vec_s<0>(n, BodyAxpyP{d_alpha, d_v, d_r}, NoFin{}, Scratch{nullptr, nullptr}, (cudaStream_t)stream);
+}
+extern "C" int kb_bicgstab_update(int64_t n, const double *d_alpha, const double *d_omega, const double *d_p,
+                                  const double *d_t, const double *d_rhat, double *d_x, double *d_r, double *d_out2,
+                                  void *d_scratch, void *stream) {
+    if (!d_alpha || !d_omega || !d_p || !d_t || !d_rhat || !d_x || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
+    return launch_vec_s<1>(n, BodyBiUpdateP{d_alpha, d_omega, d_p, d_t, d_rhat, d_x, d_r}, FinStore{d_out2},
+                           scratch_of(d_scratch), (cudaStream_t)stream);
+}
+extern "C" int kb_bicgstab_p(int64_t n, const double *d_beta, const double *d_omega, const double *d_r,
+                             const double *d_v, double *d_p, void *stream) {
+    if (!d_beta || !d_omega || !d_r || !d_v || !d_p) return KB_EINVAL;
+    return launch_vec_s<0>(n, BodyBiPP{d_beta, d_omega, d_r, d_v, d_p}, NoFin{}, Scratch{nullptr, nullptr},
+                           (cudaStream_t)stream);
+}
+extern "C" int kb_cg_update(int64_t n, const double *d_alpha, const double *d_p, const double *d_q, double *d_x,
+                            double *d_r, double *d_out2, void *d_scratch, void *stream) {
+    if (!d_alpha || !d_p || !d_q || !d_x || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
+    return launch_vec_s<1>(n, BodyCgUpdateP{d_alpha, d_p, d_q, d_x, d_r}, FinStore{d_out2}, scratch_of(d_scratch),
+                           (cudaStream_t)stream);
+}
+extern "C" int kb_cg_p(int64_t n, const double *d_beta, const double *d_r, double *d_p, void *stream) {
+    if (!d_beta || !d_r || !d_p) return KB_EINVAL;
+    return launch_vec_s<0>(n, BodyCgPP{d_beta, d_r, d_p}, NoFin{}, Scratch{nullptr, nullptr}, (cudaStream_t)stream);
+}
+extern "C" int kb_vec_mul(int64_t n, const double *d_a, const double *d_b, double *d_out, void *stream) {
+    if (!d_a || !d_b || !d_out) return KB_EINVAL;
+    return launch_vec_s<0>(n, BodyMulP{d_a, d_b, d_out}, NoFin{}, Scratch{nullptr, nullptr}, (cudaStream_t)stream);
+}
+// Jacobi scaling pieces: mode 0 -> scale = 1/diag (BiCGSTAB, column scaling), mode 1 -> 1/sqrt(diag) (CG, symmetric)
+extern "C" int kb_diag_scale(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+                             int mode, double *d_scale, void *stream) {
+    if (!d_indptr || !d_indices || !d_vals || !d_scale || nrows < 0 || (mode != 0 && mode != 1)) return KB_EINVAL;
+    if (nrows == 0) return 0;
+    const int g = kb_grid(nrows, 256, 8);
+    if (mode == 0) k_diag_scale<0><<<g, 256, 0, (cudaStream_t)stream>>>(nrows, d_indptr, d_indices, d_vals, d_scale);
+    else k_diag_scale<1><<<g, 256, 0, (cudaStream_t)stream>>>(nrows, d_indptr, d_indices, d_vals, d_scale);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int kb_scale_matrix(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+                               int mode, const double *d_scale, double *d_out, void *stream) {
+    if (!d_indptr || !d_indices || !d_vals || !d_scale || !d_out || nrows < 0 || (mode != 0 && mode != 1)) return KB_EINVAL;
+    if (nrows == 0) return 0;
+    const int g = kb_grid(nrows, 256, 8);
+    if (mode == 0) k_scale_matrix<0><<<g, 256, 0, (cudaStream_t)stream>>>(nrows, d_indptr, d_indices, d_vals, d_scale, d_out);
+    else k_scale_matrix<1><<<g, 256, 0, (cudaStream_t)stream>>>(nrows, d_indptr, d_indices, d_vals, d_scale, d_out);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int kb_profile_spmv_begin(int every) {
     if (!g_prof.have_events) {
         for (int i = 0; i < 2 * SpmvProfile::CAP; ++i) KB_CUDA(cudaEventCreate(&g_prof.ev[i]));

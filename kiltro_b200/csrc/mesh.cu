@@ -41,6 +41,37 @@ __global__ void __launch_bounds__(256) k_mesh_rect(double x0, double x1, double 
     }
 }
 
+// strip of a Rectangle mesh: node rows [j_first, j_first + nrows) of the global (nx+1) x (ny+1) grid, local numbering
+// x-fastest, coordinates bit-identical to the global mesh (row-block partition across GPUs)
+__global__ void __launch_bounds__(256) k_mesh_rect_strip(double x0, double x1, double sx, double y0, double y1, double sy,
+                                                         int64_t nx, int64_t ny, int64_t j_first, int64_t nrows,
+                                                         double *__restrict__ points, int32_t *__restrict__ elements) {
+    const int64_t nnode = (nx + 1) * nrows;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnode; p += stride) {
+        const int64_t jl = p / (nx + 1), i = p - jl * (nx + 1);
+        double2 xy = make_double2(linspace_at(x0, x1, sx, i, nx), linspace_at(y0, y1, sy, j_first + jl, ny));
+        reinterpret_cast<double2 *>(points)[p] = xy;
+        if (i < nx && jl < nrows - 1) {
+            const int c = (int)p;
+            int4 el = make_int4(c, c + 1, c + (int)nx + 2, c + (int)nx + 1);
+            reinterpret_cast<int4 *>(elements)[jl * nx + i] = el;
+        }
+    }
+}
+
+extern "C" int kb_mesh_rectangle_strip(double x0, double y0, double x1, double y1, int64_t nx, int64_t ny,
+                                       int64_t j_first, int64_t nrows, double *d_points, int32_t *d_elements,
+                                       void *stream) {
+    if (nx < 1 || ny < 1 || j_first < 0 || nrows < 2 || j_first + nrows > ny + 1 || !d_points || !d_elements) return KB_EINVAL;
+    if ((nx + 1) * nrows > INT32_MAX) return KB_ETOOBIG;
+    const double sx = (x1 - x0) / (double)nx, sy = (y1 - y0) / (double)ny;
+    k_mesh_rect_strip<<<kb_grid((nx + 1) * nrows, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        x0, x1, sx, y0, y1, sy, nx, ny, j_first, nrows, d_points, d_elements);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int kb_mesh_line(double left, double right, int64_t n, double *d_points, int32_t *d_elements, void *stream) {
     if (n < 1 || !d_points || !d_elements) return KB_EINVAL;
     if (n + 1 > INT32_MAX) return KB_ETOOBIG;

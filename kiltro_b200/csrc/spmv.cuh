@@ -20,14 +20,15 @@ constexpr int NNZ_SMEM = 3072;            // staging capacity (24 KB): target + 
 
 static inline int64_t num_blocks(int64_t nnz) { return nnz > 0 ? (nnz + NNZ_TARGET - 1) / NNZ_TARGET : 1; }
 
-// rowblk[b] = last row r with indptr[r] <= b*NNZ_TARGET (b = 1..nblk-1), rowblk[0] = 0, rowblk[nblk] = nrows
+// rowblk[b] = last row r with indptr[r] - indptr[0] <= b*NNZ_TARGET (b = 1..nblk-1), rowblk[0] = 0, rowblk[nblk] = nrows
+// (indptr may be a row-range view of a larger CSR: offsets are taken relative to indptr[0])
 static __global__ void __launch_bounds__(256) k_partition(int64_t nrows, int64_t nblk, const int32_t *__restrict__ indptr,
                                                    int32_t *__restrict__ rowblk) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nblk) return;
     if (b == 0) { rowblk[0] = 0; return; }
     if (b == nblk) { rowblk[nblk] = (int32_t)nrows; return; }
-    const int64_t target = b * NNZ_TARGET;
+    const int64_t target = (int64_t)indptr[0] + b * NNZ_TARGET;
     int64_t lo = 0, hi = nrows;              // invariant: indptr[lo] <= target ; answer in [lo, hi]
     while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;

@@ -53,6 +53,26 @@ __global__ void __launch_bounds__(256) k_transient_matrix(int64_t ndof, const in
     }
 }
 
+// out = c_k*Kff + c_m*M (+ identity on the rows of fixed DOFs when asked): the operators of the partitioned solves
+__global__ void __launch_bounds__(256) k_masked_matrix(int64_t ndof, const int32_t *__restrict__ indptr,
+                                                       const int32_t *__restrict__ indices,
+                                                       const double *__restrict__ K, const double *__restrict__ M,
+                                                       const int32_t *__restrict__ renum, double c_k, double c_m,
+                                                       int identity_fixed, double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ndof; i += stride) {
+        const bool rfree = renum[i] >= 0;
+        for (int p = indptr[i], pe = indptr[i + 1]; p < pe; ++p) {
+            const int col = indices[p];
+            const bool ff = rfree && __ldg(renum + col) >= 0;
+            double v = ff ? c_k * K[p] : 0.0;
+            if (M != nullptr) v += c_m * M[p];                 // the mass matrix stays whole: (M^-1)[in,in] convention
+            if (identity_fixed && !rfree && col == (int)i) v = 1.0;
+            out[p] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_mask_free(int64_t ndof, const int32_t *__restrict__ renum,
                                                    const double *__restrict__ in, double *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -95,6 +115,17 @@ extern "C" int kb_mask_free(int64_t ndof, const int32_t *d_renum, const double *
     if (!d_renum || !d_in || !d_out || ndof < 0) return KB_EINVAL;
     if (ndof == 0) return 0;
     k_mask_free<<<kb_grid(ndof, 256, 8), 256, 0, (cudaStream_t)stream>>>(ndof, d_renum, d_in, d_out);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb_masked_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                                const double *d_K, const double *d_M, const int32_t *d_renum, double c_k, double c_m,
+                                int identity_fixed, double *d_out, void *stream) {
+    if (!d_indptr || !d_indices || !d_K || !d_renum || !d_out || ndof < 0 || nnz < 0) return KB_EINVAL;
+    if (ndof == 0) return 0;
+    k_masked_matrix<<<kb_grid(ndof, 256, 8), 256, 0, (cudaStream_t)stream>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum,
+                                                                             c_k, c_m, identity_fixed, d_out);
     KB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,405 @@
+"""K9: row-block (mesh-strip) partitioned solves across GPUs -- new capability (the reference is single-process; SURVEY
+section 8e).  One process per GPU; torch.distributed (NCCL) carries the only two exchanges the path has:
+
+  * halo rows of the SpMV input (one mesh row = nx_nodes doubles per neighbour per SpMV),
+  * the scalars of the dot products (2 doubles per all-reduce).
+
+Each rank owns a horizontal strip of mesh rows, generates / assembles its strip plus ONE halo row of nodes per side as an
+ordinary local mesh (so the CSR rows of the nodes it owns are complete and assembly needs no communication), and iterates
+on  A' = [Kff 0; 0 I]  (identity rows for prescribed DOFs: the iterates on the free DOFs are those of the reduced system
+the single-GPU path solves).  The solver loops are written SPMD-over-a-list: with NCCL the list has one local part; with
+`LocalComm` several parts live in one process on one device and the "collectives" are plain copies/sums -- that is how
+the partitioned algorithm is tested against the single-GPU solve without a multi-GPU box, and the CPU (gloo) tests cover
+the partition arithmetic and the exchange plumbing."""
+import numpy as np
+import torch
+
+from . import _lib, device as D
+from .MeshGeneration import Mesh
+from .BoundaryCondition import BoundaryCondition
+from .FEMSolver import FEMSolver
+from .FiniteElements.Assembly import Assemble
+
+
+class StripPartition(object):
+    """Mesh rows [j0, j1) of an (nx_nodes x ny_nodes) node grid owned by `rank`, plus one halo row per interior side."""
+
+    def __init__(self, nx_nodes, ny_nodes, world, rank):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("bad rank/world")
+        if ny_nodes < 2 * world:
+            raise ValueError("need at least two mesh rows per rank")
+        self.nxn, self.nyn, self.world, self.rank = int(nx_nodes), int(ny_nodes), int(world), int(rank)
+        base, rem = divmod(self.nyn, self.world)
+        self.j0 = rank * base + min(rank, rem)
+        self.j1 = self.j0 + base + (1 if rank < rem else 0)
+        self.hb = 1 if rank > 0 else 0                  # halo row below (owned by rank-1)
+        self.ha = 1 if rank < world - 1 else 0          # halo row above (owned by rank+1)
+        self.j_first = self.j0 - self.hb
+        self.nrows_loc = self.j1 - self.j0 + self.hb + self.ha
+        self.n_own = (self.j1 - self.j0) * self.nxn
+        self.n_loc = self.nrows_loc * self.nxn
+        self.own_off = self.hb * self.nxn
+        self.global_off = self.j0 * self.nxn            # global node id of the first owned node
+
+    # slices of a full local vector
+    def own(self):
+        return slice(self.own_off, self.own_off + self.n_own)
+
+    def first_own_row(self):
+        return slice(self.own_off, self.own_off + self.nxn)
+
+    def last_own_row(self):
+        return slice(self.own_off + self.n_own - self.nxn, self.own_off + self.n_own)
+
+    def halo_below(self):
+        return slice(0, self.nxn) if self.hb else None
+
+    def halo_above(self):
+        return slice(self.own_off + self.n_own, self.own_off + self.n_own + self.nxn) if self.ha else None
+
+
+# ------------------------------------------------------------------------------------------------------ communicators
+class DistComm(object):
+    """torch.distributed (NCCL on GPUs; gloo works for CPU tensors in the host-logic tests).  One part per process."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def halo_exchange(self, parts, vecs):
+        part, v = parts[0], vecs[0]
+        dist = self.dist
+        ops, keep = [], []
+        if part.ha:
+            sb = v[part.last_own_row()].contiguous(); rb = torch.empty_like(sb); keep.append((rb, part.halo_above()))
+            ops += [dist.P2POp(dist.isend, sb, part.rank + 1, self.group), dist.P2POp(dist.irecv, rb, part.rank + 1, self.group)]
+        if part.hb:
+            sb = v[part.first_own_row()].contiguous(); rb = torch.empty_like(sb); keep.append((rb, part.halo_below()))
+            ops += [dist.P2POp(dist.isend, sb, part.rank - 1, self.group), dist.P2POp(dist.irecv, rb, part.rank - 1, self.group)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            for rb, sl in keep:
+                v[sl] = rb
+
+    def allreduce(self, outs):
+        self.dist.all_reduce(outs[0], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def barrier(self):
+        self.dist.barrier(self.group)
+
+
+class LocalComm(object):
+    """All parts in one process (one device): exchanges are copies, reductions are sums in rank order."""
+
+    def __init__(self, world):
+        self.world, self.rank = world, 0
+
+    def halo_exchange(self, parts, vecs):
+        for k, part in enumerate(parts):
+            if part.ha:
+                vecs[k][part.halo_above()] = vecs[k + 1][parts[k + 1].first_own_row()]
+            if part.hb:
+                vecs[k][part.halo_below()] = vecs[k - 1][parts[k - 1].last_own_row()]
+
+    def allreduce(self, outs):
+        total = outs[0].clone()
+        for o in outs[1:]:
+            total += o
+        for o in outs:
+            o.copy_(total)
+
+    def barrier(self):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------------ local systems
+class LocalSystem(object):
+    """The strip of one rank: local mesh, assembled operators (owned rows complete), right-hand side, work vectors."""
+
+    def __init__(self, part):
+        self.part = part
+        self.lib = _lib.load()
+
+    def _view(self, A_vals):
+        """Row-range view (owned rows) of the local CSR for the SpMV kernel."""
+        return A_vals
+
+    def spmv_dots(self, vals, x, y, w, out2):
+        p = self.part
+        _lib.check(self.lib.kb_spmv_dots(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
+                                         D.ptr(self.indices), D.ptr(vals), D.ptr(self.rowblk), D.ptr(x),
+                                         y.data_ptr() + 8 * p.own_off, w.data_ptr() + 8 * p.own_off, D.ptr(out2),
+                                         D.ptr(self.scratch), D.stream_ptr()))
+
+    def spmv(self, vals, x, y):
+        p = self.part
+        _lib.check(self.lib.kb_spmv(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off, D.ptr(self.indices),
+                                    D.ptr(vals), D.ptr(self.rowblk), D.ptr(x), y.data_ptr() + 8 * p.own_off,
+                                    D.stream_ptr()))
+
+    def own_ptr(self, v):
+        return v.data_ptr() + 8 * self.part.own_off
+
+
+def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, dirichlet_fn, neumann_fn=None,
+                       transient=False, initial_fn=None):
+    """Generates the rank's strip (+ halo rows) of Mesh.Rectangle(*rectangle) on device, assembles it with the ordinary
+    single-GPU machinery and prepares the partitioned operators.
+    velocity_fn / dirichlet_fn / neumann_fn / initial_fn: callables (points (n_loc, 2) CUDA tensor) -> CUDA tensor
+    ((n_loc, 2) velocity or None; (n_loc, 1) flags with NaN = unconstrained; (n_loc, 1) initial field)."""
+    lib = _lib.load()
+    (x0, y0), (x1, y1), nx, ny = rectangle
+    if nx + 1 != part.nxn or ny + 1 != part.nyn:
+        raise ValueError("partition does not match the rectangle")
+    pts = D.empty((part.n_loc, 2)); el = D.empty(((part.nrows_loc - 1) * nx, 4), torch.int32)
+    _lib.check(lib.kb_mesh_rectangle_strip(float(x0), float(y0), float(x1), float(y1), nx, ny, part.j_first,
+                                           part.nrows_loc, D.ptr(pts), D.ptr(el), D.stream_ptr()))
+    mesh = Mesh(element_type="quad")
+    mesh._set_device(pts, el, 2)
+    mesh.structured_shape = (part.nxn, part.nrows_loc)
+    vel = velocity_fn(pts) if velocity_fn is not None else None
+    form = formulation_cls(mesh, velocity=vel) if vel is not None else formulation_cls(mesh)
+    fs = FEMSolver(analysis_type="transient" if transient else "steady", verbose=False)
+    bc = BoundaryCondition()
+    flags = dirichlet_fn(pts)
+    bc.SetDirichletCriteria(lambda: flags)
+    if neumann_fn is not None:
+        nfl = neumann_fn(pts)
+        bc.SetNeumannCriteria(lambda: nfl)
+    K, Flux, M = Assemble(fs, form.function_spaces, form, mesh, material, bc)
+    bc.GetDirichletBoundaryConditions(form, mesh, material, fs)
+    Fn = bc.ComputeNeumannFluxes(mesh, material)
+    sysm = LocalSystem(part)
+    sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.K, sysm.M = mesh, form, bc, fs, K, M
+    sysm.symmetric = bool(form.is_symmetric)
+    sysm.indptr, sysm.indices = K.indptr, K.indices
+    ip = K.indptr[[part.own_off, part.own_off + part.n_own]].cpu()
+    sysm.nnz_own = int(ip[1] - ip[0])
+    nblk = lib.kb_spmv_num_blocks(sysm.nnz_own)
+    sysm.rowblk = D.empty(nblk + 1, torch.int32)
+    _lib.check(lib.kb_spmv_partition(part.n_own, sysm.nnz_own, K.indptr.data_ptr() + 4 * part.own_off, D.ptr(sysm.rowblk),
+                                     D.stream_ptr()))
+    sysm.scratch = D.zeros(lib.kb_blocks_scratch_bytes(sysm.nnz_own), torch.uint8)
+    n = part.n_loc
+    # right-hand side of the steady problem on A' = [Kff 0; 0 I]:  F - K[:,fixed] T_D at free rows, T_D at fixed rows
+    F = (-Fn).contiguous()
+    K_b, F_b, F = bc.ApplyDirichletGetReducedMatrices(K, F, bc.applied_dirichlet_device)
+    sysm.b = bc.TotalComponentSol(F_b, bc.applied_dirichlet_device, 0, n, 1).reshape(-1).contiguous()
+    del K_b
+    sysm.Fm = None
+    if transient:
+        # F = K[in,out] T_D - F_neumann at free DOFs, 0 at fixed DOFs (FEMSolver.py:269-272)
+        F2 = D.zeros((n, 1))
+        bc.ApplyDirichletGetReducedMatrices(K, F2, bc.applied_dirichlet_device, only_residual=True)
+        F2 = (-F2 - Fn).contiguous()
+        sysm.Fm = D.empty(n)
+        _lib.check(lib.kb_mask_free(n, D.ptr(bc.renum), D.ptr(F2), D.ptr(sysm.Fm), D.stream_ptr()))
+        if initial_fn is not None:
+            T0 = initial_fn(pts).reshape(-1).to(torch.float64).clone()
+            T0 += bc.UpdateFixDoFs(bc.applied_dirichlet_device, n, 1).reshape(-1)
+            sysm.T0 = T0
+    return sysm
+
+
+def _masked(sysm, c_k, c_m, identity_fixed):
+    lib = sysm.lib
+    out = D.empty(sysm.K.nnz)
+    _lib.check(lib.kb_masked_matrix(sysm.part.n_loc, sysm.K.nnz, D.ptr(sysm.indptr), D.ptr(sysm.indices),
+                                    D.ptr(sysm.K.data), D.ptr(sysm.M.data) if (c_m != 0.0 and sysm.M != []) else None,
+                                    D.ptr(sysm.bc.renum), float(c_k), float(c_m), int(identity_fixed), D.ptr(out),
+                                    D.stream_ptr()))
+    return out
+
+
+def _jacobi_scale(systems, comm, mats, mode):
+    """scale vectors (halo-consistent) and scaled copies of the local matrices.  mode 0: A D^-1, mode 1: D^-1/2 A D^-1/2."""
+    scales, scaled = [], []
+    for s, A in zip(systems, mats):
+        sc = D.empty(s.part.n_loc)
+        _lib.check(s.lib.kb_diag_scale(s.part.n_loc, D.ptr(s.indptr), D.ptr(s.indices), D.ptr(A), mode, D.ptr(sc),
+                                       D.stream_ptr()))
+        scales.append(sc)
+    comm.halo_exchange([s.part for s in systems], scales)      # halo rows are incomplete locally: take the owner's value
+    for s, A, sc in zip(systems, mats, scales):
+        out = D.empty(A.shape[0])
+        _lib.check(s.lib.kb_scale_matrix(s.part.n_loc, D.ptr(s.indptr), D.ptr(s.indices), D.ptr(A), mode, D.ptr(sc),
+                                         D.ptr(out), D.stream_ptr()))
+        scaled.append(out)
+    return scales, scaled
+
+
+# ------------------------------------------------------------------------------------------------------ Krylov loops
+def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
+    """Unpreconditioned BiCGSTAB on the (already Jacobi-scaled) partitioned operator.  b, x: full local vectors per part
+    (x: initial guess in, solution out, owned range).  Returns dict(iterations, relative_residual, status)."""
+    parts = [s.part for s in systems]
+    P = len(systems)
+    z = lambda s: D.zeros(s.part.n_loc)
+    r = [z(s) for s in systems]; rhat = [z(s) for s in systems]; p = [z(s) for s in systems]
+    v = [z(s) for s in systems]; t = [z(s) for s in systems]
+    d = [D.zeros(2) for _ in systems]
+    sc = [dict(rho=D.zeros(1), alpha=D.zeros(1), omega=D.zeros(1), beta=D.zeros(1)) for _ in systems]
+    st = D.stream_ptr
+    # r = b - A x ; rhat = p = r
+    comm.halo_exchange(parts, x)
+    for k, s in enumerate(systems):
+        s.spmv(Ahat[k], x[k], v[k])
+        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(v[k]), s.own_ptr(r[k]), D.ptr(d[k]),
+                                     D.ptr(s.scratch), st()))
+    comm.allreduce(d)
+    rr0, bb = float(d[0][0]), float(d[0][1])
+    tol2 = rtol * rtol * bb
+    for k in range(P):
+        rhat[k].copy_(r[k]); p[k].copy_(r[k]); sc[k]["rho"].copy_(d[k][0:1])
+    it, rr, status = 0, rr0, 0
+    if not (rr0 > tol2):
+        return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    while it < maxiter:
+        for _ in range(min(check_every, maxiter - it)):
+            comm.halo_exchange(parts, p)
+            for k, s in enumerate(systems):
+                s.spmv_dots(Ahat[k], p[k], v[k], rhat[k], d[k])
+            comm.allreduce(d)
+            for k, s in enumerate(systems):
+                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])
+                _lib.check(s.lib.kb_axpy_neg(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(v[k]), s.own_ptr(r[k]), st()))
+            comm.halo_exchange(parts, r)
+            for k, s in enumerate(systems):
+                s.spmv_dots(Ahat[k], r[k], t[k], r[k], d[k])
+            comm.allreduce(d)
+            for k, s in enumerate(systems):
+                torch.div(d[k][0:1], d[k][1:2], out=sc[k]["omega"])
+                _lib.check(s.lib.kb_bicgstab_update(s.part.n_own, D.ptr(sc[k]["alpha"]), D.ptr(sc[k]["omega"]),
+                                                    s.own_ptr(p[k]), s.own_ptr(t[k]), s.own_ptr(rhat[k]), s.own_ptr(x[k]),
+                                                    s.own_ptr(r[k]), D.ptr(d[k]), D.ptr(s.scratch), st()))
+            comm.allreduce(d)
+            for k, s in enumerate(systems):
+                # beta = (rho_new / rho)(alpha / omega) ; rho = rho_new
+                torch.div(d[k][0:1], sc[k]["rho"], out=sc[k]["beta"])
+                sc[k]["beta"].mul_(sc[k]["alpha"]).div_(sc[k]["omega"])
+                sc[k]["rho"].copy_(d[k][0:1])
+                _lib.check(s.lib.kb_bicgstab_p(s.part.n_own, D.ptr(sc[k]["beta"]), D.ptr(sc[k]["omega"]), s.own_ptr(r[k]),
+                                               s.own_ptr(v[k]), s.own_ptr(p[k]), st()))
+            it += 1
+        rr = float(d[0][1])                                   # host sync every check_every iterations
+        if not np.isfinite(rr):
+            status = _lib.KB_EBREAKDOWN
+            break
+        if rr <= tol2:
+            break
+    else:
+        status = _lib.KB_ENOTCONV
+    if status == 0 and rr > tol2:
+        status = _lib.KB_ENOTCONV
+    return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
+
+
+def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
+    """CG on the (already symmetrically Jacobi-scaled) partitioned operator."""
+    parts = [s.part for s in systems]
+    P = len(systems)
+    z = lambda s: D.zeros(s.part.n_loc)
+    r = [z(s) for s in systems]; p = [z(s) for s in systems]; q = [z(s) for s in systems]
+    d = [D.zeros(2) for _ in systems]
+    sc = [dict(rho=D.zeros(1), alpha=D.zeros(1), beta=D.zeros(1)) for _ in systems]
+    st = D.stream_ptr
+    comm.halo_exchange(parts, x)
+    for k, s in enumerate(systems):
+        s.spmv(Ahat[k], x[k], q[k])
+        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(q[k]), s.own_ptr(r[k]), D.ptr(d[k]),
+                                     D.ptr(s.scratch), st()))
+    comm.allreduce(d)
+    rr, bb = float(d[0][0]), float(d[0][1])
+    tol2 = rtol * rtol * bb
+    for k in range(P):
+        p[k].copy_(r[k]); sc[k]["rho"].copy_(d[k][0:1])
+    it, status = 0, 0
+    if not (rr > tol2):
+        return {"iterations": 0, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    while it < maxiter:
+        for _ in range(min(check_every, maxiter - it)):
+            comm.halo_exchange(parts, p)
+            for k, s in enumerate(systems):
+                s.spmv_dots(Ahat[k], p[k], q[k], p[k], d[k])
+            comm.allreduce(d)
+            for k, s in enumerate(systems):
+                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])
+                _lib.check(s.lib.kb_cg_update(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(p[k]), s.own_ptr(q[k]),
+                                              s.own_ptr(x[k]), s.own_ptr(r[k]), D.ptr(d[k]), D.ptr(s.scratch), st()))
+            comm.allreduce(d)
+            for k, s in enumerate(systems):
+                torch.div(d[k][0:1], sc[k]["rho"], out=sc[k]["beta"])
+                sc[k]["rho"].copy_(d[k][0:1])
+                _lib.check(s.lib.kb_cg_p(s.part.n_own, D.ptr(sc[k]["beta"]), s.own_ptr(r[k]), s.own_ptr(p[k]), st()))
+            it += 1
+        rr = float(d[0][0])
+        if not np.isfinite(rr):
+            status = _lib.KB_EBREAKDOWN
+            break
+        if rr <= tol2:
+            break
+    else:
+        status = _lib.KB_ENOTCONV
+    if status == 0 and rr > tol2:
+        status = _lib.KB_ENOTCONV
+    return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
+
+
+# ------------------------------------------------------------------------------------------------------ drivers
+def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto"):
+    """Partitioned steady solve.  Returns (list of owned-solution tensors (n_own,), info)."""
+    mats = [_masked(s, 1.0, 0.0, 1) for s in systems]
+    sym = all(s.symmetric for s in systems) if method == "auto" else (method == "cg")
+    mode = 1 if sym else 0
+    scales, Ahat = _jacobi_scale(systems, comm, mats, mode)
+    del mats
+    b, x = [], []
+    for s, sc in zip(systems, scales):
+        bb = s.b.clone()
+        if mode == 1:
+            _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(s.b), D.ptr(sc), D.ptr(bb), D.stream_ptr()))
+        b.append(bb); x.append(D.zeros(s.part.n_loc))
+    info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, maxiter, check_every)
+    info["method"] = "cg" if sym else "bicgstab"
+    sols = []
+    for s, sc, xh in zip(systems, scales, x):
+        out = D.empty(s.part.n_loc)
+        _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(xh), D.ptr(sc), D.ptr(out), D.stream_ptr()))   # x = D^-1 xhat (or D^-1/2)
+        sols.append(out[s.part.own()].clone())
+    return sols, info
+
+
+def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000, check_every=4):
+    """Partitioned theta-method loop (same scheme as kb_transient_run).  Returns (list of owned T^nsteps, info)."""
+    parts = [s.part for s in systems]
+    Kff = [_masked(s, 1.0, 0.0, 0) for s in systems]
+    A = [_masked(s, theta * dt, 1.0, 0) for s in systems]                 # M + theta dt Kff  (rows of fixed DOFs: M only)
+    sym = theta == 0.0 or all(s.symmetric for s in systems)
+    mode = 1 if sym else 0
+    scales, Ahat = _jacobi_scale(systems, comm, A, mode)
+    del A
+    T = [s.T0.clone() for s in systems]
+    yh = [D.zeros(s.part.n_loc) for s in systems]
+    kt = [D.zeros(s.part.n_loc) for s in systems]
+    rhs = [D.zeros(s.part.n_loc) for s in systems]
+    total = 0
+    worst = 0.0
+    for step in range(nsteps):
+        comm.halo_exchange(parts, T)
+        for k, s in enumerate(systems):
+            s.spmv(Kff[k], T[k], kt[k])
+            torch.add(kt[k], s.Fm, out=rhs[k])
+            if mode == 1:
+                rhs[k].mul_(scales[k])
+        info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, rhs, yh, rtol, maxiter, check_every)
+        total += info["iterations"]; worst = max(worst, info["relative_residual"])
+        for k, s in enumerate(systems):
+            y = yh[k] * scales[k]
+            free = s.bc.renum >= 0
+            T[k] = torch.where(free, T[k] - dt * y, T[k])
+            T[k][s.bc.columns_out_device] = s.bc.applied_dirichlet_device
+    return [Tk[s.part.own()].clone() for Tk, s in zip(T, systems)], {"iterations": total, "worst_relative_residual": worst,
+                                                                     "method": "cg" if sym else "bicgstab"}

@@ -407,3 +407,70 @@ def test_transient_theta_method(theta):
         ref.append(Tn.copy())
     ref = np.array(ref).T
     assert np.isfinite(T).all() and rel_l2(T, ref) < SOL_TOL, fs.solver_info
+
+
+# ------------------------------------------------------------------------------------------------- K9 partitioned solves
+def _dist_problem(nx, ny, world, transient, sym=False):
+    """Global problem + its row-block partition emulated on one device (LocalComm)."""
+    K = _K()
+    from kiltro_b200 import distributed as KD
+    rect = ((0.0, 0.0), (1.0, 0.75), nx, ny)
+    U = 0.45 * 2.0 * nx
+
+    def velocity_fn(pts):
+        v = torch.empty_like(pts)
+        v[:, 0] = U * (1.0 + 0.1 * torch.sin(7.0 * pts[:, 1]))
+        v[:, 1] = 0.1 * U * torch.cos(5.0 * pts[:, 0])
+        return v
+
+    def dirichlet_fn(pts):
+        f = torch.full((pts.shape[0], 1), float("nan"), dtype=torch.float64, device=pts.device)
+        f[pts[:, 0] == 0.0, 0] = 100.0
+        f[pts[:, 0] == 1.0, 0] = 500.0
+        return f
+
+    def neumann_fn(pts):
+        f = torch.full((pts.shape[0], 1), float("nan"), dtype=torch.float64, device=pts.device)
+        f[(pts[:, 1] == 0.75) & (pts[:, 0] > 0.2) & (pts[:, 0] < 0.8), 0] = 3.0
+        return f
+
+    def initial_fn(pts):
+        return (200.0 + 50.0 * torch.sin(3.0 * pts[:, 0] + pts[:, 1])).reshape(-1, 1)
+
+    mat = K.FourierConduction(2, k=1.0, area=1.0, density=2.0, heat_capacity_v=1.5, q=0.0)
+    cls = K.HeatDiffusion if sym else K.HeatAdvectionDiffusion
+    vfn = None if sym else velocity_fn
+    parts = [KD.StripPartition(nx + 1, ny + 1, world, r) for r in range(world)]
+    systems = [KD.build_local_system(p, rect, mat, cls, vfn, dirichlet_fn, neumann_fn, transient, initial_fn) for p in parts]
+    # the same problem on one GPU through the ordinary API
+    m = K.Mesh(element_type="quad"); m.Rectangle(rect[0], rect[1], nx, ny)
+    P = m.device_points()
+    form = cls(m) if sym else cls(m, velocity=velocity_fn(P))
+    bc = K.BoundaryCondition()
+    bc.SetDirichletCriteria(lambda: dirichlet_fn(P)); bc.SetNeumannCriteria(lambda: neumann_fn(P))
+    bc.SetInitialConditions(lambda: initial_fn(P))
+    return K, KD, systems, KD.LocalComm(world), (m, form, mat, bc)
+
+
+@pytest.mark.parametrize("world,sym", [(2, False), (3, False), (4, True)])
+def test_partitioned_steady_matches_single_gpu(world, sym):
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(44, 37, world, False, sym)
+    for s, p in zip(systems, [s.part for s in systems]):      # strip coordinates are bit-identical to the global mesh
+        assert torch.equal(s.mesh.device_points(), m.device_points()[p.j_first * p.nxn:p.j_first * p.nxn + p.n_loc])
+    sols, info = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10)
+    assert info["status"] == 0 and info["method"] == ("cg" if sym else "bicgstab"), info
+    solver = K.LinearSolver(tol=1e-13)
+    ref = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=solver)
+    got = torch.cat(sols).cpu().numpy()
+    assert rel_l2(got, ref.sol.ravel()) < SOL_TOL, (info, solver.info)
+
+
+@pytest.mark.parametrize("theta", [0.0, 0.5])
+def test_partitioned_transient_matches_single_gpu(theta):
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(30, 23, 3, True)
+    fs = K.FEMSolver(analysis_type="transient", number_of_increments=13, theta=theta, verbose=False)
+    fs.snapshot_increments = [12]
+    ref = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    T, info = KD.run_transient(systems, comm, fs.time_increment, 12, theta=theta, rtol=1e-13)
+    got = torch.cat(T).cpu().numpy()
+    assert rel_l2(got, ref[:, 0]) < SOL_TOL, (info, fs.solver_info)
