@@ -169,20 +169,32 @@ def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, 
     if neumann_fn is not None:
         nfl = neumann_fn(pts)
         bc.SetNeumannCriteria(lambda: nfl)
+    sysm = LocalSystem(part)
+    sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material = mesh, form, bc, fs, material
+    sysm.transient, sysm.initial_fn = transient, initial_fn
+    sysm.symmetric = bool(form.is_symmetric)
+    sysm.rowblk = None
+    reassemble(sysm)
+    return sysm
+
+
+def reassemble(sysm):
+    """Numeric phase of one rank (pattern / tile plan are cached on sysm.fs): assembly, Dirichlet/Neumann, right-hand side."""
+    lib, part = sysm.lib, sysm.part
+    mesh, form, bc, fs, material = sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material
     K, Flux, M = Assemble(fs, form.function_spaces, form, mesh, material, bc)
     bc.GetDirichletBoundaryConditions(form, mesh, material, fs)
     Fn = bc.ComputeNeumannFluxes(mesh, material)
-    sysm = LocalSystem(part)
-    sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.K, sysm.M = mesh, form, bc, fs, K, M
-    sysm.symmetric = bool(form.is_symmetric)
+    sysm.K, sysm.M = K, M
     sysm.indptr, sysm.indices = K.indptr, K.indices
-    ip = K.indptr[[part.own_off, part.own_off + part.n_own]].cpu()
-    sysm.nnz_own = int(ip[1] - ip[0])
-    nblk = lib.kb_spmv_num_blocks(sysm.nnz_own)
-    sysm.rowblk = D.empty(nblk + 1, torch.int32)
-    _lib.check(lib.kb_spmv_partition(part.n_own, sysm.nnz_own, K.indptr.data_ptr() + 4 * part.own_off, D.ptr(sysm.rowblk),
-                                     D.stream_ptr()))
-    sysm.scratch = D.zeros(lib.kb_blocks_scratch_bytes(sysm.nnz_own), torch.uint8)
+    if sysm.rowblk is None:                                   # symbolic: SpMV row partition of the owned-row view
+        ip = K.indptr[[part.own_off, part.own_off + part.n_own]].cpu()
+        sysm.nnz_own = int(ip[1] - ip[0])
+        nblk = lib.kb_spmv_num_blocks(sysm.nnz_own)
+        sysm.rowblk = D.empty(nblk + 1, torch.int32)
+        _lib.check(lib.kb_spmv_partition(part.n_own, sysm.nnz_own, K.indptr.data_ptr() + 4 * part.own_off,
+                                         D.ptr(sysm.rowblk), D.stream_ptr()))
+        sysm.scratch = D.zeros(lib.kb_blocks_scratch_bytes(sysm.nnz_own), torch.uint8)
     n = part.n_loc
     # right-hand side of the steady problem on A' = [Kff 0; 0 I]:  F - K[:,fixed] T_D at free rows, T_D at fixed rows
     F = (-Fn).contiguous()
@@ -190,15 +202,15 @@ def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, 
     sysm.b = bc.TotalComponentSol(F_b, bc.applied_dirichlet_device, 0, n, 1).reshape(-1).contiguous()
     del K_b
     sysm.Fm = None
-    if transient:
+    if sysm.transient:
         # F = K[in,out] T_D - F_neumann at free DOFs, 0 at fixed DOFs (FEMSolver.py:269-272)
         F2 = D.zeros((n, 1))
         bc.ApplyDirichletGetReducedMatrices(K, F2, bc.applied_dirichlet_device, only_residual=True)
         F2 = (-F2 - Fn).contiguous()
         sysm.Fm = D.empty(n)
         _lib.check(lib.kb_mask_free(n, D.ptr(bc.renum), D.ptr(F2), D.ptr(sysm.Fm), D.stream_ptr()))
-        if initial_fn is not None:
-            T0 = initial_fn(pts).reshape(-1).to(torch.float64).clone()
+        if sysm.initial_fn is not None:
+            T0 = sysm.initial_fn(mesh.device_points()).reshape(-1).to(torch.float64).clone()
             T0 += bc.UpdateFixDoFs(bc.applied_dirichlet_device, n, 1).reshape(-1)
             sysm.T0 = T0
     return sysm
