@@ -64,6 +64,30 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 residency hints: the matrix streams through once (evict-first) so that the x vector, whose rows are re-used by the
+// row blocks one mesh row later, stays resident (evict-last) instead of being pushed out by 1.7 GB of values/indices.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(T_CONSUMERS) : "memory"); }
 
 // sum of one double per consumer thread (fixed order); result valid in thread 0.  red: 8 doubles.
@@ -112,6 +136,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const int32_t *__re
         // All 32 lanes fetch the (row, nnz) boundaries of the next 32 row blocks at once (one dependent-load chain per
         // 32 blocks instead of one per block); lane 0 arms the barriers and issues the bulk copies.
         const int lane = threadIdx.x & 31;
+        const uint64_t pol_stream = policy_evict_first();
         int r0 = 0, p0 = 0;
         if (nmine > 0) { r0 = __ldg(rowblk + b_begin); p0 = __ldg(indptr + r0); }
         int rn = 0, pn = 0;                                     // boundaries of blocks [base+1 .. base+32]
@@ -141,8 +166,8 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const int32_t *__re
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // stage was last written by consumers
                     mbar_expect_tx(&full[s], nv * 12u + nr * 4u);
                     if (nv) {
-                        bulk_g2s(st.vals, vals + m.pa, nv * 8u, &full[s]);
-                        bulk_g2s(st.cols, indices + m.pa, nv * 4u, &full[s]);
+                        bulk_g2s_hint(st.vals, vals + m.pa, nv * 8u, &full[s], pol_stream);
+                        bulk_g2s_hint(st.cols, indices + m.pa, nv * 4u, &full[s], pol_stream);
                     }
                     if (nr) bulk_g2s(st.rptr, indptr + m.ra, nr * 4u, &full[s]);
                 }
@@ -154,6 +179,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const int32_t *__re
         // ------------------------------------------------------------------ consumers
         double d0 = 0.0, d1 = 0.0;
         const int tid = threadIdx.x;
+        const uint64_t pol_keep = policy_evict_last();
         for (int i = 0; i < nmine; ++i) {
             const int s = i % T_STAGES;
             mbar_wait(&full[s], (i / T_STAGES) & 1);
@@ -166,7 +192,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const int32_t *__re
                 const int jcut = m.pcut - m.pa;
                 for (int r = m.r0 + tid; r < m.r1; r += T_CONSUMERS) {
                     double wv = 0.0;
-                    if (DOTS) wv = __ldg(w + r);
+                    if (DOTS) wv = __ldcs(w + r);
                     const int ia = r - m.ra;
                     const int a = ((r < m.rcut) ? st.rptr[ia] : __ldg(indptr + r)) - m.pa;
                     const int b = ((r + 1 < m.rcut) ? st.rptr[ia + 1] : __ldg(indptr + r + 1)) - m.pa;
@@ -180,7 +206,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const int32_t *__re
 #pragma unroll
                         for (int k = 0; k < T_BATCH; ++k) c[k] = st.cols[(q + k < bs) ? q + k : q];
 #pragma unroll
-                        for (int k = 0; k < T_BATCH; ++k) xv[k] = __ldg(x + c[k]);
+                        for (int k = 0; k < T_BATCH; ++k) xv[k] = ldg_hint(x + c[k], pol_keep);
 #pragma unroll
                         for (int k = 0; k < T_BATCH; ++k)
                             if (q + k < bs) sum = fma(st.vals[q + k], xv[k], sum);
