@@ -25,14 +25,28 @@ ElemOpts kb_make_opts(const kb_material *m, int mode, int petrov, int want_mass)
 
 namespace {
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int NDIM> struct ElemIO;
 template <> struct ElemIO<2> {
     static constexpr int NPE = 4;
+    typedef int4 Conn;
+    static __device__ __forceinline__ Conn load_conn(const int32_t *tile_conn, int e) {
+        return __ldg(reinterpret_cast<const int4 *>(tile_conn) + e);
+    }
+    template <bool HAS_U>
+    static __device__ __forceinline__ void prefetch(const double *points, const double *velocity, const Conn &c) {
+        const int n[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            prefetch_l1(reinterpret_cast<const double2 *>(points) + n[a]);
+            if (HAS_U) prefetch_l1(reinterpret_cast<const double2 *>(velocity) + n[a]);
+        }
+    }
     template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *points, const int32_t *tile_conn, const double *velocity,
-                                                int e, const ElemOpts &o, double (&ke)[16], double (&fe)[4],
+    static __device__ __forceinline__ void eval(const double *points, const double *velocity, const Conn &c,
+                                                const ElemOpts &o, double (&ke)[16], double (&fe)[4],
                                                 double (&me)[16]) {
-        const int4 c = __ldg(reinterpret_cast<const int4 *>(tile_conn) + e);
         const int n[4] = {c.x, c.y, c.z, c.w};
         double X[4][2], U[4][2];
 #pragma unroll
@@ -49,11 +63,18 @@ template <> struct ElemIO<2> {
 };
 template <> struct ElemIO<1> {
     static constexpr int NPE = 2;
+    typedef int2 Conn;
+    static __device__ __forceinline__ Conn load_conn(const int32_t *tile_conn, int e) {
+        return __ldg(reinterpret_cast<const int2 *>(tile_conn) + e);
+    }
+    template <bool HAS_U>
+    static __device__ __forceinline__ void prefetch(const double *points, const double *velocity, const Conn &c) {
+        prefetch_l1(points + c.x); prefetch_l1(points + c.y);
+        if (HAS_U) { prefetch_l1(velocity + c.x); prefetch_l1(velocity + c.y); }
+    }
     template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *points, const int32_t *tile_conn, const double *velocity,
-                                                int e, const ElemOpts &o, double (&ke)[4], double (&fe)[2],
-                                                double (&me)[4]) {
-        const int2 c = __ldg(reinterpret_cast<const int2 *>(tile_conn) + e);
+    static __device__ __forceinline__ void eval(const double *points, const double *velocity, const Conn &c,
+                                                const ElemOpts &o, double (&ke)[4], double (&fe)[2], double (&me)[4]) {
         double X[2] = {__ldg(points + c.x), __ldg(points + c.y)};
         double U[2] = {0.0, 0.0};
         if (HAS_U) { U[0] = __ldg(velocity + c.x); U[1] = __ldg(velocity + c.y); }
@@ -78,7 +99,7 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
                  const int32_t *__restrict__ tile_conn,
                  const int32_t *__restrict__ tile_elem_ptr, const uint32_t *__restrict__ pair_rec,
                  const int32_t *__restrict__ pair_ptr, double *__restrict__ K, double *__restrict__ M,
-                 double *__restrict__ Flux) {
+                 double *__restrict__ Flux, int ntiles) {
     constexpr int NPE = ElemIO<NDIM>::NPE, CAP = NPE * NPE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sKe = reinterpret_cast<double *>(smem_raw);                 // [EMAX * CAP]
@@ -88,81 +109,103 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
     int *sDelta = reinterpret_cast<int *>(sE2R + VMAX);                 // [RMAX]
     int *sScan = sDelta + RMAX;                                         // [64]
 
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const int rb = tile_row_ptr[t], nr = tile_row_ptr[t + 1] - rb;
-    const int eb = tile_elem_ptr[t], ne = tile_elem_ptr[t + 1] - eb;
+    typedef typename ElemIO<NDIM>::Conn Conn;
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    // Persistent CTA: tiles t, t+grid, t+2*grid, ...  The next tile's extents and this thread's next element
+    // connectivity are fetched one tile ahead and the node data they point to are pulled into L1 (prefetch.global.L1),
+    // so the element phase of the next tile starts on L1 hits instead of a three-deep chain of DRAM round trips.
+    int rb = __ldg(tile_row_ptr + t), nr = __ldg(tile_row_ptr + t + 1) - rb;
+    int eb = __ldg(tile_elem_ptr + t), ne = __ldg(tile_elem_ptr + t + 1) - eb;
+    Conn conn = ElemIO<NDIM>::load_conn(tile_conn, eb + (tid < ne ? tid : 0));
 
-    // ---- row metadata first: these loads overlap the element phase
-    int row = -1, p0 = 0, len = 0, jp0 = 0, jp1 = 0;
-    if (tid < nr) {
-        row = __ldg(tile_rows + rb + tid);
-        jp0 = __ldg(pair_ptr + rb + tid);
-        jp1 = __ldg(pair_ptr + rb + tid + 1);
-        p0 = __ldg(indptr + row);
-        len = __ldg(indptr + row + 1) - p0;
-    }
-    uint32_t rec4[4] = {0u, 0u, 0u, 0u};                 // the first four (row, element) records (a quad-4 node has <= 4)
+    for (; t < ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        int rb_n = 0, nr_n = 0, eb_n = 0, ne_n = 0;
+        if (tn < ntiles) {
+            rb_n = __ldg(tile_row_ptr + tn); nr_n = __ldg(tile_row_ptr + tn + 1) - rb_n;
+            eb_n = __ldg(tile_elem_ptr + tn); ne_n = __ldg(tile_elem_ptr + tn + 1) - eb_n;
+        }
+        // ---- row metadata first: these loads overlap the element phase
+        int row = -1, p0 = 0, len = 0, jp0 = 0, jp1 = 0;
+        if (tid < nr) {
+            row = __ldg(tile_rows + rb + tid);
+            jp0 = __ldg(pair_ptr + rb + tid);
+            jp1 = __ldg(pair_ptr + rb + tid + 1);
+            p0 = __ldg(indptr + row);
+            len = __ldg(indptr + row + 1) - p0;
+        }
+        uint32_t rec4[4] = {0u, 0u, 0u, 0u};             // the first four (row, element) records (a quad-4 node has <= 4)
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (jp0 + k < jp1) rec4[k] = __ldg(pair_rec + jp0 + k);
+        for (int k = 0; k < 4; ++k)
+            if (jp0 + k < jp1) rec4[k] = __ldg(pair_rec + jp0 + k);
 
-    // ---- phase A: element matrices -> shared memory, component-major (sKe[i][slot]: conflict-free stores and reads)
-    double me[CAP];
-    if (tid < ne) {
-        double ke[CAP], fe[NPE];
-        ElemIO<NDIM>::template eval<HAS_U, MASS>(points, tile_conn, velocity, eb + tid, o, ke, fe, me);
+        // ---- phase A: element matrices -> shared memory, component-major (sKe[i][slot]: conflict-free stores and reads)
+        double me[CAP];
+        if (tid < ne) {
+            double ke[CAP], fe[NPE];
+            ElemIO<NDIM>::template eval<HAS_U, MASS>(points, velocity, conn, o, ke, fe, me);
 #pragma unroll
-        for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = ke[i];
+            for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = ke[i];
 #pragma unroll
-        for (int i = 0; i < NPE; ++i) sFe[i * EMAX + tid] = fe[i];
-    }
-    int total;
-    const int off = block_scan_excl(len, sScan, &total);
-    if (tid < nr) {
-        sDelta[tid] = p0 - off;
-        for (int k = 0; k < len; ++k) sE2R[off + k] = (unsigned short)tid;
-    }
-    for (int i = tid; i < total; i += THREADS) sV[i] = 0.0;
-    __syncthreads();
+            for (int i = 0; i < NPE; ++i) sFe[i * EMAX + tid] = fe[i];
+        }
+        // connectivity of this thread's element in the NEXT tile (consumed after phase B)
+        Conn conn_n = conn;
+        if (tn < ntiles) conn_n = ElemIO<NDIM>::load_conn(tile_conn, eb_n + (tid < ne_n ? tid : 0));
+
+        int total;
+        const int off = block_scan_excl(len, sScan, &total);
+        if (tid < nr) {
+            sDelta[tid] = p0 - off;
+            for (int k = 0; k < len; ++k) sE2R[off + k] = (unsigned short)tid;
+        }
+        for (int i = tid; i < total; i += THREADS) sV[i] = 0.0;
+        __syncthreads();
 
 #pragma unroll 1
-    for (int pass = 0; pass < (MASS ? 2 : 1); ++pass) {
-        // ---- phase B: row-owner accumulation in ascending element order
-        if (tid < nr) {
-            double f = 0.0;
-            for (int j = jp0; j < jp1; ++j) {
-                const int k4 = j - jp0;
-                uint32_t rec;
-                if (k4 < 4) rec = k4 == 0 ? rec4[0] : k4 == 1 ? rec4[1] : k4 == 2 ? rec4[2] : rec4[3];
-                else rec = __ldg(pair_rec + j);
-                const int slot = (int)((rec >> 18) & 0x1fffu), a = (int)((rec >> 16) & 3u);
-                const double *src = &sKe[(a * NPE) * EMAX + slot];
-                if (!(rec & 0x80000000u)) {
+        for (int pass = 0; pass < (MASS ? 2 : 1); ++pass) {
+            // ---- phase B: row-owner accumulation in ascending element order
+            if (tid < nr) {
+                double f = 0.0;
+                for (int j = jp0; j < jp1; ++j) {
+                    const int k4 = j - jp0;
+                    uint32_t rec;
+                    if (k4 < 4) rec = k4 == 0 ? rec4[0] : k4 == 1 ? rec4[1] : k4 == 2 ? rec4[2] : rec4[3];
+                    else rec = __ldg(pair_rec + j);
+                    const int slot = (int)((rec >> 18) & 0x1fffu), a = (int)((rec >> 16) & 3u);
+                    const double *src = &sKe[(a * NPE) * EMAX + slot];
+                    if (!(rec & 0x80000000u)) {
 #pragma unroll
-                    for (int b = 0; b < NPE; ++b) sV[off + (int)((rec >> (4 * b)) & 15u)] += src[b * EMAX];
-                } else {                                  // row longer than 16 entries: locate the columns by search
+                        for (int b = 0; b < NPE; ++b) sV[off + (int)((rec >> (4 * b)) & 15u)] += src[b * EMAX];
+                    } else {                              // row longer than 16 entries: locate the columns by search
 #pragma unroll
-                    for (int b = 0; b < NPE; ++b)
-                        sV[off + lower_bound_g(indices + p0, len, __ldg(tile_conn + (int64_t)(eb + slot) * NPE + b))] +=
-                            src[b * EMAX];
+                        for (int b = 0; b < NPE; ++b)
+                            sV[off + lower_bound_g(indices + p0, len, __ldg(tile_conn + (int64_t)(eb + slot) * NPE + b))] +=
+                                src[b * EMAX];
+                    }
+                    if (pass == 0) f += sFe[a * EMAX + slot];
                 }
-                if (pass == 0) f += sFe[a * EMAX + slot];
+                if (pass == 0) Flux[row] = f;
             }
-            if (pass == 0) Flux[row] = f;
-        }
-        __syncthreads();
-        // ---- phase C: coalesced write-out
-        double *out = pass == 0 ? K : M;
-        for (int i = tid; i < total; i += THREADS) __stcs(out + i + sDelta[sE2R[i]], sV[i]);
-        if (MASS && pass == 0) {
             __syncthreads();
-            if (tid < ne) {
+            if (pass == 0 && tn < ntiles && tid < ne_n) ElemIO<NDIM>::template prefetch<HAS_U>(points, velocity, conn_n);
+            // ---- phase C: coalesced write-out
+            double *out = pass == 0 ? K : M;
+            for (int i = tid; i < total; i += THREADS) __stcs(out + i + sDelta[sE2R[i]], sV[i]);
+            if (MASS && pass == 0) {
+                __syncthreads();
+                if (tid < ne) {
 #pragma unroll
-                for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = me[i];
+                    for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = me[i];
+                }
+                for (int i = tid; i < total; i += THREADS) sV[i] = 0.0;
+                __syncthreads();
             }
-            for (int i = tid; i < total; i += THREADS) sV[i] = 0.0;
-            __syncthreads();
         }
+        __syncthreads();                                  // the next tile overwrites the shared buffers
+        rb = rb_n; nr = nr_n; eb = eb_n; ne = ne_n; conn = conn_n;
     }
 }
 
@@ -183,9 +226,11 @@ int launch_fused(int64_t ntiles, cudaStream_t s, const double *points, const dou
                                      (int)bytes));
         configured = true;
     }
-    k_assemble_fused<NDIM, HAS_U, MASS><<<(unsigned)ntiles, THREADS, bytes, s>>>(
+    const int64_t cap = (int64_t)kb_num_sms() * 2;           // persistent: 2 CTAs per SM
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    k_assemble_fused<NDIM, HAS_U, MASS><<<grid, THREADS, bytes, s>>>(
         points, velocity, o, indptr, indices, tile_rows, tile_row_ptr, tile_conn, tile_elem_ptr, pair_rec, pair_ptr, K, M,
-        Flux);
+        Flux, (int)ntiles);
     KB_LAUNCH_CHECK();
     return 0;
 }

@@ -37,8 +37,28 @@ __device__ __forceinline__ double pg_coefficient(double unorm, double h, double 
 }
 
 // ---------------------------------------------------------------------------------------------- quad-4, 2x2 Gauss
+// reciprocal of the Jacobian determinant: fp32 seed + two Newton steps (full double accuracy to ~1 ulp, 8 instructions
+// instead of the ~15 of an IEEE division); falls back to the division outside the fp32 exponent range.
+__device__ __forceinline__ double fast_rcp(double d) {
+    const double ad = fabs(d);
+    if (!(ad > 1.0e-30 && ad < 1.0e30)) return 1.0 / d;
+    double x = (double)__frcp_rn((float)d);
+    x = x * (2.0 - d * x);
+    x = x * (2.0 - d * x);
+    return x;
+}
+
 // X[a][d], U[a][d]: nodal coordinates / velocities in local node order (counter-clockwise).
 // Ke[16] row-major (convectionel.ravel()), Fe[4], Me[16].
+//
+// Same integrals as VariationalPrinciple.py:117-173 / :216-261 / :42-69, organised for the FP64 pipe:
+//   * the parent-space Jacobian of a Q1 quad is affine in (zeta, eta): dX/dzeta depends on eta only and is a blend of the
+//     two zeta-edges, dX/deta depends on zeta only -> 2+2 edge blends instead of four 4-term sums per Gauss point;
+//   * the geometry of the four Gauss points is evaluated first (four independent chains: determinant, reciprocal,
+//     inverse, gradients), then the accumulation streams over them;
+//   * the diffusion part is symmetric: 10 entries are accumulated and mirrored at the end;
+//   * dV (and area*k*dV) are folded into one operand of each product before the 4x4 update.
+// Rounding differs from NumPy's einsum order at the 1e-16 level (tests: <= 1e-12 relative to the reference's output).
 __device__ __forceinline__ void quad4(const double (&X)[4][2], const double (&U)[4][2], const ElemOpts &o,
                                       double (&Ke)[16], double (&Fe)[4], double (&Me)[16]) {
     // mean velocity, element length |X1 - X0|, PG coefficient                       VariationalPrinciple.py:122-124
@@ -49,67 +69,118 @@ __device__ __forceinline__ void quad4(const double (&X)[4][2], const double (&U)
         const double dx = X[1][0] - X[0][0], dy = X[1][1] - X[0][1];
         coef = pg_coefficient(sqrt(ub0 * ub0 + ub1 * ub1), sqrt(dx * dx + dy * dy), o.k);
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { Ke[i] = 0.0; Me[i] = 0.0; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Fe[i] = 0.0;
+    const double rb0 = o.rho_cv * ub0, rb1 = o.rho_cv * ub1;         // rho c_v u   (advection, :152)
+    const double cb0 = coef * ub0, cb1 = coef * ub1;                 // alpha/|u| u (PG weights, :321)
+    const double ak = o.area * o.k;
 
+    // edges: dX/dzeta = Ne0/2 (X1-X0) + Ne1/2 (X2-X3) ; dX/deta = Nz0/2 (X3-X0) + Nz1/2 (X2-X1)
+    const double e01x = X[1][0] - X[0][0], e01y = X[1][1] - X[0][1];
+    const double e32x = X[2][0] - X[3][0], e32y = X[2][1] - X[3][1];
+    const double e03x = X[3][0] - X[0][0], e03y = X[3][1] - X[0][1];
+    const double e12x = X[2][0] - X[1][0], e12y = X[2][1] - X[1][1];
+    constexpr double HHI = 0.5 * NHI, HLO = 0.5 * NLO;               // |dN/dxi| at a Gauss point: N/2
+    // index 0: Gauss coordinate -GZ, 1: +GZ
+    const double Jzx[2] = {HHI * e01x + HLO * e32x, HLO * e01x + HHI * e32x};
+    const double Jzy[2] = {HHI * e01y + HLO * e32y, HLO * e01y + HHI * e32y};
+    const double Jex[2] = {HHI * e03x + HLO * e12x, HLO * e03x + HHI * e12x};
+    const double Jey[2] = {HHI * e03y + HLO * e12y, HLO * e03y + HHI * e12y};
+
+    double D[10];                 // symmetric diffusion part, upper triangle (00 01 02 03 11 12 13 22 23 33)
+    double C[16];                 // advection part
+    double dV[4];
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {          // eta  (2nd parent direction), outer loop   FunctionSpace.py:49
+    for (int i = 0; i < 10; ++i) D[i] = 0.0;
 #pragma unroll
-        for (int gj = 0; gj < 2; ++gj) {      // zeta (1st parent direction), inner loop   FunctionSpace.py:50
-            const double Ne0 = N1(0, gi), Ne1 = N1(1, gi), Nz0 = N1(0, gj), Nz1 = N1(1, gj);
-            // Bases / gBases at this Gauss point, node_arranger [0,1,3,2]             FunctionSpace.py:53-59
-            const double B[4] = {Ne0 * Nz0, Ne0 * Nz1, Ne1 * Nz1, Ne1 * Nz0};
-            const double gz[4] = {Ne0 * -0.5, Ne0 * 0.5, Ne1 * 0.5, Ne1 * -0.5};      // d/dzeta
-            const double ge[4] = {-0.5 * Nz0, -0.5 * Nz1, 0.5 * Nz1, 0.5 * Nz0};      // d/deta
-            // ParentGradientX[i][l] = sum_j gBases[i][j] X[j][l]                       VariationalPrinciple.py:139
-            double J00 = 0, J01 = 0, J10 = 0, J11 = 0;
+    for (int i = 0; i < 16; ++i) C[i] = 0.0;
+    double S = 0.0;               // reference mode: the broadcast scalar
+    const bool consistent = o.mode == KB_MODE_CONSISTENT;
+    const bool has_adv = (rb0 != 0.0) || (rb1 != 0.0);
+    // Gauss points g = 2*gi + gj (gi: eta index, outer; gj: zeta index, inner)               FunctionSpace.py:49-50
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                J00 += gz[a] * X[a][0]; J01 += gz[a] * X[a][1];
-                J10 += ge[a] * X[a][0]; J11 += ge[a] * X[a][1];
-            }
+    for (int gi = 0; gi < 2; ++gi) {
+#pragma unroll
+        for (int gj = 0; gj < 2; ++gj) {
+            const int g = 2 * gi + gj;
+            const double J00 = Jzx[gi], J01 = Jzy[gi], J10 = Jex[gj], J11 = Jey[gj];   // ParentGradientX          :139
             const double det = J00 * J11 - J01 * J10;
-            const double idet = 1.0 / det;
-            const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;   // :140
-            const double dV = fabs(det);                                                // weights are 1.0   :145
-            // SpatialGradient[j][l] = sum_k Jinv[j][k] gBases[k][l]                    :142
-            double G0[4], G1[4], ug[4], W[4];
+            const double idet = fast_rcp(det);
+            dV[g] = fabs(det);                                                          // weights are 1.0          :145
+            const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;   // inverse   :140
+            // gBases at this point: d/dzeta = (-hE0, hE0, hE1, -hE1), d/deta = (-hZ0, -hZ1, hZ1, hZ0)
+            const double hE0 = gi == 0 ? HHI : HLO, hE1 = gi == 0 ? HLO : HHI;
+            const double hZ0 = gj == 0 ? HHI : HLO, hZ1 = gj == 0 ? HLO : HHI;
+            const double p0 = i00 * hE0, p1 = i00 * hE1, q0 = i01 * hZ0, q1 = i01 * hZ1;
+            const double G0[4] = {-p0 - q0, p0 - q1, p1 + q1, q0 - p1};                 // dN/dx                    :142
+            const double r0 = i10 * hE0, r1 = i10 * hE1, s0 = i11 * hZ0, s1 = i11 * hZ1;
+            const double G1[4] = {-r0 - s0, r0 - s1, r1 + s1, s0 - r1};                 // dN/dy
+            const double w = ak * dV[g];
+            double H0[4], H1[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                G0[a] = i00 * gz[a] + i01 * ge[a];
-                G1[a] = i10 * gz[a] + i11 * ge[a];
-                ug[a] = o.rho_cv * (ub0 * G0[a] + ub1 * G1[a]);                         // advection           :152
-                W[a] = B[a] + coef * (ub0 * gz[a] + ub1 * ge[a]);                       // PG weight (parent-space grads) :321
-            }
-            const double ak = o.area * o.k;
-            if (o.mode == KB_MODE_REFERENCE) {
-                double s = 0.0;                                                         // np.dot(advection, W): scalar  :170
+            for (int a = 0; a < 4; ++a) { H0[a] = w * G0[a]; H1[a] = w * G1[a]; }
+            int t = 0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) s += ug[a] * W[a];
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int b = a; b < 4; ++b) { D[t] += H0[a] * G0[b] + H1[a] * G1[b]; ++t; }   // (area k G)^T G dV     :150,169
+            if (has_adv) {
+                double ug[4];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        Ke[4 * a + b] += (ak * (G0[a] * G0[b] + G1[a] * G1[b]) + s) * dV;
-            } else {
+                for (int a = 0; a < 4; ++a) ug[a] = (rb0 * G0[a] + rb1 * G1[a]) * dV[g];          // advection dV     :152
+                // weights: Bases (+ PG correction from the parent-space gradients)        FunctionSpace.py:53-59, :321
+                const double Ne0 = 2.0 * hE0, Ne1 = 2.0 * hE1, Nz0 = 2.0 * hZ0, Nz1 = 2.0 * hZ1;
+                const double W[4] = {Ne0 * Nz0 + (cb0 * -hE0 + cb1 * -hZ0), Ne0 * Nz1 + (cb0 * hE0 + cb1 * -hZ1),
+                                     Ne1 * Nz1 + (cb0 * hE1 + cb1 * hZ1), Ne1 * Nz0 + (cb0 * -hE1 + cb1 * hZ0)};
+                if (consistent) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        Ke[4 * a + b] += (ak * (G0[a] * G0[b] + G1[a] * G1[b]) + W[a] * ug[b]) * dV;   // MaterialBase.py:47,58
-            }
-            const double aq = o.area * o.q;
+                        for (int b = 0; b < 4; ++b) C[4 * a + b] += W[a] * ug[b];                       // MaterialBase.py:58
+                } else {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) Fe[a] += aq * B[a] * dV;                        // :154,159 (Galerkin bases)
-            if (o.want_mass) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) Me[4 * a + b] += o.rho_cv * B[a] * B[b] * dV;          // :63-67
+                    for (int a = 0; a < 4; ++a) S += ug[a] * W[a];                                      // np.dot(advection, W) :170
+                }
             }
         }
+    }
+    // ---- write out: mirror the diffusion part, add the advection part
+    {
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) {
+                Ke[4 * a + b] = D[t] + (consistent ? C[4 * a + b] : S);
+                if (b != a) Ke[4 * b + a] = D[t] + (consistent ? C[4 * b + a] : S);
+                ++t;
+            }
+    }
+    // source vector: area q N dV (Galerkin bases)                                                        :154,159
+    const double aq = o.area * o.q;
+    const double B0[4] = {NHI * NHI, NHI * NLO, NLO * NLO, NLO * NHI};      // Bases[:, g=0]; other points permute it
+    // Bases[a][g]: g=0 (B0[0],B0[1],B0[2],B0[3]); g=1: zeta flips -> (B0[1],B0[0],B0[3],B0[2]);
+    //              g=2: eta flips -> (B0[3],B0[2],B0[1],B0[0]); g=3: both -> (B0[2],B0[3],B0[0],B0[1])
+    constexpr int PERM[4][4] = {{0, 1, 2, 3}, {1, 0, 3, 2}, {3, 2, 1, 0}, {2, 3, 0, 1}};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double f = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) f += (aq * B0[PERM[g][a]]) * dV[g];
+        Fe[a] = f;
+    }
+    if (o.want_mass) {                                                                                   // :63-67
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) {
+                double m = 0.0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) m += (o.rho_cv * (B0[PERM[g][a]] * B0[PERM[g][b]])) * dV[g];
+                Me[4 * a + b] = m;
+                Me[4 * b + a] = m;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Me[i] = 0.0;
     }
 }
 
