@@ -1,0 +1,104 @@
+"""Parity at BASELINE.json's full single-GPU size (S16: 4000 x 4000 nodes, 16 M DOF) through size-independent properties:
+the oracle cannot run here in reasonable time, so the checks are closed forms, conservation identities, structural
+invariants and bitwise determinism."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+NPS = 4000
+
+
+@pytest.fixture(scope="module")
+def big():
+    import kiltro_b200 as K
+    mesh = K.Mesh(element_type="quad")
+    mesh.Rectangle(lower_left_point=(0.0, 0.0), upper_right_point=(1.0, 1.0), nx=NPS - 1, ny=NPS - 1)
+    fs = K.FEMSolver(analysis_type="transient", verbose=False)
+    mat = K.FourierConduction(2, k=1.0, area=1.0, density=2.0, heat_capacity_v=1.5, q=3.0)
+    return K, mesh, fs, mat
+
+
+def test_pattern_structure_fullsize(big):
+    K, mesh, fs, mat = big
+    form = K.HeatDiffusion(mesh)
+    sp = fs.ComputeSparsityFEM(mesh, form)
+    n = NPS
+    assert sp.nnz == (3 * n - 2) ** 2
+    ip = sp.indptr.to(torch.int64)
+    lens = ip[1:] - ip[:-1]
+    assert int(ip[0]) == 0 and int(ip[-1]) == sp.nnz and int(lens.min()) == 4 and int(lens.max()) == 9
+    assert int((lens == 4).sum()) == 4 and int((lens == 6).sum()) == 4 * (n - 2)
+    # strictly ascending columns inside every row
+    d = sp.indices[1:].to(torch.int64) - sp.indices[:-1].to(torch.int64)
+    row_start = torch.zeros(sp.nnz, dtype=torch.bool, device="cuda"); row_start[ip[1:-1]] = True
+    assert bool(((d > 0) | row_start[1:]).all())
+    # the reference's scatter maps: data_global is a surjection onto [0, nnz) with 1..4 contributors per entry
+    cnt = torch.bincount(sp.data_global_indices.to(torch.int64), minlength=sp.nnz)
+    assert int(cnt.min()) == 1 and int(cnt.max()) == 4 and int(cnt.sum()) == 16 * mesh.nelem
+
+
+def test_assembly_identities_fullsize(big):
+    K, mesh, fs, mat = big
+    form = K.HeatDiffusion(mesh)
+    Kc, Flux, M = K.Assemble(fs, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
+    assert fs.assembly_used == "fused" and fs.sparsity.tile_plan.info["structured"]
+    nn = mesh.nnodes
+    ones = torch.ones(nn, dtype=torch.float64, device="cuda")
+    kmax = float(Kc.data.abs().max())
+    # pure diffusion: constants are in the null space (row sums vanish)
+    assert float(Kc.dot(ones).abs().max()) < 1e-12 * kmax
+    # mass matrix and source vector integrate constants exactly: sum M = rho c_v |Omega|, sum Flux = area q |Omega|
+    assert abs(float(M.dot(ones).sum()) - 2.0 * 1.5 * 1.0) < 1e-9
+    assert abs(float(Flux.sum()) - 1.0 * 3.0 * 1.0) < 1e-9
+    # symmetry through the bilinear form
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    x = torch.randn(nn, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(nn, dtype=torch.float64, device="cuda", generator=g)
+    a, b = float(torch.dot(x, Kc.dot(y))), float(torch.dot(y, Kc.dot(x)))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b), 1.0)
+    # deterministic: a second assembly and the two-pass seam give the same bits
+    K2 = K.Assemble(fs, form.function_spaces, form, mesh, mat, K.BoundaryCondition())[0]
+    assert torch.equal(K2.data, Kc.data)
+    fs2 = K.FEMSolver(analysis_type="transient", verbose=False, assembly="two_pass")
+    K3, F3, M3 = K.Assemble(fs2, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
+    assert torch.equal(K3.data, Kc.data) and torch.equal(M3.data, M.data) and torch.equal(F3, Flux)
+
+
+def test_steady_closed_form_fullsize(big):
+    """Uniform velocity (cell Peclet 0.45), Dirichlet x=0 -> 100, x=1 -> 500: the consistent Galerkin scheme has the exact
+    discrete solution T_i = T_0 + dT (r^i - 1)/(r^n - 1), r = (1+Pe)/(1-Pe), independent of y."""
+    K, mesh, _, _ = big
+    n = NPS - 1
+    h = 1.0 / n
+    Pe = 0.45
+    nn = mesh.nnodes
+    vel = torch.zeros((nn, 2), dtype=torch.float64, device="cuda"); vel[:, 0] = Pe * 2.0 / h
+    flags = torch.full((nn, 1), float("nan"), dtype=torch.float64, device="cuda")
+    left = torch.arange(NPS, device="cuda") * NPS
+    flags[left, 0] = 100.0; flags[left + NPS - 1, 0] = 500.0
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    mat = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+    solver = K.LinearSolver(linear_solver_type="bicgstab", tol=1e-11, check_every=100)
+    fs = K.FEMSolver(verbose=False)
+    sol = fs.Solve(formulation=K.HeatAdvectionDiffusion(mesh, velocity=vel), mesh=mesh, material=mat, boundary_condition=bc,
+                   solver=solver)
+    assert solver.info["status"] == 0, solver.info
+    lr = math.log((1 + Pe) / (1 - Pe))
+    i = np.arange(NPS, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        exact = 100.0 + 400.0 * np.exp((i - n) * lr) * (-np.expm1(-i * lr)) / (-np.expm1(-n * lr))
+    exact[0] = 100.0
+    T = sol.sol_device[:, 0, 0].reshape(NPS, NPS)
+    ex = torch.from_numpy(exact).cuda()
+    err = float((T - ex[None, :]).abs().max()) / 500.0
+    assert err < 1e-8, (err, solver.info)
+    # residual of the full system at the returned solution (free rows)
+    Kc = K.Assemble(fs, fs.sparsity and K.HeatAdvectionDiffusion(mesh, velocity=vel).function_spaces,
+                    K.HeatAdvectionDiffusion(mesh, velocity=vel), mesh, mat, bc)[0]
+    r = Kc.dot(T.reshape(-1))
+    free = bc.renum >= 0
+    assert float(r[free].abs().max()) < 1e-6 * float(Kc.data.abs().max()) * 500.0
