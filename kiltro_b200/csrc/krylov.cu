@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) k_vec(int64_t n, Body body, double *__res
     __shared__ int s_last;
     double d0 = 0.0, d1 = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) body(i, d0, d1);
     if (DOTS) {
         d0 = block_sum(d0, red);
@@ -160,6 +161,113 @@ int launch_vec(int64_t n, Body body, Final fin, const Work &w, const int *done, 
     KB_LAUNCH_CHECK();
     return 0;
 }
+
+// Hot vector kernels: the body is split into load / apply so that four grid-stride iterations have all their loads in
+// flight before the first store (explicit memory-level parallelism; the compiler cannot hoist loads over the stores of
+// the previous iteration because the streams may alias as far as it knows).  Scalars are read once per thread.
+template <int DOTS, class Body, class Final>
+__global__ void __launch_bounds__(256) k_vec4(int64_t n, Body body, double *__restrict__ partials,
+                                              unsigned int *__restrict__ ticket, const int *__restrict__ done,
+                                              Final fin) {
+    if (done != nullptr && *done != 0) return;
+    __shared__ double red[32];
+    __shared__ int s_last;
+    double d0 = 0.0, d1 = 0.0;
+    const typename Body::S sc = body.scalars();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        typename Body::L l0, l1, l2, l3;
+        body.load(i, l0); body.load(i + stride, l1); body.load(i + 2 * stride, l2); body.load(i + 3 * stride, l3);
+        body.apply(i, l0, sc, d0, d1); body.apply(i + stride, l1, sc, d0, d1);
+        body.apply(i + 2 * stride, l2, sc, d0, d1); body.apply(i + 3 * stride, l3, sc, d0, d1);
+    }
+    for (; i < n; i += stride) {
+        typename Body::L l0;
+        body.load(i, l0);
+        body.apply(i, l0, sc, d0, d1);
+    }
+    if (DOTS) {
+        d0 = block_sum(d0, red);
+        d1 = block_sum(d1, red);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = d0;
+            partials[gridDim.x + blockIdx.x] = d1;
+            __threadfence();
+            const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double a0 = 0.0, a1 = 0.0;
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += 256) {
+                a0 += __ldcg(partials + k);
+                a1 += __ldcg(partials + gridDim.x + k);
+            }
+            a0 = block_sum(a0, red);
+            a1 = block_sum(a1, red);
+            if (threadIdx.x == 0) fin(a0, a1);
+        }
+    }
+}
+
+template <int DOTS, class Body, class Final>
+int launch_vec4(int64_t n, Body body, Final fin, double *partials, unsigned int *ticket, const int *done, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int grid = kb_grid(kb_cdiv(n, 4), 256, 8);
+    k_vec4<DOTS, Body, Final><<<grid, 256, 0, s>>>(n, body, partials, ticket, done, fin);
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- hot bodies (scalars by device pointer: the single-GPU solver passes addresses inside its scalar block, the
+// partitioned solver (K9) its all-reduced values)
+struct HBiS {               // r -= alpha v
+    const double *alpha, *v; double *r;
+    struct S { double a; }; struct L { double r, v; };
+    __device__ S scalars() const { return S{alpha[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.v = __ldcs(v + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &, double &) const { r[i] = l.r - s.a * l.v; }
+};
+struct HBiUpdate {          // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
+    const double *alpha, *omega, *p, *t, *rhat; double *x, *r;
+    struct S { double a, om; }; struct L { double x, p, s, t, rh; };
+    __device__ S scalars() const { return S{alpha[0], omega[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.s = r[i]; l.t = __ldcs(t + i); l.rh = rhat[i]; }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &d1) const {
+        x[i] = l.x + (s.a * l.p + s.om * l.s);
+        const double ri = l.s - s.om * l.t;
+        r[i] = ri;
+        d0 += l.rh * ri; d1 += ri * ri;
+    }
+};
+struct HBiP {               // p = r + beta (p - omega v)
+    const double *beta, *omega, *r, *v; double *p;
+    struct S { double b, om; }; struct L { double r, p, v; };
+    __device__ S scalars() const { return S{beta[0], omega[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.p = p[i]; l.v = __ldcs(v + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &, double &) const { p[i] = l.r + s.b * (l.p - s.om * l.v); }
+};
+struct HCgUpdate {          // x += alpha p ; r -= alpha q ; d0 = <r,r>
+    const double *alpha, *p, *q; double *x, *r;
+    struct S { double a; }; struct L { double x, p, r, q; };
+    __device__ S scalars() const { return S{alpha[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.r = r[i]; l.q = __ldcs(q + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
+        x[i] = l.x + s.a * l.p;
+        const double ri = l.r - s.a * l.q;
+        r[i] = ri;
+        d0 += ri * ri;
+    }
+};
+struct HCgP {               // p = r + beta p
+    const double *beta, *r; double *p;
+    struct S { double b; }; struct L { double r, p; };
+    __device__ S scalars() const { return S{beta[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.p = p[i]; }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &, double &) const { p[i] = l.r + s.b * l.p; }
+};
 
 // SpMV launcher: persistent TMA-fed kernel when the CSR arrays are 16-byte aligned, one-shot CSR-stream kernel otherwise
 int g_force_simple_spmv = 0;
@@ -237,7 +345,7 @@ struct FinCgAlpha {         // after q = A p, d0 = <p,q>: alpha = rho / <p,q>
     }
 };
 struct BodyCgUpdate {       // x += alpha p ; r -= alpha q ; d0 = <r,r>
-    const double *sc, *p, *q; double *x, *r;
+    const double *__restrict__ sc, *__restrict__ p, *__restrict__ q; double *__restrict__ x, *__restrict__ r;
     __device__ void operator()(int64_t i, double &d0, double &) const {
         const double a = sc[S_ALPHA];
         x[i] += a * p[i];
@@ -257,7 +365,7 @@ struct FinCgBeta {          // beta = rho_new / rho ; rho = rho_new ; convergenc
     }
 };
 struct BodyCgP {            // p = r + beta p
-    const double *sc, *r; double *p;
+    const double *__restrict__ sc, *__restrict__ r; double *__restrict__ p;
     __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + sc[S_BETA] * p[i]; }
 };
 
@@ -271,7 +379,7 @@ struct FinBiAlpha {         // after v = A p, d0 = <rhat,v>: alpha = rho / <rhat
     }
 };
 struct BodyBiS {            // s = r - alpha v   (in place in r)
-    const double *sc, *v; double *r;
+    const double *__restrict__ sc, *__restrict__ v; double *__restrict__ r;
     __device__ void operator()(int64_t i, double &, double &) const { r[i] -= sc[S_ALPHA] * v[i]; }
 };
 struct FinBiOmega {         // after t = A s, d0 = <s,t>, d1 = <t,t>: omega = <t,s>/<t,t> (0 when t = 0)
@@ -279,7 +387,7 @@ struct FinBiOmega {         // after t = A s, d0 = <s,t>, d1 = <t,t>: omega = <t
     __device__ void operator()(double ts, double tt) const { sc[S_OMEGA] = tt > 0.0 ? ts / tt : 0.0; }
 };
 struct BodyBiUpdate {       // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
-    const double *sc, *p, *t, *rhat; double *x, *r;
+    const double *__restrict__ sc, *__restrict__ p, *__restrict__ t, *__restrict__ rhat; double *__restrict__ x, *__restrict__ r;
     __device__ void operator()(int64_t i, double &d0, double &d1) const {
         const double a = sc[S_ALPHA], om = sc[S_OMEGA];
         const double si = r[i];
@@ -300,7 +408,7 @@ struct FinBiBeta {          // beta = (rho_new/rho)(alpha/omega) ; rho = rho_new
     }
 };
 struct BodyBiP {            // p = r + beta (p - omega v)
-    const double *sc, *r, *v; double *p;
+    const double *__restrict__ sc, *__restrict__ r, *__restrict__ v; double *__restrict__ p;
     __device__ void operator()(int64_t i, double &, double &) const {
         p[i] = r[i] + sc[S_BETA] * (p[i] - sc[S_OMEGA] * v[i]);
     }
@@ -384,15 +492,15 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
                 if (METHOD == 0) {
                     if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, p, w.done, FinCgAlpha{w.sc, w.done}, s))) return rc;
                     if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used++ + 1], s);
-                    if ((rc = launch_vec<1>(n, BodyCgUpdate{w.sc, p, q, xh, r}, FinCgBeta{w.sc, w.done, w.iter}, w, w.done, s))) return rc;
-                    if ((rc = launch_vec<0>(n, BodyCgP{w.sc, r, p}, NoFin{}, w, w.done, s))) return rc;
+                    if ((rc = launch_vec4<1>(n, HCgUpdate{w.sc + S_ALPHA, p, q, xh, r}, FinCgBeta{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
+                    if ((rc = launch_vec4<0>(n, HCgP{w.sc + S_BETA, r, p}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
                 } else {
                     if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, rhat, w.done, FinBiAlpha{w.sc, w.done}, s))) return rc;
                     if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used++ + 1], s);
-                    if ((rc = launch_vec<0>(n, BodyBiS{w.sc, q, r}, NoFin{}, w, w.done, s))) return rc;
+                    if ((rc = launch_vec4<0>(n, HBiS{w.sc + S_ALPHA, q, r}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
                     if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, r, t, r, w.done, FinBiOmega{w.sc}, s))) return rc;
-                    if ((rc = launch_vec<1>(n, BodyBiUpdate{w.sc, p, t, rhat, xh, r}, FinBiBeta{w.sc, w.done, w.iter}, w, w.done, s))) return rc;
-                    if ((rc = launch_vec<0>(n, BodyBiP{w.sc, r, q, p}, NoFin{}, w, w.done, s))) return rc;
+                    if ((rc = launch_vec4<1>(n, HBiUpdate{w.sc + S_ALPHA, w.sc + S_OMEGA, p, t, rhat, xh, r}, FinBiBeta{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
+                    if ((rc = launch_vec4<0>(n, HBiP{w.sc + S_BETA, w.sc + S_OMEGA, r, q, p}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
                 }
             }
             if ((rc = read_state(w, &hs, s))) return rc;
@@ -523,11 +631,11 @@ namespace {
 struct FinStore { double *out; __device__ void operator()(double a, double b) const { out[0] = a; out[1] = b; } };
 struct BodyDot2 { const double *a, *b; __device__ void operator()(int64_t i, double &d0, double &d1) const { const double bi = b[i]; d0 += a[i] * bi; d1 += bi * bi; } };
 struct BodyAxpyP {          // r -= alpha v
-    const double *alpha, *v; double *r;
+    const double *__restrict__ alpha, *__restrict__ v; double *__restrict__ r;
     __device__ void operator()(int64_t i, double &, double &) const { r[i] -= alpha[0] * v[i]; }
 };
 struct BodyBiUpdateP {      // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
-    const double *alpha, *omega, *p, *t, *rhat; double *x, *r;
+    const double *__restrict__ alpha, *__restrict__ omega, *__restrict__ p, *__restrict__ t, *__restrict__ rhat; double *__restrict__ x, *__restrict__ r;
     __device__ void operator()(int64_t i, double &d0, double &d1) const {
         const double a = alpha[0], om = omega[0], si = r[i];
         x[i] += a * p[i] + om * si;
@@ -537,11 +645,11 @@ struct BodyBiUpdateP {      // x += alpha p + omega s ; r = s - omega t ; d0 = <
     }
 };
 struct BodyBiPP {           // p = r + beta (p - omega v)
-    const double *beta, *omega, *r, *v; double *p;
+    const double *__restrict__ beta, *__restrict__ omega, *__restrict__ r, *__restrict__ v; double *__restrict__ p;
     __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * (p[i] - omega[0] * v[i]); }
 };
 struct BodyCgUpdateP {      // x += alpha p ; r -= alpha q ; d0 = <r,r>
-    const double *alpha, *p, *q; double *x, *r;
+    const double *__restrict__ alpha, *__restrict__ p, *__restrict__ q; double *__restrict__ x, *__restrict__ r;
     __device__ void operator()(int64_t i, double &d0, double &) const {
         const double a = alpha[0];
         x[i] += a * p[i];
@@ -551,7 +659,7 @@ struct BodyCgUpdateP {      // x += alpha p ; r -= alpha q ; d0 = <r,r>
     }
 };
 struct BodyCgPP {           // p = r + beta p
-    const double *beta, *r; double *p;
+    const double *__restrict__ beta, *__restrict__ r; double *__restrict__ p;
     __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * p[i]; }
 };
 struct BodyMulP {           // out = a .* b
@@ -611,30 +719,31 @@ extern "C" int kb_residual(int64_t n, const double *d_b, const double *d_q, doub
 }
 extern "C" int kb_axpy_neg(int64_t n, const double *d_alpha, const double *d_v, double *d_r, void *stream) {
     if (!d_alpha || !d_v || !d_r) return KB_EINVAL;
-    return launch_vec_s<0>(n, BodyAxpyP{d_alpha, d_v, d_r}, NoFin{}, Scratch{nullptr, nullptr}, (cudaStream_t)stream);
+    return launch_vec4<0>(n, HBiS{d_alpha, d_v, d_r}, NoFin{}, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 extern "C" int kb_bicgstab_update(int64_t n, const double *d_alpha, const double *d_omega, const double *d_p,
                                   const double *d_t, const double *d_rhat, double *d_x, double *d_r, double *d_out2,
                                   void *d_scratch, void *stream) {
     if (!d_alpha || !d_omega || !d_p || !d_t || !d_rhat || !d_x || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
-    return launch_vec_s<1>(n, BodyBiUpdateP{d_alpha, d_omega, d_p, d_t, d_rhat, d_x, d_r}, FinStore{d_out2},
-                           scratch_of(d_scratch), (cudaStream_t)stream);
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_vec4<1>(n, HBiUpdate{d_alpha, d_omega, d_p, d_t, d_rhat, d_x, d_r}, FinStore{d_out2}, sc.partials, sc.ticket,
+                          nullptr, (cudaStream_t)stream);
 }
 extern "C" int kb_bicgstab_p(int64_t n, const double *d_beta, const double *d_omega, const double *d_r,
                              const double *d_v, double *d_p, void *stream) {
     if (!d_beta || !d_omega || !d_r || !d_v || !d_p) return KB_EINVAL;
-    return launch_vec_s<0>(n, BodyBiPP{d_beta, d_omega, d_r, d_v, d_p}, NoFin{}, Scratch{nullptr, nullptr},
-                           (cudaStream_t)stream);
+    return launch_vec4<0>(n, HBiP{d_beta, d_omega, d_r, d_v, d_p}, NoFin{}, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 extern "C" int kb_cg_update(int64_t n, const double *d_alpha, const double *d_p, const double *d_q, double *d_x,
                             double *d_r, double *d_out2, void *d_scratch, void *stream) {
     if (!d_alpha || !d_p || !d_q || !d_x || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
-    return launch_vec_s<1>(n, BodyCgUpdateP{d_alpha, d_p, d_q, d_x, d_r}, FinStore{d_out2}, scratch_of(d_scratch),
-                           (cudaStream_t)stream);
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_vec4<1>(n, HCgUpdate{d_alpha, d_p, d_q, d_x, d_r}, FinStore{d_out2}, sc.partials, sc.ticket, nullptr,
+                          (cudaStream_t)stream);
 }
 extern "C" int kb_cg_p(int64_t n, const double *d_beta, const double *d_r, double *d_p, void *stream) {
     if (!d_beta || !d_r || !d_p) return KB_EINVAL;
-    return launch_vec_s<0>(n, BodyCgPP{d_beta, d_r, d_p}, NoFin{}, Scratch{nullptr, nullptr}, (cudaStream_t)stream);
+    return launch_vec4<0>(n, HCgP{d_beta, d_r, d_p}, NoFin{}, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 extern "C" int kb_vec_mul(int64_t n, const double *d_a, const double *d_b, double *d_out, void *stream) {
     if (!d_a || !d_b || !d_out) return KB_EINVAL;

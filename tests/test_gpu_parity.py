@@ -474,3 +474,38 @@ def test_partitioned_transient_matches_single_gpu(theta):
     T, info = KD.run_transient(systems, comm, fs.time_increment, 12, theta=theta, rtol=1e-13)
     got = torch.cat(T).cpu().numpy()
     assert rel_l2(got, ref[:, 0]) < SOL_TOL, (info, fs.solver_info)
+
+
+# ------------------------------------------------------------------------------------------------- "next" row n1
+def test_load_increments_and_heat_source():
+    """cumulative load increments (the reference's loop crashes for L > 1, FEMSolver.py:167-228)
+    and the opt-in heat-source term (the reference assembles Flux and drops it)."""
+    from oracle import kiltro_oracle as O
+    K = _K()
+    c = STE.case("mixed_consistent")
+    m = make_mesh(c["points"], c["elements"])
+    matv = list(c["material"]); matv[4] = 7.5                      # q != 0
+    mat = material_for(matv, 2)
+
+    def solve(**kw):
+        form = K.HeatAdvectionDiffusion(m, velocity=c["velocity"])
+        bc = K.BoundaryCondition()
+        bc.SetDirichletCriteria(lambda: c["dirichlet_flags"].copy()); bc.SetNeumannCriteria(lambda: c["neumann_flags"].copy())
+        fs = K.FEMSolver(verbose=False, **kw)
+        return fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13)).sol
+
+    one = solve()
+    assert rel_l2(one, c["sol"]) < SOL_TOL                         # q does not reach the RHS by default (F6)
+    three = solve(number_of_load_increments=3)
+    assert three.shape == (m.nnodes, 1, 3)
+    for i in range(3):
+        assert rel_l2(three[:, :, i], one[:, :, 0] * (i + 1) / 3.0) < SOL_TOL
+    # with the source: RHS = -F_neumann + Flux
+    nn = m.nnodes
+    A = O.assemble(c["points"], c["elements"], c["velocity"], tuple(matv), "consistent", False, False)
+    cin, cout, td = O.dirichlet_split(c["dirichlet_flags"])
+    res = -O.neumann_fluxes(c["neumann_flags"], nn) + A["Flux"]
+    kb = O.apply_dirichlet_reduce(A["indices"], A["indptr"], A["K"], res, cin, cout, td)
+    ref = O.total_component_sol(O.linear_solve(kb[0], kb[1], kb[2], kb[3]), cin, cout, td, nn)
+    src = solve(include_heat_source=True)
+    assert rel_l2(src.ravel(), ref) < SOL_TOL and rel_l2(src.ravel(), one.ravel()) > 1e-4
