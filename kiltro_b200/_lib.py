@@ -53,6 +53,7 @@ SIGNATURES = {
     "kb_total_component_sol": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_spmv_num_blocks": (I64, [I64]),
     "kb_spmv_force_simple": (None, [I32]),
+    "kb_spmv_force_idx32": (None, [I32]),
     "kb_profile_spmv_begin": (I32, [I32]),
     "kb_profile_spmv_end": (I32, [ctypes.POINTER(I64), ctypes.POINTER(F64)]),
     "kb_spmv_partition": (I32, [I64, I64, c_vp, c_vp, c_vp]),

@@ -53,6 +53,9 @@ enum { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RES2, S_TOL2, S_AUX0, S_AUX1, S_CO
 
 struct Work {
     double *vals_hat, *scale, *v0, *v1, *v2, *v3, *v4, *v5, *partials, *sc;
+    int16_t *cols16;    // 16-bit column offsets (col - row) of the scaled copy, valid when *bandflag == 0
+    int *bandflag;      // device: set to 1 by the setup pass when some |col - row| does not fit 16 bits
+    bool use16 = false; // host copy of the decision (re-read from bandflag after setup)
     int32_t *rowblk;
     unsigned int *ticket;
     int *done;          // done[0]: 0 running, 1 converged, 2 breakdown ; done[1]: iteration at which it was set
@@ -74,6 +77,8 @@ size_t carve(Work *w, char *base, int64_t n, int64_t nnz) {
     TAKE(scale, double, n + 1);
     TAKE(v0, double, n + 1); TAKE(v1, double, n + 1); TAKE(v2, double, n + 1);
     TAKE(v3, double, n + 1); TAKE(v4, double, n + 1); TAKE(v5, double, n + 1);
+    TAKE(cols16, int16_t, nnz > 0 ? nnz + 8 : 8);
+    TAKE(bandflag, int, 4);
     TAKE(partials, double, nvec_blocks);
     TAKE(sc, double, S_COUNT);
     TAKE(rowblk, int32_t, nblk + 1);
@@ -107,12 +112,24 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_scale_matrix(int64_t n, const int32_t *__restrict__ indptr,
                                                       const int32_t *__restrict__ indices,
                                                       const double *__restrict__ vals,
-                                                      const double *__restrict__ scale, double *__restrict__ out) {
+                                                      const double *__restrict__ scale, double *__restrict__ out,
+                                                      int16_t *__restrict__ cols16 = nullptr,
+                                                      int *__restrict__ bandflag = nullptr) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool wide = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double si = MODE == 1 ? scale[i] : 1.0;
-        for (int p = indptr[i], pe = indptr[i + 1]; p < pe; ++p) out[p] = si * vals[p] * __ldg(scale + indices[p]);
+        for (int p = indptr[i], pe = indptr[i + 1]; p < pe; ++p) {
+            const int col = indices[p];
+            out[p] = si * vals[p] * __ldg(scale + col);
+            if (cols16 != nullptr) {
+                const int d = col - (int)i;
+                if (d < -32768 || d > 32767) wide = true;
+                cols16[p] = (int16_t)d;
+            }
+        }
     }
+    if (wide) *bandflag = 1;          // benign race: every writer stores the same value
 }
 
 // generic fused vector kernel: body(i) per element, optional 2 dot accumulators finalised by the last CTA
@@ -271,21 +288,31 @@ struct HCgP {               // p = r + beta p
 
 // SpMV launcher: persistent TMA-fed kernel when the CSR arrays are 16-byte aligned, one-shot CSR-stream kernel otherwise
 int g_force_simple_spmv = 0;
+int g_force_idx32 = 1;   // 16-bit column offsets are OFF by default: measured 14 % slower at 16 M rows (see spmv_tma.cuh)
 
 template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                     const int32_t *rowblk, double *partials, unsigned int *ticket, const double *x, double *y,
-                    const double *dotw, const int *done, Final fin, cudaStream_t s) {
+                    const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr) {
     const int64_t nblk = num_blocks(nnz);
-    if (!g_force_simple_spmv && tma_eligible(indptr, indices, vals)) {
+    if (!g_force_simple_spmv && indices16 != nullptr && tma_eligible(indptr, indices16, vals)) {
+        static bool configured16 = false;
+        constexpr size_t bytes = tma_smem_bytes<short>();
+        if (!configured16) {
+            KB_CUDA(cudaFuncSetAttribute(k_spmv_tma<DOTS, Final, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured16 = true;
+        }
+        k_spmv_tma<DOTS, Final, short><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, (const short *)indices16, vals,
+                                                                               rowblk, x, y, dotw, partials, ticket, done, fin);
+    } else if (!g_force_simple_spmv && tma_eligible(indptr, indices, vals)) {
         static bool configured = false;          // one flag per template instantiation
+        constexpr size_t bytes = tma_smem_bytes<int>();
         if (!configured) {
-            KB_CUDA(cudaFuncSetAttribute(k_spmv_tma<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)T_SMEM_BYTES));
+            KB_CUDA(cudaFuncSetAttribute(k_spmv_tma<DOTS, Final, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             configured = true;
         }
-        k_spmv_tma<DOTS, Final><<<tma_grid(nblk), T_THREADS, T_SMEM_BYTES, s>>>(nblk, indptr, indices, vals, rowblk, x, y,
-                                                                               dotw, partials, ticket, done, fin);
+        k_spmv_tma<DOTS, Final, int><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, indices, vals, rowblk, x, y, dotw,
+                                                                             partials, ticket, done, fin);
     } else {
         k_spmv<DOTS, Final><<<(unsigned)nblk, THREADS, 0, s>>>(n, indptr, indices, vals, rowblk, x, y, dotw, partials,
                                                               ticket, done, fin);
@@ -299,7 +326,7 @@ int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *in
                 const Work &w, const double *x, double *y, const double *dotw, const int *done, Final fin,
                 cudaStream_t s) {
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
-                                        fin, s);
+                                        fin, s, w.use16 ? w.cols16 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ functors
@@ -456,8 +483,16 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
         const int g = kb_grid(n, 256, 8);
         k_diag_scale<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale);
         KB_LAUNCH_CHECK();
-        k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat);
+        KB_CUDA(cudaMemsetAsync(w.bandflag, 0, sizeof(int) * 4, s));
+        k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat,
+                                                             g_force_idx32 ? nullptr : w.cols16, w.bandflag);
         KB_LAUNCH_CHECK();
+    }
+    if (!g_force_idx32) {   // 16-bit column offsets are used when the band fits (decided once per setup; one small readback)
+        int flag = 1;
+        KB_CUDA(cudaMemcpyAsync(&flag, w.bandflag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        KB_CUDA(cudaStreamSynchronize(s));
+        w.use16 = (flag == 0) && !g_force_idx32;
     }
     int rc;
     // xh = x / scale ; bh = scaled rhs
@@ -809,6 +844,8 @@ extern "C" int kb_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, cons
 
 /* development switch: 1 forces the one-shot (non-TMA) SpMV kernel */
 extern "C" void kb_spmv_force_simple(int on) { g_force_simple_spmv = on; }
+/* development switch: 1 keeps 32-bit column indices in the solvers even when the 16-bit offset form is available */
+extern "C" void kb_spmv_force_idx32(int on) { g_force_idx32 = on; }
 
 extern "C" size_t kb_krylov_workspace_bytes(int64_t nrows, int64_t nnz) { return carve(nullptr, nullptr, nrows, nnz); }
 
