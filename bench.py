@@ -262,6 +262,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-nodes-per-side", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--idx32", action="store_true", help="keep 32-bit column indices in the solver's SpMV (default: 16-bit "
+                    "offsets when the matrix band fits)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -285,6 +287,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
+    if args.idx32:
+        lib.kb_spmv_force_idx32(1)
 
     def barrier():
         if world > 1:

@@ -288,7 +288,7 @@ struct HCgP {               // p = r + beta p
 
 // SpMV launcher: persistent TMA-fed kernel when the CSR arrays are 16-byte aligned, one-shot CSR-stream kernel otherwise
 int g_force_simple_spmv = 0;
-int g_force_idx32 = 1;   // 16-bit column offsets are OFF by default: measured 14 % slower at 16 M rows (see spmv_tma.cuh)
+int g_force_idx32 = 0;   // 1 keeps 32-bit column indices even when the 16-bit offset form is available (kb_spmv_force_idx32)
 
 template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,

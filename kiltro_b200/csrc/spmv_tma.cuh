@@ -28,10 +28,9 @@ constexpr int T_RCAP = 1032;                     // staged row pointers per stag
 struct __align__(16) StageMeta { int r0, r1, p0, p1, pa, pcut, ra, rcut, slow, pad0, pad1, pad2; };
 
 // IDX = int: column indices as stored in the CSR; IDX = short: 16-bit offsets (col - row), available when the matrix
-// bandwidth fits (structured FE numberings do): 10 instead of 12 bytes per non-zero cross HBM.  MEASURED (16 M rows, in
-// BiCGSTAB): 0.50 ms vs 0.44 ms for 32-bit indices -- the row-strided 16-bit shared-memory reads (stride 18 B) are
-// 2-way bank-conflicted and the kernel is LSU-sensitive, so the saved HBM bytes do not pay.  Kept behind
-// kb_spmv_force_idx32(0) as an experiment; the solvers use 32-bit indices.
+// bandwidth fits (structured FE numberings do): 10 instead of 12 bytes per non-zero cross HBM.  Measured at 16 M rows
+// inside BiCGSTAB: 0.321 ms (16-bit) vs 0.352 ms (32-bit) per launch; the solvers pick the 16-bit form when every
+// |col - row| fits (checked on device while the Jacobi-scaled copy is made).
 template <class IDX>
 struct __align__(128) StageT {
     double vals[T_VCAP];
@@ -148,6 +147,12 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
         // 32 blocks instead of one per block); lane 0 arms the barriers and issues the bulk copies.
         const int lane = threadIdx.x & 31;
         const uint64_t pol_stream = policy_evict_first();
+        // Slices are widened UP to the copy granule as well whenever the extra entries still lie inside the arrays (they
+        // belong to the next row block): only the very last block of the matrix keeps a tail that consumers must fetch
+        // with ordinary loads -- otherwise every block would stall one warp on a dependent global load.
+        const int nrows_total = __ldg(rowblk + nblk);
+        const int p_lim = __ldg(indptr + nrows_total) & ~(GRAN - 1);
+        const int r_lim = (nrows_total + 1) & ~3;
         int r0 = 0, p0 = 0;
         if (nmine > 0) { r0 = __ldg(rowblk + b_begin); p0 = __ldg(indptr + r0); }
         int rn = 0, pn = 0;                                     // boundaries of blocks [base+1 .. base+32]
@@ -163,12 +168,13 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
                     Stage &st = stages[s];
                     StageMeta m;
                     m.r0 = r0; m.r1 = r1; m.p0 = p0; m.p1 = p1;
-                    m.pa = p0 & ~(GRAN - 1); m.pcut = p1 & ~(GRAN - 1);
+                    const int p1up = (p1 + GRAN - 1) & ~(GRAN - 1), r1up = (r1 + 1 + 3) & ~3;
+                    m.pa = p0 & ~(GRAN - 1); m.pcut = p1up < p_lim ? p1up : p_lim;
                     if (m.pcut < m.pa) m.pcut = m.pa;
-                    m.ra = r0 & ~3; m.rcut = (r1 + 1) & ~3;
+                    m.ra = r0 & ~3; m.rcut = r1up < r_lim ? r1up : r_lim;
                     if (m.rcut < m.ra) m.rcut = m.ra;
-                    m.slow = (p1 - m.pa) > T_VCAP ? 1 : 0;
-                    const bool rows_staged = (r1 + 1 - m.ra) <= T_RCAP && !m.slow;
+                    m.slow = (p1up - m.pa) > T_VCAP ? 1 : 0;
+                    const bool rows_staged = (r1up - m.ra) <= T_RCAP && !m.slow;
                     if (!rows_staged) m.rcut = m.ra;            // nothing staged: consumers read indptr directly
                     m.pad0 = m.pad1 = m.pad2 = 0;
                     st.meta = m;
