@@ -1,20 +1,24 @@
 // K1+K3 fused: numeric assembly with element matrices computed on chip and never written to HBM.
 //
 // Replaces the element loop of FiniteElements/Assembly.py:46-72 (GetElementalMatrices -> scatter-add into CSR data ->
-// Flux) for the whole mesh in one launch.  One CTA per tile of the plan (tileplan.cuh):
-//   phase A  one thread per incident element: gather connectivity / coordinates / velocity (vector loads, L1-shared
-//            between neighbours), evaluate the fp64 2x2-Gauss element matrix in registers (element.cuh), park it in
-//            shared memory;
-//   phase B  one thread per owned row: walk the row's (element, local node) pairs in ascending element order -- the
-//            order of the reference's sequential `+=` -- and add the element row into the row's CSR slots held in
-//            shared memory (positions precomputed by the symbolic phase; no atomics, no searching, deterministic);
+// Flux) for the whole mesh in one launch.  Persistent CTAs (2 per SM) walk the tiles of the plan (tileplan.cuh); per tile:
+//   phase A  one thread per incident element: the nodal coordinates / velocities were gathered into shared memory by
+//            cp.async (LDGSTS) while the PREVIOUS tile was being processed; the thread evaluates the fp64 2x2-Gauss
+//            element matrix in registers (element.cuh) and parks it in shared memory component-major; it then starts
+//            the gathers of its element of the NEXT tile into the same staging slots;
+//   phase B  one thread per owned row: walks the row's (element, local node, slot positions) records in ascending
+//            element order -- the order of the reference's sequential `+=` (Assembly.py:46,60-61) -- and adds the
+//            element row into the row's CSR slots held in shared memory (positions precomputed by the symbolic phase;
+//            no atomics, no searching, deterministic);
 //   phase C  the tile's CSR values leave through coalesced streaming stores (a tile's rows are runs of consecutive
 //            rows, so its entries are long contiguous pieces of K.data).
-// The mass matrix (transient) reuses the same shared buffers in a second pass over phases B and C.
+// (A thread-per-entry phase B without the shared read-modify-write was tried: 2.9 ms instead of 1.6 ms at 16 M DOF --
+// more instructions in an issue-bound kernel.)
+// Row metadata (row ids, pair ranges, first records) of the next tile is fetched one tile ahead too, so no phase waits
+// on a dependent global load.  The mass matrix (transient) is a second pass of phase B over the same buffers.
 //
-// HBM traffic per launch is the mesh (connectivity, coordinates, velocity: read ~1.14x because of the tile rim), the
-// plan (4 B per (row, element) pair + 12 B per row) and one write of K.data; column indices are not read at all.
-// The kernel is co-limited by the FP64 pipe (~400 DFMA per element) and HBM; see DESIGN.md for the roofline.
+// HBM traffic per launch: the mesh (coordinates / velocity through the tile-local connectivity copy, ~1.14x because of
+// the tile rim), the plan (4 B per (row, element) pair + 12 B per row) and one write of K.data; `indices` is not read.
 #include "element.cuh"
 #include "tileplan.cuh"
 
@@ -25,59 +29,71 @@ ElemOpts kb_make_opts(const kb_material *m, int mode, int petrov, int want_mass)
 
 namespace {
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int NDIM> struct ElemIO;
 template <> struct ElemIO<2> {
     static constexpr int NPE = 4;
+    static constexpr int STAGE_DOUBLES = 16;          // per element: 4 nodes x (x,y) + 4 nodes x (ux,uy)
     typedef int4 Conn;
     static __device__ __forceinline__ Conn load_conn(const int32_t *tile_conn, int e) {
         return __ldg(reinterpret_cast<const int4 *>(tile_conn) + e);
     }
+    // staging layout: chunk-major double2 [8][EMAX] -> consecutive threads touch consecutive 16-byte words
     template <bool HAS_U>
-    static __device__ __forceinline__ void prefetch(const double *points, const double *velocity, const Conn &c) {
+    static __device__ __forceinline__ void gather_async(double *stage, int tid, const double *points,
+                                                        const double *velocity, const Conn &c) {
         const int n[4] = {c.x, c.y, c.z, c.w};
+        double2 *s2 = reinterpret_cast<double2 *>(stage);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            prefetch_l1(reinterpret_cast<const double2 *>(points) + n[a]);
-            if (HAS_U) prefetch_l1(reinterpret_cast<const double2 *>(velocity) + n[a]);
+            cp_async16(s2 + a * EMAX + tid, reinterpret_cast<const double2 *>(points) + n[a]);
+            if (HAS_U) cp_async16(s2 + (4 + a) * EMAX + tid, reinterpret_cast<const double2 *>(velocity) + n[a]);
         }
     }
     template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *points, const double *velocity, const Conn &c,
-                                                const ElemOpts &o, double (&ke)[16], double (&fe)[4],
-                                                double (&me)[16]) {
-        const int n[4] = {c.x, c.y, c.z, c.w};
+    static __device__ __forceinline__ void eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[16],
+                                                double (&fe)[4], double (&me)[16]) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(stage);
         double X[4][2], U[4][2];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const double2 p = __ldg(reinterpret_cast<const double2 *>(points) + n[a]);
+            const double2 p = s2[a * EMAX + tid];
             X[a][0] = p.x; X[a][1] = p.y;
-            if (HAS_U) {
-                const double2 u = __ldg(reinterpret_cast<const double2 *>(velocity) + n[a]);
-                U[a][0] = u.x; U[a][1] = u.y;
-            } else { U[a][0] = 0.0; U[a][1] = 0.0; }
+            if (HAS_U) { const double2 u = s2[(4 + a) * EMAX + tid]; U[a][0] = u.x; U[a][1] = u.y; }
+            else { U[a][0] = 0.0; U[a][1] = 0.0; }
         }
         quad4(X, U, o, ke, fe, me);
     }
 };
 template <> struct ElemIO<1> {
     static constexpr int NPE = 2;
+    static constexpr int STAGE_DOUBLES = 4;
     typedef int2 Conn;
     static __device__ __forceinline__ Conn load_conn(const int32_t *tile_conn, int e) {
         return __ldg(reinterpret_cast<const int2 *>(tile_conn) + e);
     }
     template <bool HAS_U>
-    static __device__ __forceinline__ void prefetch(const double *points, const double *velocity, const Conn &c) {
-        prefetch_l1(points + c.x); prefetch_l1(points + c.y);
-        if (HAS_U) { prefetch_l1(velocity + c.x); prefetch_l1(velocity + c.y); }
+    static __device__ __forceinline__ void gather_async(double *stage, int tid, const double *points,
+                                                        const double *velocity, const Conn &c) {
+        cp_async8(stage + 0 * EMAX + tid, points + c.x);
+        cp_async8(stage + 1 * EMAX + tid, points + c.y);
+        if (HAS_U) { cp_async8(stage + 2 * EMAX + tid, velocity + c.x); cp_async8(stage + 3 * EMAX + tid, velocity + c.y); }
     }
     template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *points, const double *velocity, const Conn &c,
-                                                const ElemOpts &o, double (&ke)[4], double (&fe)[2], double (&me)[4]) {
-        double X[2] = {__ldg(points + c.x), __ldg(points + c.y)};
+    static __device__ __forceinline__ void eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[4],
+                                                double (&fe)[2], double (&me)[4]) {
+        double X[2] = {stage[0 * EMAX + tid], stage[1 * EMAX + tid]};
         double U[2] = {0.0, 0.0};
-        if (HAS_U) { U[0] = __ldg(velocity + c.x); U[1] = __ldg(velocity + c.y); }
+        if (HAS_U) { U[0] = stage[2 * EMAX + tid]; U[1] = stage[3 * EMAX + tid]; }
         line2(X, U, o, ke, fe, me);
     }
 };
@@ -91,70 +107,106 @@ __device__ __forceinline__ int lower_bound_g(const int32_t *a, int n, int v) {
     return lo;
 }
 
+// shared-memory carve-up (bytes) -- also used by the launcher
+template <int NDIM> struct Smem {
+    static constexpr int NPE = ElemIO<NDIM>::NPE, CAP = NPE * NPE;
+    static constexpr size_t oKe = 0;
+    static constexpr size_t oFe = oKe + 8 * (size_t)EMAX * CAP;
+    static constexpr size_t oStage = oFe + 8 * (size_t)EMAX * NPE;
+    static constexpr size_t oV = oStage + 8 * (size_t)EMAX * ElemIO<NDIM>::STAGE_DOUBLES;
+    static constexpr size_t oDelta = oV + 8 * (size_t)VMAX;
+    static constexpr size_t oE2R = oDelta + 4 * (size_t)RMAX;
+    static constexpr size_t oScan = oE2R + 2 * (size_t)VMAX;
+    static constexpr size_t bytes = oScan + 4 * 64;
+};
+
 template <int NDIM, bool HAS_U, bool MASS>
 __global__ void __launch_bounds__(THREADS, 2)
 k_assemble_fused(const double *__restrict__ points, const double *__restrict__ velocity, ElemOpts o,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                  const int32_t *__restrict__ tile_rows, const int32_t *__restrict__ tile_row_ptr,
-                 const int32_t *__restrict__ tile_conn,
-                 const int32_t *__restrict__ tile_elem_ptr, const uint32_t *__restrict__ pair_rec,
-                 const int32_t *__restrict__ pair_ptr, double *__restrict__ K, double *__restrict__ M,
-                 double *__restrict__ Flux, int ntiles) {
+                 const int32_t *__restrict__ tile_conn, const int32_t *__restrict__ tile_elem_ptr,
+                 const uint32_t *__restrict__ pair_rec, const int32_t *__restrict__ pair_ptr, double *__restrict__ K,
+                 double *__restrict__ M, double *__restrict__ Flux, int ntiles) {
     constexpr int NPE = ElemIO<NDIM>::NPE, CAP = NPE * NPE;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sKe = reinterpret_cast<double *>(smem_raw);                 // [EMAX * CAP]
-    double *sFe = sKe + EMAX * CAP;                                     // [EMAX * NPE]
-    double *sV = sFe + EMAX * NPE;                                      // [VMAX]
-    unsigned short *sE2R = reinterpret_cast<unsigned short *>(sV + VMAX);   // [VMAX]
-    int *sDelta = reinterpret_cast<int *>(sE2R + VMAX);                 // [RMAX]
-    int *sScan = sDelta + RMAX;                                         // [64]
-
+    typedef Smem<NDIM> L;
     typedef typename ElemIO<NDIM>::Conn Conn;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sKe = reinterpret_cast<double *>(smem_raw + L::oKe);        // [CAP][EMAX] component-major
+    double *sFe = reinterpret_cast<double *>(smem_raw + L::oFe);        // [NPE][EMAX]
+    double *sStage = reinterpret_cast<double *>(smem_raw + L::oStage);  // cp.async landing zone of the gathers
+    double *sV = reinterpret_cast<double *>(smem_raw + L::oV);          // CSR values of the tile's rows
+    int *sDelta = reinterpret_cast<int *>(smem_raw + L::oDelta);        // global position - local position
+    unsigned short *sE2R = reinterpret_cast<unsigned short *>(smem_raw + L::oE2R);   // local entry -> local row
+    int *sScan = reinterpret_cast<int *>(smem_raw + L::oScan);
+
     const int tid = threadIdx.x;
     int t = blockIdx.x;
     if (t >= ntiles) return;
-    // Persistent CTA: tiles t, t+grid, t+2*grid, ...  The next tile's extents and this thread's next element
-    // connectivity are fetched one tile ahead and the node data they point to are pulled into L1 (prefetch.global.L1),
-    // so the element phase of the next tile starts on L1 hits instead of a three-deep chain of DRAM round trips.
+
+    // ---- prologue: everything the first tile needs
     int rb = __ldg(tile_row_ptr + t), nr = __ldg(tile_row_ptr + t + 1) - rb;
     int eb = __ldg(tile_elem_ptr + t), ne = __ldg(tile_elem_ptr + t + 1) - eb;
-    Conn conn = ElemIO<NDIM>::load_conn(tile_conn, eb + (tid < ne ? tid : 0));
+    if (tid < ne) {
+        const Conn c = ElemIO<NDIM>::load_conn(tile_conn, eb + tid);
+        ElemIO<NDIM>::template gather_async<HAS_U>(sStage, tid, points, velocity, c);
+    }
+    cp_async_commit();
+    int row = 0, jp0 = 0, jp1 = 0;
+    if (tid < nr) {
+        row = __ldg(tile_rows + rb + tid);
+        jp0 = __ldg(pair_ptr + rb + tid);
+        jp1 = __ldg(pair_ptr + rb + tid + 1);
+    }
 
     for (; t < ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x;
+        // extents of the next tile (consumed after phase A)
         int rb_n = 0, nr_n = 0, eb_n = 0, ne_n = 0;
         if (tn < ntiles) {
             rb_n = __ldg(tile_row_ptr + tn); nr_n = __ldg(tile_row_ptr + tn + 1) - rb_n;
             eb_n = __ldg(tile_elem_ptr + tn); ne_n = __ldg(tile_elem_ptr + tn + 1) - eb_n;
         }
-        // ---- row metadata first: these loads overlap the element phase
-        int row = -1, p0 = 0, len = 0, jp0 = 0, jp1 = 0;
+        // second-level row metadata of THIS tile: addresses were fetched a tile ago, results are used after phase A
+        int p0 = 0, p1 = 0;
+        uint4 rec4 = make_uint4(0u, 0u, 0u, 0u);
         if (tid < nr) {
-            row = __ldg(tile_rows + rb + tid);
-            jp0 = __ldg(pair_ptr + rb + tid);
-            jp1 = __ldg(pair_ptr + rb + tid + 1);
             p0 = __ldg(indptr + row);
-            len = __ldg(indptr + row + 1) - p0;
+            p1 = __ldg(indptr + row + 1);
+            const int np = jp1 - jp0;
+            if (np > 0) rec4.x = __ldg(pair_rec + jp0);
+            if (np > 1) rec4.y = __ldg(pair_rec + jp0 + 1);
+            if (np > 2) rec4.z = __ldg(pair_rec + jp0 + 2);
+            if (np > 3) rec4.w = __ldg(pair_rec + jp0 + 3);
         }
-        uint32_t rec4[4] = {0u, 0u, 0u, 0u};             // the first four (row, element) records (a quad-4 node has <= 4)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (jp0 + k < jp1) rec4[k] = __ldg(pair_rec + jp0 + k);
 
-        // ---- phase A: element matrices -> shared memory, component-major (sKe[i][slot]: conflict-free stores and reads)
+        // ---- phase A: element matrices -> shared memory, component-major (conflict-free stores and reads)
+        cp_async_wait_all();                              // this thread's gathers (issued one tile ago) have landed
         double me[CAP];
         if (tid < ne) {
             double ke[CAP], fe[NPE];
-            ElemIO<NDIM>::template eval<HAS_U, MASS>(points, velocity, conn, o, ke, fe, me);
+            ElemIO<NDIM>::template eval<HAS_U, MASS>(sStage, tid, o, ke, fe, me);
 #pragma unroll
             for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = ke[i];
 #pragma unroll
             for (int i = 0; i < NPE; ++i) sFe[i * EMAX + tid] = fe[i];
         }
-        // connectivity of this thread's element in the NEXT tile (consumed after phase B)
-        Conn conn_n = conn;
-        if (tn < ntiles) conn_n = ElemIO<NDIM>::load_conn(tile_conn, eb_n + (tid < ne_n ? tid : 0));
+        // the staging slots of this thread are free again: start the gathers of its element of the next tile
+        if (tn < ntiles && tid < ne_n) {
+            const Conn c = ElemIO<NDIM>::load_conn(tile_conn, eb_n + tid);
+            ElemIO<NDIM>::template gather_async<HAS_U>(sStage, tid, points, velocity, c);
+        }
+        cp_async_commit();
+        // first-level row metadata of the next tile
+        int row_n = 0, jp0_n = 0, jp1_n = 0;
+        if (tn < ntiles && tid < nr_n) {
+            row_n = __ldg(tile_rows + rb_n + tid);
+            jp0_n = __ldg(pair_ptr + rb_n + tid);
+            jp1_n = __ldg(pair_ptr + rb_n + tid + 1);
+        }
 
+        // ---- row bookkeeping of this tile: local offsets (block scan of the row lengths), entry -> row map
+        const int len = tid < nr ? p1 - p0 : 0;
         int total;
         const int off = block_scan_excl(len, sScan, &total);
         if (tid < nr) {
@@ -171,9 +223,8 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
                 double f = 0.0;
                 for (int j = jp0; j < jp1; ++j) {
                     const int k4 = j - jp0;
-                    uint32_t rec;
-                    if (k4 < 4) rec = k4 == 0 ? rec4[0] : k4 == 1 ? rec4[1] : k4 == 2 ? rec4[2] : rec4[3];
-                    else rec = __ldg(pair_rec + j);
+                    const uint32_t rec = k4 == 0 ? rec4.x : k4 == 1 ? rec4.y : k4 == 2 ? rec4.z : k4 == 3 ? rec4.w
+                                                                                               : __ldg(pair_rec + j);
                     const int slot = (int)((rec >> 18) & 0x1fffu), a = (int)((rec >> 16) & 3u);
                     const double *src = &sKe[(a * NPE) * EMAX + slot];
                     if (!(rec & 0x80000000u)) {
@@ -185,12 +236,11 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
                             sV[off + lower_bound_g(indices + p0, len, __ldg(tile_conn + (int64_t)(eb + slot) * NPE + b))] +=
                                 src[b * EMAX];
                     }
-                    if (pass == 0) f += sFe[a * EMAX + slot];
+                    if (pass == 0) f += sFe[a * EMAX + slot];         // source vector                Assembly.py:69-72
                 }
                 if (pass == 0) Flux[row] = f;
             }
             __syncthreads();
-            if (pass == 0 && tn < ntiles && tid < ne_n) ElemIO<NDIM>::template prefetch<HAS_U>(points, velocity, conn_n);
             // ---- phase C: coalesced write-out
             double *out = pass == 0 ? K : M;
             for (int i = tid; i < total; i += THREADS) __stcs(out + i + sDelta[sE2R[i]], sV[i]);
@@ -205,22 +255,18 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
             }
         }
         __syncthreads();                                  // the next tile overwrites the shared buffers
-        rb = rb_n; nr = nr_n; eb = eb_n; ne = ne_n; conn = conn_n;
+        rb = rb_n; nr = nr_n; eb = eb_n; ne = ne_n;
+        row = row_n; jp0 = jp0_n; jp1 = jp1_n;
     }
 }
 
-template <int NDIM> constexpr size_t fused_smem_bytes() {
-    return 8 * (size_t)(EMAX * ElemIO<NDIM>::NPE * ElemIO<NDIM>::NPE + EMAX * ElemIO<NDIM>::NPE + VMAX) + 2 * (size_t)VMAX +
-           4 * (size_t)RMAX + 4 * 64;
-}
-
 template <int NDIM, bool HAS_U, bool MASS>
-int launch_fused(int64_t ntiles, cudaStream_t s, const double *points, const double *velocity,
-                 const ElemOpts &o, const int32_t *indptr, const int32_t *indices, const int32_t *tile_rows,
-                 const int32_t *tile_row_ptr, const int32_t *tile_conn, const int32_t *tile_elem_ptr,
-                 const uint32_t *pair_rec, const int32_t *pair_ptr, double *K, double *M, double *Flux) {
+int launch_fused(int64_t ntiles, cudaStream_t s, const double *points, const double *velocity, const ElemOpts &o,
+                 const int32_t *indptr, const int32_t *indices, const int32_t *tile_rows, const int32_t *tile_row_ptr,
+                 const int32_t *tile_conn, const int32_t *tile_elem_ptr, const uint32_t *pair_rec,
+                 const int32_t *pair_ptr, double *K, double *M, double *Flux) {
     static bool configured = false;
-    constexpr size_t bytes = fused_smem_bytes<NDIM>();
+    constexpr size_t bytes = Smem<NDIM>::bytes;
     if (!configured) {
         KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)bytes));
@@ -252,7 +298,7 @@ extern "C" int kb_assemble_fused(int ndim, const double *d_points, const int32_t
     if (ntiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const ElemOpts o = kb_make_opts(material, mode, petrov, d_M != nullptr);
-#define KB_FUSED(ND, HU, MS)                                                                                     \
+#define KB_FUSED(ND, HU, MS)                                                                                      \
     return launch_fused<ND, HU, MS>(ntiles, s, d_points, d_velocity, o, d_indptr, d_indices, d_tile_rows,            \
                                     d_tile_row_ptr, d_tile_conn, d_tile_elem_ptr, d_pair_rec, d_pair_ptr, d_K, d_M,    \
                                     d_Flux)
