@@ -372,7 +372,11 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "avg_launch_ms": spmv_ms, "launches_timed": int(ns.value),
-                "algorithmic_bytes_per_launch": algorithmic_bytes_spmv(nfree, nnz_b)}
+                "algorithmic_bytes_per_launch": algorithmic_bytes_spmv(nfree, nnz_b),
+                "note": "achieved = SURVEY 8(d) algorithmic bytes (12 B/nnz + 20 B/row) / CUDA-event time of the SpMV launches "
+                        "inside the timed solver loop; the kernel stores column indices as 16-bit row offsets when the band "
+                        "fits (%s here), so fewer bytes than the algorithmic count actually cross HBM (see traffic)"
+                        % ("32-bit forced" if args.idx32 else "16-bit")}
 
     # ---- e2e: same step from pinned host buffers in the reference's array formats
     e2e = None
