@@ -66,7 +66,7 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t carve(Work *w, char *base, int64_t n, int64_t nnz) {
     const int64_t nblk = num_blocks(nnz);
-    const int64_t nvec_blocks = 2 * (int64_t)kb_num_sms() * 8 + 2 * nblk + 64;
+    const int64_t nvec_blocks = 4 * (int64_t)kb_num_sms() * 8 + 4 * nblk + 64;
     size_t off = 0;
 #define TAKE(field, type, count)                                  \
     do {                                                          \
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_vec(int64_t n, Body body, double *__res
     }
 }
 
-struct NoFin { __device__ void operator()(double, double) const {} };
+struct NoFin { __device__ void operator()(double, double, double = 0.0, double = 0.0) const {} };
 
 template <int DOTS, class Body, class Final>
 int launch_vec(int64_t n, Body body, Final fin, const Work &w, const int *done, cudaStream_t s) {
@@ -259,6 +259,19 @@ struct HBiUpdate {          // x += alpha p + omega s ; r = s - omega t ; d0 = <
         d0 += l.rh * ri; d1 += ri * ri;
     }
 };
+struct HBiUpdateP {         // x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; d0 = <r,r>
+    const double *alpha, *omega, *beta, *t, *v; double *x, *r, *p;
+    struct S { double a, om, b; }; struct L { double x, p, s, t, v; };
+    __device__ S scalars() const { return S{alpha[0], omega[0], beta[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.s = r[i]; l.t = __ldcs(t + i); l.v = __ldcs(v + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
+        x[i] = l.x + (s.a * l.p + s.om * l.s);
+        const double ri = l.s - s.om * l.t;
+        r[i] = ri;
+        p[i] = ri + s.b * (l.p - s.om * l.v);
+        d0 += ri * ri;
+    }
+};
 struct HBiP {               // p = r + beta (p - omega v)
     const double *beta, *omega, *r, *v; double *p;
     struct S { double b, om; }; struct L { double r, p, v; };
@@ -293,7 +306,8 @@ int g_force_idx32 = 0;   // 1 keeps 32-bit column indices even when the 16-bit o
 template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                     const int32_t *rowblk, double *partials, unsigned int *ticket, const double *x, double *y,
-                    const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr) {
+                    const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr,
+                    const double *dotw2 = nullptr) {
     const int64_t nblk = num_blocks(nnz);
     if (!g_force_simple_spmv && indices16 != nullptr && tma_eligible(indptr, indices16, vals)) {
         static bool configured16 = false;
@@ -303,7 +317,8 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
             configured16 = true;
         }
         k_spmv_tma<DOTS, Final, short><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, (const short *)indices16, vals,
-                                                                               rowblk, x, y, dotw, partials, ticket, done, fin);
+                                                                               rowblk, x, y, dotw, partials, ticket, done, fin,
+                                                                               dotw2);
     } else if (!g_force_simple_spmv && tma_eligible(indptr, indices, vals)) {
         static bool configured = false;          // one flag per template instantiation
         constexpr size_t bytes = tma_smem_bytes<int>();
@@ -312,10 +327,10 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
             configured = true;
         }
         k_spmv_tma<DOTS, Final, int><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, indices, vals, rowblk, x, y, dotw,
-                                                                             partials, ticket, done, fin);
+                                                                             partials, ticket, done, fin, dotw2);
     } else {
         k_spmv<DOTS, Final><<<(unsigned)nblk, THREADS, 0, s>>>(n, indptr, indices, vals, rowblk, x, y, dotw, partials,
-                                                              ticket, done, fin);
+                                                              ticket, done, fin, dotw2);
     }
     KB_LAUNCH_CHECK();
     return 0;
@@ -324,9 +339,9 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
 template <int DOTS, class Final>
 int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                 const Work &w, const double *x, double *y, const double *dotw, const int *done, Final fin,
-                cudaStream_t s) {
+                cudaStream_t s, const double *dotw2 = nullptr) {
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
-                                        fin, s, w.use16 ? w.cols16 : nullptr);
+                                        fin, s, w.use16 ? w.cols16 : nullptr, dotw2);
 }
 
 // ------------------------------------------------------------------------------------------------ functors
@@ -349,7 +364,7 @@ struct BodyResidual {       // r = b - q ; p = r ; rhat = r ; d0 = <r,r> ; d1 = 
 };
 struct FinInit {            // rho = <r,r> ; tol2 = max(rtol^2 <b,b>, tiny) ; done if already converged
     double *sc; int *done; double rtol2;
-    __device__ void operator()(double rr, double bb) const {
+    __device__ void operator()(double rr, double bb, double = 0.0, double = 0.0) const {
         sc[S_RHO] = rr; sc[S_RES2] = rr; sc[S_AUX0] = bb;
         const double tol2 = rtol2 * bb;
         sc[S_TOL2] = tol2;
@@ -365,7 +380,7 @@ struct BodyUnscale {        // x = xh * scale
 // ---- CG
 struct FinCgAlpha {         // after q = A p, d0 = <p,q>: alpha = rho / <p,q>
     double *sc; int *done;
-    __device__ void operator()(double pq, double) const {
+    __device__ void operator()(double pq, double, double = 0.0, double = 0.0) const {
         const double a = sc[S_RHO] / pq;
         sc[S_ALPHA] = a;
         if (!isfinite(a) || pq == 0.0) done[0] = 2;
@@ -383,7 +398,7 @@ struct BodyCgUpdate {       // x += alpha p ; r -= alpha q ; d0 = <r,r>
 };
 struct FinCgBeta {          // beta = rho_new / rho ; rho = rho_new ; convergence test ; iteration count
     double *sc; int *done; int *iter;
-    __device__ void operator()(double rr, double) const {
+    __device__ void operator()(double rr, double, double = 0.0, double = 0.0) const {
         sc[S_BETA] = rr / sc[S_RHO];
         sc[S_RHO] = rr; sc[S_RES2] = rr;
         const int it = ++iter[0];
@@ -399,7 +414,7 @@ struct BodyCgP {            // p = r + beta p
 // ---- BiCGSTAB
 struct FinBiAlpha {         // after v = A p, d0 = <rhat,v>: alpha = rho / <rhat,v>
     double *sc; int *done;
-    __device__ void operator()(double rv, double) const {
+    __device__ void operator()(double rv, double, double = 0.0, double = 0.0) const {
         const double a = sc[S_RHO] / rv;
         sc[S_ALPHA] = a;
         if (!isfinite(a) || rv == 0.0) done[0] = 2;
@@ -411,7 +426,7 @@ struct BodyBiS {            // s = r - alpha v   (in place in r)
 };
 struct FinBiOmega {         // after t = A s, d0 = <s,t>, d1 = <t,t>: omega = <t,s>/<t,t> (0 when t = 0)
     double *sc;
-    __device__ void operator()(double ts, double tt) const { sc[S_OMEGA] = tt > 0.0 ? ts / tt : 0.0; }
+    __device__ void operator()(double ts, double tt, double = 0.0, double = 0.0) const { sc[S_OMEGA] = tt > 0.0 ? ts / tt : 0.0; }
 };
 struct BodyBiUpdate {       // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
     const double *__restrict__ sc, *__restrict__ p, *__restrict__ t, *__restrict__ rhat; double *__restrict__ x, *__restrict__ r;
@@ -424,9 +439,31 @@ struct BodyBiUpdate {       // x += alpha p + omega s ; r = s - omega t ; d0 = <
         d0 += rhat[i] * ri; d1 += ri * ri;
     }
 };
+// Merged update (one vector kernel instead of two): with <rhat,t> and <rhat,s> taken in the epilogue of t = A s,
+// rho_new = <rhat, s - omega t> = <rhat,s> - omega <rhat,t> is known BEFORE x and r are updated, so beta is too and
+// p = r + beta (p - omega v) rides along with the x/r update (64 n bytes instead of 56 n + 32 n).
+struct FinBiOmega2 {        // d = {<s,t>, <t,t>, <rhat,t>, <rhat,s>}
+    double *sc; int *done; int *iter;
+    __device__ void operator()(double ts, double tt, double rt, double rs) const {
+        const double om = tt > 0.0 ? ts / tt : 0.0;
+        const double rho_new = rs - om * rt;
+        const double beta = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / om);
+        sc[S_OMEGA] = om; sc[S_BETA] = beta; sc[S_RHO] = rho_new;
+        sc[S_AUX1] = (isfinite(beta) && rho_new != 0.0 && om != 0.0) ? 0.0 : 1.0;     // breakdown unless converged below
+    }
+};
+struct FinBiRes {           // after the merged update: d0 = <r,r>
+    double *sc; int *done; int *iter;
+    __device__ void operator()(double rr, double, double = 0.0, double = 0.0) const {
+        sc[S_RES2] = rr;
+        const int it = ++iter[0];
+        if (!(rr > sc[S_TOL2]) && isfinite(rr)) { done[0] = 1; done[1] = it; }
+        else if (!isfinite(rr) || sc[S_AUX1] != 0.0) { done[0] = 2; done[1] = it; }
+    }
+};
 struct FinBiBeta {          // beta = (rho_new/rho)(alpha/omega) ; rho = rho_new ; convergence / breakdown ; iteration count
     double *sc; int *done; int *iter;
-    __device__ void operator()(double rho_new, double rr) const {
+    __device__ void operator()(double rho_new, double rr, double = 0.0, double = 0.0) const {
         const double beta = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
         sc[S_BETA] = beta; sc[S_RHO] = rho_new; sc[S_RES2] = rr;
         const int it = ++iter[0];
@@ -533,9 +570,8 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
                     if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, rhat, w.done, FinBiAlpha{w.sc, w.done}, s))) return rc;
                     if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used++ + 1], s);
                     if ((rc = launch_vec4<0>(n, HBiS{w.sc + S_ALPHA, q, r}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
-                    if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, r, t, r, w.done, FinBiOmega{w.sc}, s))) return rc;
-                    if ((rc = launch_vec4<1>(n, HBiUpdate{w.sc + S_ALPHA, w.sc + S_OMEGA, p, t, rhat, xh, r}, FinBiBeta{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
-                    if ((rc = launch_vec4<0>(n, HBiP{w.sc + S_BETA, w.sc + S_OMEGA, r, q, p}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
+                    if ((rc = launch_spmv<2>(n, nnz, indptr, indices, w.vals_hat, w, r, t, r, w.done, FinBiOmega2{w.sc, w.done, w.iter}, s, rhat))) return rc;
+                    if ((rc = launch_vec4<1>(n, HBiUpdateP{w.sc + S_ALPHA, w.sc + S_OMEGA, w.sc + S_BETA, t, q, xh, r, p}, FinBiRes{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
                 }
             }
             if ((rc = read_state(w, &hs, s))) return rc;
@@ -663,7 +699,7 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
 // driven from the host side when a collective sits between a dot product and its use (row-block partitioned multi-GPU
 // solve, kiltro_b200/distributed.py): local partial dots come back in d_out2 (2 doubles) and are all-reduced by the caller.
 namespace {
-struct FinStore { double *out; __device__ void operator()(double a, double b) const { out[0] = a; out[1] = b; } };
+struct FinStore { double *out; __device__ void operator()(double a, double b, double = 0.0, double = 0.0) const { out[0] = a; out[1] = b; } };
 struct BodyDot2 { const double *a, *b; __device__ void operator()(int64_t i, double &d0, double &d1) const { const double bi = b[i]; d0 += a[i] * bi; d1 += bi * bi; } };
 struct BodyAxpyP {          // r -= alpha v
     const double *__restrict__ alpha, *__restrict__ v; double *__restrict__ r;

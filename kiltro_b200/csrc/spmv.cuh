@@ -38,7 +38,7 @@ static __global__ void __launch_bounds__(256) k_partition(int64_t nrows, int64_t
 }
 
 struct NoFinal {
-    __device__ void operator()(double, double) const {}
+    __device__ void operator()(double, double, double = 0.0, double = 0.0) const {}
 };
 
 // DOTS: 0 none, 1 = <w,y> and <y,y>.  Final(d0, d1) runs in exactly one thread after all CTAs contributed.
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv(int64_t nrows, const int32_t *
                                                   const double *__restrict__ x, double *__restrict__ y,
                                                   const double *__restrict__ w, double *__restrict__ partials,
                                                   unsigned int *__restrict__ ticket, const int *__restrict__ done,
-                                                  Final fin) {
+                                                  Final fin, const double *__restrict__ w2 = nullptr) {
     if (done != nullptr && *done != 0) return;
     __shared__ double prod[NNZ_SMEM];
     __shared__ double red[32];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv(int64_t nrows, const int32_t *
     const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
     const int p0 = indptr[r0], p1 = indptr[r1];
     const int cnt = p1 - p0;
-    double d0 = 0.0, d1 = 0.0;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
     if (cnt <= NNZ_SMEM) {
         // phase 1: nnz-parallel products, 4 independent loads in flight per thread
         int k = threadIdx.x;
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv(int64_t nrows, const int32_t *
             for (int q = a; q < b; ++q) s += prod[q];
             y[r] = s;
             if (DOTS) { d0 += __ldg(w + r) * s; d1 += s * s; }
+            if (DOTS == 2) { d2 += __ldg(w2 + r) * s; d3 += __ldg(w2 + r) * __ldg(w + r); }
         }
     } else {
         // slow path: the CTA walks its rows one at a time
@@ -91,15 +92,18 @@ __global__ void __launch_bounds__(THREADS) k_spmv(int64_t nrows, const int32_t *
             if (threadIdx.x == 0) {
                 y[r] = s;
                 if (DOTS) { d0 += __ldg(w + r) * s; d1 += s * s; }
+                if (DOTS == 2) { d2 += __ldg(w2 + r) * s; d3 += __ldg(w2 + r) * __ldg(w + r); }
             }
         }
     }
     if (DOTS) {
         d0 = block_sum(d0, red);
         d1 = block_sum(d1, red);
+        if (DOTS == 2) { d2 = block_sum(d2, red); d3 = block_sum(d3, red); }
         if (threadIdx.x == 0) {
             partials[blockIdx.x] = d0;
             partials[gridDim.x + blockIdx.x] = d1;
+            if (DOTS == 2) { partials[2 * gridDim.x + blockIdx.x] = d2; partials[3 * gridDim.x + blockIdx.x] = d3; }
             __threadfence();
             const unsigned int t = atomicInc(ticket, gridDim.x - 1);     // wraps back to 0: self-resetting
             s_last = (t == gridDim.x - 1);
@@ -107,14 +111,16 @@ __global__ void __launch_bounds__(THREADS) k_spmv(int64_t nrows, const int32_t *
         __syncthreads();
         if (s_last) {
             __threadfence();
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) {
                 a0 += __ldcg(partials + i);
                 a1 += __ldcg(partials + gridDim.x + i);
+                if (DOTS == 2) { a2 += __ldcg(partials + 2 * gridDim.x + i); a3 += __ldcg(partials + 3 * gridDim.x + i); }
             }
             a0 = block_sum(a0, red);
             a1 = block_sum(a1, red);
-            if (threadIdx.x == 0) fin(a0, a1);
+            if (DOTS == 2) { a2 = block_sum(a2, red); a3 = block_sum(a3, red); }
+            if (threadIdx.x == 0) fin(a0, a1, a2, a3);
         }
     }
 }

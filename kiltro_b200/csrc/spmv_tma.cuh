@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(T_THREADS, 2)
 k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restrict__ indices,
            const double *__restrict__ vals, const int32_t *__restrict__ rowblk, const double *__restrict__ x,
            double *__restrict__ y, const double *__restrict__ w, double *__restrict__ partials,
-           unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin) {
+           unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
+           const double *__restrict__ w2 = nullptr) {
+    // DOTS: 0 none; 1 -> {<w,y>, <y,y>}; 2 -> additionally {<w2,y>, <w2,w>} (the merged BiCGSTAB update, krylov.cu)
     if (done != nullptr && *done != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef StageT<IDX> Stage;
@@ -194,7 +196,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        double d0 = 0.0, d1 = 0.0;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
         const int tid = threadIdx.x;
         const uint64_t pol_keep = policy_evict_last();
         for (int i = 0; i < nmine; ++i) {
@@ -208,8 +210,9 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
                 // never travel back through shared memory and the L1 sees coalesced gathers.
                 const int jcut = m.pcut - m.pa;
                 for (int r = m.r0 + tid; r < m.r1; r += T_CONSUMERS) {
-                    double wv = 0.0;
+                    double wv = 0.0, w2v = 0.0;
                     if (DOTS) wv = __ldcs(w + r);
+                    if (DOTS == 2) w2v = __ldg(w2 + r);
                     const int ia = r - m.ra;
                     const int a = ((r < m.rcut) ? st.rptr[ia] : __ldg(indptr + r)) - m.pa;
                     const int b = ((r + 1 < m.rcut) ? st.rptr[ia + 1] : __ldg(indptr + r + 1)) - m.pa;
@@ -233,6 +236,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
                         sum = fma(__ldg(vals + m.pa + q), __ldg(x + ((int)__ldg(indices + m.pa + q) + (REL ? r : 0))), sum);
                     y[r] = sum;
                     if (DOTS) { d0 += wv * sum; d1 += sum * sum; }
+                    if (DOTS == 2) { d2 += w2v * sum; d3 += w2v * wv; }
                 }
             } else {
                 // very long row(s): the consumers walk the rows of this block straight from global memory
@@ -244,6 +248,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
                     if (tid == 0) {
                         y[r] = sum;
                         if (DOTS) { d0 += __ldg(w + r) * sum; d1 += sum * sum; }
+                        if (DOTS == 2) { d2 += __ldg(w2 + r) * sum; d3 += __ldg(w2 + r) * __ldg(w + r); }
                     }
                 }
             }
@@ -253,9 +258,11 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
         if (DOTS) {
             d0 = consumer_sum(d0, red);
             d1 = consumer_sum(d1, red);
+            if (DOTS == 2) { d2 = consumer_sum(d2, red); d3 = consumer_sum(d3, red); }
             if (tid == 0) {
                 partials[blockIdx.x] = d0;
                 partials[gridDim.x + blockIdx.x] = d1;
+                if (DOTS == 2) { partials[2 * gridDim.x + blockIdx.x] = d2; partials[3 * gridDim.x + blockIdx.x] = d3; }
                 __threadfence();
                 const unsigned int t = atomicInc(ticket, gridDim.x - 1);
                 *s_last = (t == gridDim.x - 1);
@@ -263,14 +270,16 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
             consumer_sync();
             if (*s_last) {
                 __threadfence();
-                double a0 = 0.0, a1 = 0.0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 for (int k = tid; k < (int)gridDim.x; k += T_CONSUMERS) {
                     a0 += __ldcg(partials + k);
                     a1 += __ldcg(partials + gridDim.x + k);
+                    if (DOTS == 2) { a2 += __ldcg(partials + 2 * gridDim.x + k); a3 += __ldcg(partials + 3 * gridDim.x + k); }
                 }
                 a0 = consumer_sum(a0, red);
                 a1 = consumer_sum(a1, red);
-                if (tid == 0) fin(a0, a1);
+                if (DOTS == 2) { a2 = consumer_sum(a2, red); a3 = consumer_sum(a3, red); }
+                if (tid == 0) fin(a0, a1, a2, a3);
             }
         }
     }
