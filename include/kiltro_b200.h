@@ -218,6 +218,13 @@ size_t kb_blocks_scratch_bytes(int64_t nnz);
 int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
                  const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, double *d_out2,
                  void *d_scratch, void *stream);                          /* y = A x ; out = {<w,y>, <y,y>} */
+int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
+                  const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
+                  double *d_out4, void *d_scratch, void *stream);         /* out = {<w,y>, <y,y>, <w2,y>, <w2,w>} */
+/* merged BiCGSTAB update: x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r> */
+int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,
+                         const double *d_t, const double *d_v, double *d_x, double *d_r, double *d_p, double *d_out2,
+                         void *d_scratch, void *stream);
 int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream); /* {<a,b>,<b,b>} */
 int kb_residual(int64_t n, const double *d_b, const double *d_q, double *d_r, double *d_out2, void *d_scratch,
                 void *stream);                                            /* r = b - q ; out = {<r,r>, <b,b>} */

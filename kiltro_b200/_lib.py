@@ -73,6 +73,8 @@ SIGNATURES = {
     "kb_mesh_rectangle_strip": (I32, [F64, F64, F64, F64, I64, I64, I64, I64, c_vp, c_vp, c_vp]),
     "kb_blocks_scratch_bytes": (ctypes.c_size_t, [I64]),
     "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_bicgstab_update_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_dot2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_residual": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_axpy_neg": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),

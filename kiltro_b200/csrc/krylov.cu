@@ -765,7 +765,7 @@ int launch_vec_s(int64_t n, Body body, Final fin, const Scratch &sc, cudaStream_
 
 // bytes of device scratch the building blocks need for a system with nnz non-zeros (zero-initialise it once)
 extern "C" size_t kb_blocks_scratch_bytes(int64_t nnz) {
-    return 256 + sizeof(double) * (size_t)(2 * num_blocks(nnz) + 2 * 8 * (int64_t)kb_num_sms() + 64);
+    return 256 + sizeof(double) * (size_t)(4 * num_blocks(nnz) + 4 * 8 * (int64_t)kb_num_sms() + 64);
 }
 
 // y = A x over `nrows` rows + local partial dots d_out2 = {<w,y>, <y,y>}
@@ -778,6 +778,28 @@ extern "C" int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr,
     const Scratch sc = scratch_of(d_scratch);
     return launch_spmv_raw<1, FinStore>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
                                         d_y, d_w, nullptr, FinStore{d_out2}, (cudaStream_t)stream);
+}
+// 4-dot form: out4 = {<w,y>, <y,y>, <w2,y>, <w2,w>}  (merged BiCGSTAB update)
+struct FinStore4 { double *out; __device__ void operator()(double a, double b, double c, double d) const { out[0] = a; out[1] = b; out[2] = c; out[3] = d; } };
+extern "C" int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                             const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y,
+                             const double *d_w, const double *d_w2, double *d_out4, void *d_scratch, void *stream) {
+    if (!d_indptr || !d_indices || (!d_vals && nnz > 0) || !d_rowblk || !d_x || !d_y || !d_w || !d_w2 || !d_out4 ||
+        !d_scratch)
+        return KB_EINVAL;
+    if (nrows <= 0) return 0;
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_spmv_raw<2, FinStore4>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
+                                         d_y, d_w, nullptr, FinStore4{d_out4}, (cudaStream_t)stream, nullptr, d_w2);
+}
+// x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r>   (s is passed in r)
+extern "C" int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,
+                                    const double *d_t, const double *d_v, double *d_x, double *d_r, double *d_p,
+                                    double *d_out2, void *d_scratch, void *stream) {
+    if (!d_alpha || !d_omega || !d_beta || !d_t || !d_v || !d_x || !d_r || !d_p || !d_out2 || !d_scratch) return KB_EINVAL;
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_vec4<1>(n, HBiUpdateP{d_alpha, d_omega, d_beta, d_t, d_v, d_x, d_r, d_p}, FinStore{d_out2}, sc.partials,
+                          sc.ticket, nullptr, (cudaStream_t)stream);
 }
 extern "C" int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream) {
     if (!d_a || !d_b || !d_out2 || !d_scratch) return KB_EINVAL;

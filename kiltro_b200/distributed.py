@@ -134,6 +134,13 @@ class LocalSystem(object):
                                          y.data_ptr() + 8 * p.own_off, w.data_ptr() + 8 * p.own_off, D.ptr(out2),
                                          D.ptr(self.scratch), D.stream_ptr()))
 
+    def spmv_dots4(self, vals, x, y, w, w2, out4):
+        p = self.part
+        _lib.check(self.lib.kb_spmv_dots4(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
+                                          D.ptr(self.indices), D.ptr(vals), D.ptr(self.rowblk), D.ptr(x),
+                                          y.data_ptr() + 8 * p.own_off, w.data_ptr() + 8 * p.own_off,
+                                          w2.data_ptr() + 8 * p.own_off, D.ptr(out4), D.ptr(self.scratch), D.stream_ptr()))
+
     def spmv(self, vals, x, y):
         p = self.part
         _lib.check(self.lib.kb_spmv(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off, D.ptr(self.indices),
@@ -245,27 +252,30 @@ def _jacobi_scale(systems, comm, mats, mode):
 
 # ------------------------------------------------------------------------------------------------------ Krylov loops
 def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
-    """Unpreconditioned BiCGSTAB on the (already Jacobi-scaled) partitioned operator.  b, x: full local vectors per part
-    (x: initial guess in, solution out, owned range).  Returns dict(iterations, relative_residual, status)."""
+    """Unpreconditioned BiCGSTAB on the (already Jacobi-scaled) partitioned operator, in the merged-update form of the
+    single-GPU solver (csrc/krylov.cu): two all-reduces per iteration (after each SpMV; 2 and 4 doubles), the
+    residual norm is reduced only when convergence is checked.  b, x: full local vectors per part (x: initial guess in,
+    solution out, owned range).  Returns dict(iterations, relative_residual, status)."""
     parts = [s.part for s in systems]
     P = len(systems)
     z = lambda s: D.zeros(s.part.n_loc)
     r = [z(s) for s in systems]; rhat = [z(s) for s in systems]; p = [z(s) for s in systems]
     v = [z(s) for s in systems]; t = [z(s) for s in systems]
-    d = [D.zeros(2) for _ in systems]
+    d = [D.zeros(4) for _ in systems]
+    dr = [D.zeros(2) for _ in systems]
     sc = [dict(rho=D.zeros(1), alpha=D.zeros(1), omega=D.zeros(1), beta=D.zeros(1)) for _ in systems]
     st = D.stream_ptr
     # r = b - A x ; rhat = p = r
     comm.halo_exchange(parts, x)
     for k, s in enumerate(systems):
         s.spmv(Ahat[k], x[k], v[k])
-        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(v[k]), s.own_ptr(r[k]), D.ptr(d[k]),
+        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(v[k]), s.own_ptr(r[k]), D.ptr(dr[k]),
                                      D.ptr(s.scratch), st()))
-    comm.allreduce(d)
-    rr0, bb = float(d[0][0]), float(d[0][1])
+    comm.allreduce(dr)
+    rr0, bb = float(dr[0][0]), float(dr[0][1])
     tol2 = rtol * rtol * bb
     for k in range(P):
-        rhat[k].copy_(r[k]); p[k].copy_(r[k]); sc[k]["rho"].copy_(d[k][0:1])
+        rhat[k].copy_(r[k]); p[k].copy_(r[k]); sc[k]["rho"].copy_(dr[k][0:1])
     it, rr, status = 0, rr0, 0
     if not (rr0 > tol2):
         return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
@@ -273,30 +283,28 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
         for _ in range(min(check_every, maxiter - it)):
             comm.halo_exchange(parts, p)
             for k, s in enumerate(systems):
-                s.spmv_dots(Ahat[k], p[k], v[k], rhat[k], d[k])
-            comm.allreduce(d)
+                s.spmv_dots(Ahat[k], p[k], v[k], rhat[k], d[k][0:2])
+            comm.allreduce([dk[0:2] for dk in d])
             for k, s in enumerate(systems):
-                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])
+                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])                      # alpha = rho / <rhat,v>
                 _lib.check(s.lib.kb_axpy_neg(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(v[k]), s.own_ptr(r[k]), st()))
             comm.halo_exchange(parts, r)
             for k, s in enumerate(systems):
-                s.spmv_dots(Ahat[k], r[k], t[k], r[k], d[k])
+                s.spmv_dots4(Ahat[k], r[k], t[k], r[k], rhat[k], d[k])                     # {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
             comm.allreduce(d)
             for k, s in enumerate(systems):
-                torch.div(d[k][0:1], d[k][1:2], out=sc[k]["omega"])
-                _lib.check(s.lib.kb_bicgstab_update(s.part.n_own, D.ptr(sc[k]["alpha"]), D.ptr(sc[k]["omega"]),
-                                                    s.own_ptr(p[k]), s.own_ptr(t[k]), s.own_ptr(rhat[k]), s.own_ptr(x[k]),
-                                                    s.own_ptr(r[k]), D.ptr(d[k]), D.ptr(s.scratch), st()))
-            comm.allreduce(d)
-            for k, s in enumerate(systems):
-                # beta = (rho_new / rho)(alpha / omega) ; rho = rho_new
-                torch.div(d[k][0:1], sc[k]["rho"], out=sc[k]["beta"])
-                sc[k]["beta"].mul_(sc[k]["alpha"]).div_(sc[k]["omega"])
-                sc[k]["rho"].copy_(d[k][0:1])
-                _lib.check(s.lib.kb_bicgstab_p(s.part.n_own, D.ptr(sc[k]["beta"]), D.ptr(sc[k]["omega"]), s.own_ptr(r[k]),
-                                               s.own_ptr(v[k]), s.own_ptr(p[k]), st()))
+                a = sc[k]
+                torch.div(d[k][0:1], d[k][1:2], out=a["omega"])                            # omega = <s,t>/<t,t>
+                rho_new = d[k][3:4] - a["omega"] * d[k][2:3]                               # <rhat, s - omega t>
+                torch.div(rho_new, a["rho"], out=a["beta"])
+                a["beta"].mul_(a["alpha"]).div_(a["omega"])                                # (rho_new/rho)(alpha/omega)
+                a["rho"].copy_(rho_new)
+                _lib.check(s.lib.kb_bicgstab_update_p(s.part.n_own, D.ptr(a["alpha"]), D.ptr(a["omega"]), D.ptr(a["beta"]),
+                                                      s.own_ptr(t[k]), s.own_ptr(v[k]), s.own_ptr(x[k]), s.own_ptr(r[k]),
+                                                      s.own_ptr(p[k]), D.ptr(dr[k]), D.ptr(s.scratch), st()))
             it += 1
-        rr = float(d[0][1])                                   # host sync every check_every iterations
+        comm.allreduce(dr)                                     # ||r||^2 only when convergence is looked at
+        rr = float(dr[0][0])                                   # host sync every check_every iterations
         if not np.isfinite(rr):
             status = _lib.KB_EBREAKDOWN
             break
