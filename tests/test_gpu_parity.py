@@ -509,3 +509,18 @@ def test_load_increments_and_heat_source():
     ref = O.total_component_sol(O.linear_solve(kb[0], kb[1], kb[2], kb[3]), cin, cout, td, nn)
     src = solve(include_heat_source=True)
     assert rel_l2(src.ravel(), ref) < SOL_TOL and rel_l2(src.ravel(), one.ravel()) > 1e-4
+
+
+# ------------------------------------------------------------------------------------------------- example scripts (configs 1-3)
+@pytest.mark.parametrize("script", ["steady_1d.py", "steady_2d.py", "transient_2d.py"])
+def test_example_scripts_run(script):
+    import os, subprocess, sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    if script == "steady_1d.py":
+        assert "23.7" in out.stdout and "112.8" in out.stdout            # steady_1d_addi.pdf
+    if script == "steady_2d.py":
+        assert "105.18" in out.stdout and "249.7" in out.stdout          # steady_2d_addi.pdf
+    if script == "transient_2d.py":
+        assert "time increment 0.8" in out.stdout and "199.8" in out.stdout
