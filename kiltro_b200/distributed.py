@@ -84,6 +84,28 @@ class DistComm(object):
             for rb, sl in keep:
                 v[sl] = rb
 
+    def halo_start(self, parts, vecs):
+        """Posts the sends/receives of the boundary rows; returns a handle for halo_finish (the transfers run on NCCL's
+        stream while the caller computes the rows that do not need the halo)."""
+        part, v = parts[0], vecs[0]
+        dist = self.dist
+        ops, keep = [], []
+        if part.ha:
+            sb = v[part.last_own_row()].contiguous(); rb = torch.empty_like(sb); keep.append((rb, part.halo_above()))
+            ops += [dist.P2POp(dist.isend, sb, part.rank + 1, self.group), dist.P2POp(dist.irecv, rb, part.rank + 1, self.group)]
+        if part.hb:
+            sb = v[part.first_own_row()].contiguous(); rb = torch.empty_like(sb); keep.append((rb, part.halo_below()))
+            ops += [dist.P2POp(dist.isend, sb, part.rank - 1, self.group), dist.P2POp(dist.irecv, rb, part.rank - 1, self.group)]
+        works = dist.batch_isend_irecv(ops) if ops else []
+        return (works, keep, v)
+
+    def halo_finish(self, handle):
+        works, keep, v = handle
+        for r in works:
+            r.wait()
+        for rb, sl in keep:
+            v[sl] = rb
+
     def allreduce(self, outs):
         self.dist.all_reduce(outs[0], op=self.dist.ReduceOp.SUM, group=self.group)
 
@@ -103,6 +125,12 @@ class LocalComm(object):
                 vecs[k][part.halo_above()] = vecs[k + 1][parts[k + 1].first_own_row()]
             if part.hb:
                 vecs[k][part.halo_below()] = vecs[k - 1][parts[k - 1].last_own_row()]
+
+    def halo_start(self, parts, vecs):
+        return (parts, vecs)
+
+    def halo_finish(self, handle):
+        self.halo_exchange(*handle)
 
     def allreduce(self, outs):
         total = outs[0].clone()
@@ -149,6 +177,60 @@ class LocalSystem(object):
 
     def own_ptr(self, v):
         return v.data_ptr() + 8 * self.part.own_off
+
+    # ---- overlap of the halo exchange with the rows that do not need it
+    def build_ranges(self):
+        """Splits the owned rows into [first mesh row | interior | last mesh row]; the interior rows only reference owned
+        columns, so their SpMV can run while the halo rows are in flight."""
+        p, lib = self.part, self.lib
+        self.ranges = None
+        nrows_mesh = p.j1 - p.j0
+        if nrows_mesh < 3:
+            return
+        cuts = [p.own_off, p.own_off + p.nxn, p.own_off + p.n_own - p.nxn, p.own_off + p.n_own]
+        ip = self.indptr[cuts].cpu().tolist()
+        self.ranges = []
+        for a in range(3):
+            r0, nr, nnz = cuts[a], cuts[a + 1] - cuts[a], ip[a + 1] - ip[a]
+            rb = D.empty(lib.kb_spmv_num_blocks(nnz) + 1, torch.int32)
+            _lib.check(lib.kb_spmv_partition(nr, nnz, self.indptr.data_ptr() + 4 * r0, D.ptr(rb), D.stream_ptr()))
+            self.ranges.append((r0, nr, nnz, rb))
+        self.dparts = [D.zeros(4) for _ in range(3)]
+
+    def _range_spmv(self, k, vals, x, y, w, w2, out):
+        r0, nr, nnz, rb = self.ranges[k]
+        ip = self.indptr.data_ptr() + 4 * r0
+        yp, wp = y.data_ptr() + 8 * r0, w.data_ptr() + 8 * r0
+        if w2 is None:
+            _lib.check(self.lib.kb_spmv_dots(nr, nnz, ip, D.ptr(self.indices), D.ptr(vals), D.ptr(rb), D.ptr(x), yp, wp,
+                                             D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
+        else:
+            _lib.check(self.lib.kb_spmv_dots4(nr, nnz, ip, D.ptr(self.indices), D.ptr(vals), D.ptr(rb), D.ptr(x), yp, wp,
+                                              w2.data_ptr() + 8 * r0, D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
+
+
+def spmv_overlapped(systems, comm, vals, x, y, w, w2, out):
+    """y = A x on the owned rows of every part with the halo exchange of x hidden behind the interior rows; out[k] gets the
+    local partial dots (2 values, or 4 when w2 is given)."""
+    parts = [s.part for s in systems]
+    nd = 2 if w2 is None else 4
+    if any(s.ranges is None for s in systems):
+        comm.halo_exchange(parts, x)
+        for k, s in enumerate(systems):
+            if w2 is None:
+                s.spmv_dots(vals[k], x[k], y[k], w[k], out[k][0:2])
+            else:
+                s.spmv_dots4(vals[k], x[k], y[k], w[k], w2[k], out[k])
+        return
+    h = comm.halo_start(parts, x)
+    for k, s in enumerate(systems):
+        s._range_spmv(1, vals[k], x[k], y[k], w[k], None if w2 is None else w2[k], s.dparts[1])
+    comm.halo_finish(h)
+    for k, s in enumerate(systems):
+        s._range_spmv(0, vals[k], x[k], y[k], w[k], None if w2 is None else w2[k], s.dparts[0])
+        s._range_spmv(2, vals[k], x[k], y[k], w[k], None if w2 is None else w2[k], s.dparts[2])
+        torch.add(s.dparts[0][0:nd], s.dparts[1][0:nd], out=out[k][0:nd])
+        out[k][0:nd].add_(s.dparts[2][0:nd])
 
 
 def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, dirichlet_fn, neumann_fn=None,
@@ -202,6 +284,7 @@ def reassemble(sysm):
         _lib.check(lib.kb_spmv_partition(part.n_own, sysm.nnz_own, K.indptr.data_ptr() + 4 * part.own_off,
                                          D.ptr(sysm.rowblk), D.stream_ptr()))
         sysm.scratch = D.zeros(lib.kb_blocks_scratch_bytes(sysm.nnz_own), torch.uint8)
+        sysm.build_ranges()
     n = part.n_loc
     # right-hand side of the steady problem on A' = [Kff 0; 0 I]:  F - K[:,fixed] T_D at free rows, T_D at fixed rows
     F = (-Fn).contiguous()
@@ -281,16 +364,12 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
         return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
     while it < maxiter:
         for _ in range(min(check_every, maxiter - it)):
-            comm.halo_exchange(parts, p)
-            for k, s in enumerate(systems):
-                s.spmv_dots(Ahat[k], p[k], v[k], rhat[k], d[k][0:2])
+            spmv_overlapped(systems, comm, Ahat, p, v, rhat, None, d)
             comm.allreduce([dk[0:2] for dk in d])
             for k, s in enumerate(systems):
                 torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])                      # alpha = rho / <rhat,v>
                 _lib.check(s.lib.kb_axpy_neg(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(v[k]), s.own_ptr(r[k]), st()))
-            comm.halo_exchange(parts, r)
-            for k, s in enumerate(systems):
-                s.spmv_dots4(Ahat[k], r[k], t[k], r[k], rhat[k], d[k])                     # {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
+            spmv_overlapped(systems, comm, Ahat, r, t, r, rhat, d)                        # {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
             comm.allreduce(d)
             for k, s in enumerate(systems):
                 a = sc[k]
@@ -341,9 +420,7 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
         return {"iterations": 0, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
     while it < maxiter:
         for _ in range(min(check_every, maxiter - it)):
-            comm.halo_exchange(parts, p)
-            for k, s in enumerate(systems):
-                s.spmv_dots(Ahat[k], p[k], q[k], p[k], d[k])
+            spmv_overlapped(systems, comm, Ahat, p, q, p, None, d)
             comm.allreduce(d)
             for k, s in enumerate(systems):
                 torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])
