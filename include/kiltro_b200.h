@@ -225,6 +225,17 @@ int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int
 int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,
                          const double *d_t, const double *d_v, double *d_x, double *d_r, double *d_p, double *d_out2,
                          void *d_scratch, void *stream);
+/* scalar-fused forms (no scalar kernels between a collective and the vector work): every thread derives alpha / omega /
+ * beta from the all-reduced dots; rho is double-buffered by the caller (d_rho_in != d_rho_out). */
+int kb_bicgstab_s2(int64_t n, const double *d_rho, const double *d_dots, const double *d_v, double *d_r,
+                   double *d_alpha_out, void *stream);                    /* alpha = rho/dots[0] ; r -= alpha v */
+int kb_bicgstab_update_p2(int64_t n, const double *d_rho_in, double *d_rho_out, const double *d_alpha,
+                          const double *d_dots4, const double *d_t, const double *d_v, double *d_x, double *d_r,
+                          double *d_p, double *d_out2, void *d_scratch, void *stream);
+int kb_cg_update2(int64_t n, const double *d_rho, const double *d_dots, const double *d_p, const double *d_q, double *d_x,
+                  double *d_r, double *d_out2, void *d_scratch, void *stream);   /* alpha = rho/dots[0] */
+int kb_cg_p2(int64_t n, const double *d_rho_in, double *d_rho_out, const double *d_dots, const double *d_r, double *d_p,
+             void *stream);                                               /* beta = dots[0]/rho_in ; rho_out = dots[0] */
 int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream); /* {<a,b>,<b,b>} */
 int kb_residual(int64_t n, const double *d_b, const double *d_q, double *d_r, double *d_out2, void *d_scratch,
                 void *stream);                                            /* r = b - q ; out = {<r,r>, <b,b>} */

@@ -75,6 +75,10 @@ SIGNATURES = {
     "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_update_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_bicgstab_s2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_bicgstab_update_p2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_cg_update2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_cg_p2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_dot2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_residual": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_axpy_neg": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),

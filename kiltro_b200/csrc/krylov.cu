@@ -801,6 +801,91 @@ extern "C" int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const doub
     return launch_vec4<1>(n, HBiUpdateP{d_alpha, d_omega, d_beta, d_t, d_v, d_x, d_r, d_p}, FinStore{d_out2}, sc.partials,
                           sc.ticket, nullptr, (cudaStream_t)stream);
 }
+// ---- scalar-fused forms for host-driven loops: the all-reduced dot products arrive as device pointers and every
+// thread derives alpha / omega / beta from them (no tiny scalar kernels between the collectives and the vector work).
+namespace {
+struct HBiS2 {              // alpha = rho / d[0] ; r -= alpha v ; alpha is stored for the update kernel
+    const double *rho, *d, *v; double *r, *alpha_out;
+    struct S { double a; }; struct L { double r, v; };
+    __device__ S scalars() const {
+        const double a = rho[0] / d[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0) alpha_out[0] = a;
+        return S{a};
+    }
+    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.v = __ldcs(v + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &, double &) const { r[i] = l.r - s.a * l.v; }
+};
+struct HBiUpdateP2 {        // omega, rho_new, beta from d4 = {<s,t>,<t,t>,<rhat,t>,<rhat,s>} ; merged x / r / p update
+    const double *rho_in, *alpha, *d4, *t, *v; double *x, *r, *p, *rho_out;
+    struct S { double a, om, b; }; struct L { double x, p, s, t, v; };
+    __device__ S scalars() const {
+        const double om = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
+        const double rho_new = d4[3] - om * d4[2];
+        const double a = alpha[0];
+        const double b = (rho_new / rho_in[0]) * (a / om);
+        if (blockIdx.x == 0 && threadIdx.x == 0) rho_out[0] = rho_new;     // rho_out != rho_in (double-buffered by the caller)
+        return S{a, om, b};
+    }
+    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.s = r[i]; l.t = __ldcs(t + i); l.v = __ldcs(v + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
+        x[i] = l.x + (s.a * l.p + s.om * l.s);
+        const double ri = l.s - s.om * l.t;
+        r[i] = ri;
+        p[i] = ri + s.b * (l.p - s.om * l.v);
+        d0 += ri * ri;
+    }
+};
+struct HCgUpdate2 {         // alpha = rho / d[0] ; x += alpha p ; r -= alpha q ; d0 = <r,r>
+    const double *rho, *d, *p, *q; double *x, *r;
+    struct S { double a; }; struct L { double x, p, r, q; };
+    __device__ S scalars() const { return S{rho[0] / d[0]}; }
+    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.r = r[i]; l.q = __ldcs(q + i); }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
+        x[i] = l.x + s.a * l.p;
+        const double ri = l.r - s.a * l.q;
+        r[i] = ri;
+        d0 += ri * ri;
+    }
+};
+struct HCgP2 {              // beta = d[0] / rho_in ; p = r + beta p ; rho_out = d[0]
+    const double *rho_in, *d, *r; double *p, *rho_out;
+    struct S { double b; }; struct L { double r, p; };
+    __device__ S scalars() const {
+        const double b = d[0] / rho_in[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0) rho_out[0] = d[0];
+        return S{b};
+    }
+    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.p = p[i]; }
+    __device__ void apply(int64_t i, const L &l, const S &s, double &, double &) const { p[i] = l.r + s.b * l.p; }
+};
+}  // namespace
+extern "C" int kb_bicgstab_s2(int64_t n, const double *d_rho, const double *d_dots, const double *d_v, double *d_r,
+                              double *d_alpha_out, void *stream) {
+    if (!d_rho || !d_dots || !d_v || !d_r || !d_alpha_out) return KB_EINVAL;
+    return launch_vec4<0>(n, HBiS2{d_rho, d_dots, d_v, d_r, d_alpha_out}, NoFin{}, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+extern "C" int kb_bicgstab_update_p2(int64_t n, const double *d_rho_in, double *d_rho_out, const double *d_alpha,
+                                     const double *d_dots4, const double *d_t, const double *d_v, double *d_x,
+                                     double *d_r, double *d_p, double *d_out2, void *d_scratch, void *stream) {
+    if (!d_rho_in || !d_rho_out || d_rho_in == d_rho_out || !d_alpha || !d_dots4 || !d_t || !d_v || !d_x || !d_r || !d_p ||
+        !d_out2 || !d_scratch)
+        return KB_EINVAL;
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_vec4<1>(n, HBiUpdateP2{d_rho_in, d_alpha, d_dots4, d_t, d_v, d_x, d_r, d_p, d_rho_out}, FinStore{d_out2},
+                          sc.partials, sc.ticket, nullptr, (cudaStream_t)stream);
+}
+extern "C" int kb_cg_update2(int64_t n, const double *d_rho, const double *d_dots, const double *d_p, const double *d_q,
+                             double *d_x, double *d_r, double *d_out2, void *d_scratch, void *stream) {
+    if (!d_rho || !d_dots || !d_p || !d_q || !d_x || !d_r || !d_out2 || !d_scratch) return KB_EINVAL;
+    const Scratch sc = scratch_of(d_scratch);
+    return launch_vec4<1>(n, HCgUpdate2{d_rho, d_dots, d_p, d_q, d_x, d_r}, FinStore{d_out2}, sc.partials, sc.ticket, nullptr,
+                          (cudaStream_t)stream);
+}
+extern "C" int kb_cg_p2(int64_t n, const double *d_rho_in, double *d_rho_out, const double *d_dots, const double *d_r,
+                        double *d_p, void *stream) {
+    if (!d_rho_in || !d_rho_out || d_rho_in == d_rho_out || !d_dots || !d_r || !d_p) return KB_EINVAL;
+    return launch_vec4<0>(n, HCgP2{d_rho_in, d_dots, d_r, d_p, d_rho_out}, NoFin{}, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
 extern "C" int kb_dot2(int64_t n, const double *d_a, const double *d_b, double *d_out2, void *d_scratch, void *stream) {
     if (!d_a || !d_b || !d_out2 || !d_scratch) return KB_EINVAL;
     return launch_vec_s<1>(n, BodyDot2{d_a, d_b}, FinStore{d_out2}, scratch_of(d_scratch), (cudaStream_t)stream);

@@ -21,6 +21,11 @@ from .FEMSolver import FEMSolver
 from .FiniteElements.Assembly import Assemble
 
 
+# Hide the halo exchange behind the interior rows of the SpMV (3 launches instead of 1).  Measured on 2 B200s at 16 M DOF
+# per GPU: no gain (the exchange is short compared with the launch overhead it adds), so it is off by default.
+OVERLAP_HALO = False
+
+
 class StripPartition(object):
     """Mesh rows [j0, j1) of an (nx_nodes x ny_nodes) node grid owned by `rank`, plus one halo row per interior side."""
 
@@ -214,7 +219,7 @@ def spmv_overlapped(systems, comm, vals, x, y, w, w2, out):
     local partial dots (2 values, or 4 when w2 is given)."""
     parts = [s.part for s in systems]
     nd = 2 if w2 is None else 4
-    if any(s.ranges is None for s in systems):
+    if not OVERLAP_HALO or any(s.ranges is None for s in systems):
         comm.halo_exchange(parts, x)
         for k, s in enumerate(systems):
             if w2 is None:
@@ -346,7 +351,8 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
     v = [z(s) for s in systems]; t = [z(s) for s in systems]
     d = [D.zeros(4) for _ in systems]
     dr = [D.zeros(2) for _ in systems]
-    sc = [dict(rho=D.zeros(1), alpha=D.zeros(1), omega=D.zeros(1), beta=D.zeros(1)) for _ in systems]
+    sc = [dict(rho=[D.zeros(1), D.zeros(1)], alpha=D.zeros(1)) for _ in systems]      # rho is double-buffered
+    cur = 0
     st = D.stream_ptr
     # r = b - A x ; rhat = p = r
     comm.halo_exchange(parts, x)
@@ -358,30 +364,34 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
     rr0, bb = float(dr[0][0]), float(dr[0][1])
     tol2 = rtol * rtol * bb
     for k in range(P):
-        rhat[k].copy_(r[k]); p[k].copy_(r[k]); sc[k]["rho"].copy_(dr[k][0:1])
+        rhat[k].copy_(r[k]); p[k].copy_(r[k]); sc[k]["rho"][0].copy_(dr[k][0:1])
     it, rr, status = 0, rr0, 0
     if not (rr0 > tol2):
         return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    import os, time
+    dbg = os.environ.get("KB_DIST_DEBUG") == "1" and comm.rank == 0
     while it < maxiter:
+        if dbg and it == check_every:
+            torch.cuda.synchronize(); t_enq0 = time.perf_counter()
         for _ in range(min(check_every, maxiter - it)):
             spmv_overlapped(systems, comm, Ahat, p, v, rhat, None, d)
             comm.allreduce([dk[0:2] for dk in d])
-            for k, s in enumerate(systems):
-                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])                      # alpha = rho / <rhat,v>
-                _lib.check(s.lib.kb_axpy_neg(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(v[k]), s.own_ptr(r[k]), st()))
+            for k, s in enumerate(systems):                                                # alpha = rho/<rhat,v> ; s = r - alpha v
+                _lib.check(s.lib.kb_bicgstab_s2(s.part.n_own, D.ptr(sc[k]["rho"][cur]), D.ptr(d[k]), s.own_ptr(v[k]),
+                                                s.own_ptr(r[k]), D.ptr(sc[k]["alpha"]), st()))
             spmv_overlapped(systems, comm, Ahat, r, t, r, rhat, d)                        # {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
             comm.allreduce(d)
-            for k, s in enumerate(systems):
-                a = sc[k]
-                torch.div(d[k][0:1], d[k][1:2], out=a["omega"])                            # omega = <s,t>/<t,t>
-                rho_new = d[k][3:4] - a["omega"] * d[k][2:3]                               # <rhat, s - omega t>
-                torch.div(rho_new, a["rho"], out=a["beta"])
-                a["beta"].mul_(a["alpha"]).div_(a["omega"])                                # (rho_new/rho)(alpha/omega)
-                a["rho"].copy_(rho_new)
-                _lib.check(s.lib.kb_bicgstab_update_p(s.part.n_own, D.ptr(a["alpha"]), D.ptr(a["omega"]), D.ptr(a["beta"]),
-                                                      s.own_ptr(t[k]), s.own_ptr(v[k]), s.own_ptr(x[k]), s.own_ptr(r[k]),
-                                                      s.own_ptr(p[k]), D.ptr(dr[k]), D.ptr(s.scratch), st()))
+            for k, s in enumerate(systems):                                                # omega, rho_new, beta inside the kernel
+                _lib.check(s.lib.kb_bicgstab_update_p2(s.part.n_own, D.ptr(sc[k]["rho"][cur]), D.ptr(sc[k]["rho"][cur ^ 1]),
+                                                       D.ptr(sc[k]["alpha"]), D.ptr(d[k]), s.own_ptr(t[k]), s.own_ptr(v[k]),
+                                                       s.own_ptr(x[k]), s.own_ptr(r[k]), s.own_ptr(p[k]), D.ptr(dr[k]),
+                                                       D.ptr(s.scratch), st()))
+            cur ^= 1
             it += 1
+        if dbg and it == 2 * check_every:
+            t_enq1 = time.perf_counter(); torch.cuda.synchronize(); t_done = time.perf_counter()
+            print("[dist debug] per iteration: CPU enqueue %.1f us, GPU-complete %.1f us" % (
+                (t_enq1 - t_enq0) / check_every * 1e6, (t_done - t_enq0) / check_every * 1e6), flush=True)
         comm.allreduce(dr)                                     # ||r||^2 only when convergence is looked at
         rr = float(dr[0][0])                                   # host sync every check_every iterations
         if not np.isfinite(rr):
@@ -403,7 +413,9 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
     z = lambda s: D.zeros(s.part.n_loc)
     r = [z(s) for s in systems]; p = [z(s) for s in systems]; q = [z(s) for s in systems]
     d = [D.zeros(2) for _ in systems]
-    sc = [dict(rho=D.zeros(1), alpha=D.zeros(1), beta=D.zeros(1)) for _ in systems]
+    dr = [D.zeros(2) for _ in systems]
+    sc = [dict(rho=[D.zeros(1), D.zeros(1)]) for _ in systems]                          # rho is double-buffered
+    cur = 0
     st = D.stream_ptr
     comm.halo_exchange(parts, x)
     for k, s in enumerate(systems):
@@ -414,7 +426,7 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
     rr, bb = float(d[0][0]), float(d[0][1])
     tol2 = rtol * rtol * bb
     for k in range(P):
-        p[k].copy_(r[k]); sc[k]["rho"].copy_(d[k][0:1])
+        p[k].copy_(r[k]); sc[k]["rho"][0].copy_(d[k][0:1])
     it, status = 0, 0
     if not (rr > tol2):
         return {"iterations": 0, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
@@ -422,17 +434,17 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
         for _ in range(min(check_every, maxiter - it)):
             spmv_overlapped(systems, comm, Ahat, p, q, p, None, d)
             comm.allreduce(d)
-            for k, s in enumerate(systems):
-                torch.div(sc[k]["rho"], d[k][0:1], out=sc[k]["alpha"])
-                _lib.check(s.lib.kb_cg_update(s.part.n_own, D.ptr(sc[k]["alpha"]), s.own_ptr(p[k]), s.own_ptr(q[k]),
-                                              s.own_ptr(x[k]), s.own_ptr(r[k]), D.ptr(d[k]), D.ptr(s.scratch), st()))
-            comm.allreduce(d)
-            for k, s in enumerate(systems):
-                torch.div(d[k][0:1], sc[k]["rho"], out=sc[k]["beta"])
-                sc[k]["rho"].copy_(d[k][0:1])
-                _lib.check(s.lib.kb_cg_p(s.part.n_own, D.ptr(sc[k]["beta"]), s.own_ptr(r[k]), s.own_ptr(p[k]), st()))
+            for k, s in enumerate(systems):                                                # alpha = rho/<p,q>
+                _lib.check(s.lib.kb_cg_update2(s.part.n_own, D.ptr(sc[k]["rho"][cur]), D.ptr(d[k]), s.own_ptr(p[k]),
+                                               s.own_ptr(q[k]), s.own_ptr(x[k]), s.own_ptr(r[k]), D.ptr(dr[k]),
+                                               D.ptr(s.scratch), st()))
+            comm.allreduce(dr)
+            for k, s in enumerate(systems):                                                # beta = <r,r>/rho ; rho = <r,r>
+                _lib.check(s.lib.kb_cg_p2(s.part.n_own, D.ptr(sc[k]["rho"][cur]), D.ptr(sc[k]["rho"][cur ^ 1]), D.ptr(dr[k]),
+                                          s.own_ptr(r[k]), s.own_ptr(p[k]), st()))
+            cur ^= 1
             it += 1
-        rr = float(d[0][0])
+        rr = float(dr[0][0])
         if not np.isfinite(rr):
             status = _lib.KB_EBREAKDOWN
             break
