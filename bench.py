@@ -283,8 +283,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its version there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its version)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     if args.idx32:

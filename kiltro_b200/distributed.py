@@ -11,6 +11,8 @@ the single-GPU path solves).  The solver loops are written SPMD-over-a-list: wit
 `LocalComm` several parts live in one process on one device and the "collectives" are plain copies/sums -- that is how
 the partitioned algorithm is tested against the single-GPU solve without a multi-GPU box, and the CPU (gloo) tests cover
 the partition arithmetic and the exchange plumbing."""
+import sys
+
 import numpy as np
 import torch
 
@@ -391,7 +393,7 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
         if dbg and it == 2 * check_every:
             t_enq1 = time.perf_counter(); torch.cuda.synchronize(); t_done = time.perf_counter()
             print("[dist debug] per iteration: CPU enqueue %.1f us, GPU-complete %.1f us" % (
-                (t_enq1 - t_enq0) / check_every * 1e6, (t_done - t_enq0) / check_every * 1e6), flush=True)
+                (t_enq1 - t_enq0) / check_every * 1e6, (t_done - t_enq0) / check_every * 1e6), file=sys.stderr, flush=True)
         comm.allreduce(dr)                                     # ||r||^2 only when convergence is looked at
         rr = float(dr[0][0])                                   # host sync every check_every iterations
         if not np.isfinite(rr):
