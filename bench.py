@@ -30,6 +30,23 @@ if ROOT not in sys.path:
 METRIC = "assembly+solve DOF/s, 2D conv-diff at 16M DOF"
 UNIT = "DOF/s"
 
+# stdout carries exactly ONE JSON line: everything else any library prints (NCCL's version banner, solver warnings, ...)
+# is sent to stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
@@ -155,7 +172,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ N > 1: partitioned
@@ -245,7 +262,7 @@ def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier
                         "note": "mesh/velocity/flags are generated on device from the partition descriptor; the solution "
                                 "is read back to pinned host memory"},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -265,6 +282,7 @@ def main():
     ap.add_argument("--idx32", action="store_true", help="keep 32-bit column indices in the solver's SpMV (default: 16-bit "
                     "offsets when the matrix band fits)")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -439,7 +457,7 @@ def main():
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "t_symbolic_ms": t_symbolic * 1e3,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == "__main__":
