@@ -198,6 +198,9 @@ int kb_transient_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, cons
                         double *d_Kff, double *d_A, void *stream);
 /* out = in at free DOFs, 0 at fixed DOFs */
 int kb_mask_free(int64_t ndof, const int32_t *d_renum, const double *d_in, double *d_out, void *stream);
+/* one update: T = prescribed value at fixed DOFs, T - dt*y at free DOFs (in place) */
+int kb_transient_update(int64_t ndof, const int32_t *d_renum, const double *d_applied, const double *d_y, double dt,
+                        double *d_T, void *stream);
 /* The whole time loop on device.  d_T: T^0 in, T^nsteps out.  h_snap_steps: ascending step indices (0 = initial state)
  * whose state is copied to d_snapshots (nsnap x ndof).  a_symmetric selects CG (1) or BiCGSTAB (0) for A.  h_info:
  * iterations = total Krylov iterations, residual = worst relative residual over the steps.  Synchronises `stream`. */

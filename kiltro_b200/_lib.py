@@ -66,6 +66,7 @@ SIGNATURES = {
     "kb_time_step_rule": (I32, [I32, c_vp, c_vp, I64, ctypes.POINTER(kb_material), F64, c_vp, c_vp]),
     "kb_transient_matrix": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, c_vp, c_vp]),
     "kb_mask_free": (I32, [I64, c_vp, c_vp, c_vp, c_vp]),
+    "kb_transient_update": (I32, [I64, c_vp, c_vp, c_vp, F64, c_vp, c_vp]),
     "kb_transient_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
     "kb_transient_run": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, I32, c_vp, c_vp, c_vp, c_vp, F64, I32,
                                ctypes.POINTER(ctypes.c_int32), I32, c_vp, F64, I32, c_vp, ctypes.c_size_t,

@@ -617,6 +617,18 @@ struct BodyStep {           // T = fixed ? td : T - dt*y
 };
 }  // namespace
 
+// T = fixed ? applied : T - dt*y   (one theta-step update; also used by the partitioned transient loop)
+extern "C" int kb_transient_update(int64_t ndof, const int32_t *d_renum, const double *d_applied, const double *d_y,
+                                   double dt, double *d_T, void *stream) {
+    if (!d_renum || !d_applied || !d_y || !d_T || ndof < 0) return KB_EINVAL;
+    if (ndof == 0) return 0;
+    const int grid = kb_grid(ndof, 256, 8);
+    k_vec<0, BodyStep, NoFin><<<grid, 256, 0, (cudaStream_t)stream>>>(ndof, BodyStep{d_renum, d_applied, d_y, d_T, dt}, nullptr,
+                                                                    nullptr, nullptr, NoFin{});
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" size_t kb_transient_workspace_bytes(int64_t ndof, int64_t nnz) {
     return carve(nullptr, nullptr, ndof, nnz) + 4 * align256(sizeof(double) * (size_t)(ndof + 1)) +
            align256(sizeof(int32_t) * (size_t)(num_blocks(nnz) + 1)) + align256(2 * sizeof(double) * 4096);

@@ -504,13 +504,12 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
             s.spmv(Kff[k], T[k], kt[k])
             torch.add(kt[k], s.Fm, out=rhs[k])
             if mode == 1:
-                rhs[k].mul_(scales[k])
+                _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(rhs[k]), D.ptr(scales[k]), D.ptr(rhs[k]), D.stream_ptr()))
         info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, rhs, yh, rtol, maxiter, check_every)
         total += info["iterations"]; worst = max(worst, info["relative_residual"])
         for k, s in enumerate(systems):
-            y = yh[k] * scales[k]
-            free = s.bc.renum >= 0
-            T[k] = torch.where(free, T[k] - dt * y, T[k])
-            T[k][s.bc.columns_out_device] = s.bc.applied_dirichlet_device
+            _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(yh[k]), D.ptr(scales[k]), D.ptr(kt[k]), D.stream_ptr()))   # y = D^-1 yhat
+            _lib.check(s.lib.kb_transient_update(s.part.n_loc, D.ptr(s.bc.renum), D.ptr(s.bc.applied_dirichlet_device),
+                                                 D.ptr(kt[k]), float(dt), D.ptr(T[k]), D.stream_ptr()))
     return [Tk[s.part.own()].clone() for Tk, s in zip(T, systems)], {"iterations": total, "worst_relative_residual": worst,
                                                                      "method": "cg" if sym else "bicgstab"}
