@@ -150,9 +150,11 @@ extern "C" int kb_apply_dirichlet_reduce(int64_t ndof, const int32_t *d_indptr, 
                                          const double *d_applied, double load_factor, double *d_F, int64_t n_free,
                                          int32_t *d_Kb_indptr, int32_t *d_Kb_indices, double *d_Kb_data,
                                          double *d_Mb_data, double *d_Fb, int64_t *h_nnz_b, void *stream) {
-    if (!d_indptr || !d_indices || !d_K || !d_renum || !d_applied || !d_F || !d_Kb_indptr || !d_Kb_indices ||
-        !d_Kb_data || !d_Fb || !h_nnz_b || ndof < 0 || n_free < 0 || n_free > ndof)
+    if (!d_indptr || !d_indices || !d_K || !d_renum || !d_F || !d_Kb_indptr || !h_nnz_b || ndof < 0 || n_free < 0 ||
+        n_free > ndof)
         return KB_EINVAL;
+    if (n_free > 0 && (!d_Kb_indices || !d_Kb_data || !d_Fb)) return KB_EINVAL;      // empty reduced system: nothing to fill
+    if (n_free < ndof && !d_applied) return KB_EINVAL;
     if ((d_M == nullptr) != (d_Mb_data == nullptr)) return KB_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const int g = kb_grid(ndof > 0 ? ndof : 1, 256, 8);

@@ -524,3 +524,67 @@ def test_example_scripts_run(script):
         assert "105.18" in out.stdout and "249.7" in out.stdout          # steady_2d_addi.pdf
     if script == "transient_2d.py":
         assert "time increment 0.8" in out.stdout and "199.8" in out.stdout
+
+
+# ------------------------------------------------------------------------------------------------- edge cases
+def test_all_dofs_prescribed_gives_empty_system():
+    """Empty reduced system: LinearSolver returns a copy of b with a warning (FEMSolver.py:358-360)."""
+    import warnings
+    K = _K()
+    m = K.Mesh(element_type="quad"); m.Rectangle((0, 0), (1, 1), 3, 2)
+    d = np.arange(m.nnodes, dtype=np.float64).reshape(-1, 1) + 1.0
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        sol = K.FEMSolver(verbose=False).Solve(formulation=K.HeatDiffusion(m), mesh=m,
+                                               material=K.FourierConduction(2, k=1.0, area=1.0, density=1.0, c_v=1.0),
+                                               boundary_condition=bc)
+    assert np.array_equal(sol.sol[:, 0, 0], d[:, 0])
+    assert any("Empty linear system" in str(x.message) for x in w)
+    assert bc.n_free == 0 and bc.columns_in.shape == (0,)
+
+
+def test_single_element_and_single_free_dof():
+    from oracle import kiltro_oracle as O
+    K = _K()
+    pts, el = O.mesh_rectangle((0, 0), (2.0, 1.0), 1, 1)
+    d = np.full((4, 1), np.nan); d[0] = 10.0; d[1] = 20.0; d[3] = -5.0          # one free DOF
+    m = make_mesh(pts, el)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d)
+    sol = K.FEMSolver(verbose=False).Solve(formulation=K.HeatDiffusion(m), mesh=m,
+                                           material=K.FourierConduction(2, k=3.0, area=1.0, density=1.0, c_v=1.0),
+                                           boundary_condition=bc, solver=K.LinearSolver(tol=1e-14))
+    ref = O.steady_solve(pts, el, None, (3.0, 1.0, 1.0, 1.0, 0.0), d, None, "reference", False)
+    assert rel_l2(sol.sol.ravel(), ref) < 1e-12
+
+
+def test_pattern_with_unused_node_and_repeated_solve_reuse():
+    """A node that belongs to no element yields an empty CSR row (indptr stays flat); the C oracle agrees."""
+    from oracle import kiltro_oracle as O, native as ON
+    K = _K()
+    pts, el = O.mesh_rectangle((0, 0), (1, 1), 4, 3)
+    pts = np.vstack([pts, [[5.0, 5.0]]])                                          # node 20 is unused
+    m = make_mesh(pts, el)
+    got = K.ComputeSparsityPattern(m, 1)
+    want = ON.c_sparsity_pattern(el, pts.shape[0], 1)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert got[1][-1] == got[1][-2]                                              # empty last row
+
+
+def test_line_mesh_steady_large_vs_oracle():
+    from oracle import kiltro_oracle as O
+    K = _K()
+    n = 20000
+    pts, el = O.mesh_line(0.0, 1.0, n)
+    vel = np.full((n + 1, 1), 0.6 * 2.0 * n)                                      # cell Peclet 0.6
+    d = np.full((n + 1, 1), np.nan); d[0] = 1.0; d[-1] = 0.0
+    m = make_mesh(pts, el)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d)
+    solver = K.LinearSolver(tol=1e-12, maxiter=200000, check_every=200)
+    sol = K.FEMSolver(verbose=False).Solve(formulation=K.HeatAdvectionDiffusion(m, velocity=vel), mesh=m,
+                                           material=K.FourierConduction(1, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0),
+                                           boundary_condition=bc, solver=solver)
+    ref = O.steady_solve(pts, el, vel, (1.0, 1.0, 1.0, 1.0, 0.0), d, None, "consistent", False)
+    assert solver.info["status"] == 0, solver.info
+    assert rel_l2(sol.sol.ravel(), ref) < SOL_TOL, solver.info
