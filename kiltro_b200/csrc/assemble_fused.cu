@@ -115,8 +115,8 @@ template <int NDIM> struct Smem {
     static constexpr size_t oStage = oFe + 8 * (size_t)EMAX * NPE;
     static constexpr size_t oV = oStage + 8 * (size_t)EMAX * ElemIO<NDIM>::STAGE_DOUBLES;
     static constexpr size_t oDelta = oV + 8 * (size_t)VMAX;
-    static constexpr size_t oE2R = oDelta + 4 * (size_t)RMAX;
-    static constexpr size_t oScan = oE2R + 2 * (size_t)VMAX;
+    static constexpr size_t oSegOff = oDelta + 4 * (size_t)RMAX;
+    static constexpr size_t oScan = oSegOff + 4 * (size_t)(RMAX + 4);
     static constexpr size_t bytes = oScan + 4 * 64;
 };
 
@@ -136,8 +136,8 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
     double *sFe = reinterpret_cast<double *>(smem_raw + L::oFe);        // [NPE][EMAX]
     double *sStage = reinterpret_cast<double *>(smem_raw + L::oStage);  // cp.async landing zone of the gathers
     double *sV = reinterpret_cast<double *>(smem_raw + L::oV);          // CSR values of the tile's rows
-    int *sDelta = reinterpret_cast<int *>(smem_raw + L::oDelta);        // global position - local position
-    unsigned short *sE2R = reinterpret_cast<unsigned short *>(smem_raw + L::oE2R);   // local entry -> local row
+    int *sDelta = reinterpret_cast<int *>(smem_raw + L::oDelta);        // per run: global position - local position
+    int *sSegOff = reinterpret_cast<int *>(smem_raw + L::oSegOff);      // local offsets of the runs of consecutive rows
     int *sScan = reinterpret_cast<int *>(smem_raw + L::oScan);
 
     const int tid = threadIdx.x;
@@ -145,6 +145,7 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
     if (t >= ntiles) return;
 
     // ---- prologue: everything the first tile needs
+    const int G = gridDim.x;
     int rb = __ldg(tile_row_ptr + t), nr = __ldg(tile_row_ptr + t + 1) - rb;
     int eb = __ldg(tile_elem_ptr + t), ne = __ldg(tile_elem_ptr + t + 1) - eb;
     if (tid < ne) {
@@ -152,15 +153,16 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
         ElemIO<NDIM>::template gather_async<HAS_U>(sStage, tid, points, velocity, c);
     }
     cp_async_commit();
-    int row = 0, jp0 = 0, jp1 = 0;
+    int row = 0, rowp = -2, jp0 = 0, jp1 = 0;
     if (tid < nr) {
         row = __ldg(tile_rows + rb + tid);
+        if (tid > 0) rowp = __ldg(tile_rows + rb + tid - 1);
         jp0 = __ldg(pair_ptr + rb + tid);
         jp1 = __ldg(pair_ptr + rb + tid + 1);
     }
 
-    for (; t < ntiles; t += gridDim.x) {
-        const int tn = t + gridDim.x;
+    for (; t < ntiles; t += G) {
+        const int tn = t + G;
         // extents of the next tile (consumed after phase A)
         int rb_n = 0, nr_n = 0, eb_n = 0, ne_n = 0;
         if (tn < ntiles) {
@@ -198,21 +200,23 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
         }
         cp_async_commit();
         // first-level row metadata of the next tile
-        int row_n = 0, jp0_n = 0, jp1_n = 0;
+        int row_n = 0, rowp_n = -2, jp0_n = 0, jp1_n = 0;
         if (tn < ntiles && tid < nr_n) {
             row_n = __ldg(tile_rows + rb_n + tid);
+            if (tid > 0) rowp_n = __ldg(tile_rows + rb_n + tid - 1);
             jp0_n = __ldg(pair_ptr + rb_n + tid);
             jp1_n = __ldg(pair_ptr + rb_n + tid + 1);
         }
 
-        // ---- row bookkeeping of this tile: local offsets (block scan of the row lengths), entry -> row map
+        // ---- row bookkeeping: one block scan gives the local offset of every row's entries (low 16 bits) and the index
+        // of the run of consecutive rows it belongs to (high bits); a run's entries are contiguous in K.data.
         const int len = tid < nr ? p1 - p0 : 0;
-        int total;
-        const int off = block_scan_excl(len, sScan, &total);
-        if (tid < nr) {
-            sDelta[tid] = p0 - off;
-            for (int k = 0; k < len; ++k) sE2R[off + k] = (unsigned short)tid;
-        }
+        const int segstart = (tid < nr && row != rowp + 1) ? 1 : 0;
+        int packed_total;
+        const int ex = block_scan_excl(len | (segstart << 16), sScan, &packed_total);
+        const int off = ex & 0xffff, total = packed_total & 0xffff, nseg = packed_total >> 16;
+        if (segstart) { sSegOff[ex >> 16] = off; sDelta[ex >> 16] = p0 - off; }
+        if (tid == 0) sSegOff[nseg] = total;
         for (int i = tid; i < total; i += THREADS) sV[i] = 0.0;
         __syncthreads();
 
@@ -241,9 +245,12 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
                 if (pass == 0) Flux[row] = f;
             }
             __syncthreads();
-            // ---- phase C: coalesced write-out
+            // ---- phase C: coalesced write-out, one warp per run of consecutive rows
             double *out = pass == 0 ? K : M;
-            for (int i = tid; i < total; i += THREADS) __stcs(out + i + sDelta[sE2R[i]], sV[i]);
+            for (int sg = tid >> 5; sg < nseg; sg += THREADS / 32) {
+                const int a0 = sSegOff[sg], b0 = sSegOff[sg + 1], dl = sDelta[sg];
+                for (int i = a0 + (tid & 31); i < b0; i += 32) __stcs(out + i + dl, sV[i]);
+            }
             if (MASS && pass == 0) {
                 __syncthreads();
                 if (tid < ne) {
@@ -256,7 +263,7 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
         }
         __syncthreads();                                  // the next tile overwrites the shared buffers
         rb = rb_n; nr = nr_n; eb = eb_n; ne = ne_n;
-        row = row_n; jp0 = jp0_n; jp1 = jp1_n;
+        row = row_n; rowp = rowp_n; jp0 = jp0_n; jp1 = jp1_n;
     }
 }
 

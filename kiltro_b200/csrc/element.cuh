@@ -85,6 +85,24 @@ __device__ __forceinline__ void quad4(const double (&X)[4][2], const double (&U)
     const double Jex[2] = {HHI * e03x + HLO * e12x, HLO * e03x + HHI * e12x};
     const double Jey[2] = {HHI * e03y + HLO * e12y, HLO * e03y + HHI * e12y};
 
+    // the four Jacobian determinants and their reciprocals by one batched inversion (one reciprocal + 9 products
+    // instead of four reciprocals; falls back to plain divisions when the product leaves the safe exponent range)
+    double det4[4], idet4[4];
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+        for (int gj = 0; gj < 2; ++gj) det4[2 * gi + gj] = Jzx[gi] * Jey[gj] - Jzy[gi] * Jex[gj];
+    {
+        const double p01 = det4[0] * det4[1], p23 = det4[2] * det4[3], P = p01 * p23, aP = fabs(P);
+        if (aP > 1.0e-250 && aP < 1.0e250) {
+            const double iP = fast_rcp(P);
+            const double i01 = iP * p23, i23 = iP * p01;
+            idet4[0] = i01 * det4[1]; idet4[1] = i01 * det4[0]; idet4[2] = i23 * det4[3]; idet4[3] = i23 * det4[2];
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) idet4[g] = 1.0 / det4[g];
+        }
+    }
     double D[10];                 // symmetric diffusion part, upper triangle (00 01 02 03 11 12 13 22 23 33)
     double C[16];                 // advection part
     double dV[4];
@@ -102,9 +120,8 @@ __device__ __forceinline__ void quad4(const double (&X)[4][2], const double (&U)
         for (int gj = 0; gj < 2; ++gj) {
             const int g = 2 * gi + gj;
             const double J00 = Jzx[gi], J01 = Jzy[gi], J10 = Jex[gj], J11 = Jey[gj];   // ParentGradientX          :139
-            const double det = J00 * J11 - J01 * J10;
-            const double idet = fast_rcp(det);
-            dV[g] = fabs(det);                                                          // weights are 1.0          :145
+            const double idet = idet4[g];
+            dV[g] = fabs(det4[g]);                                                      // weights are 1.0          :145
             const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;   // inverse   :140
             // gBases at this point: d/dzeta = (-hE0, hE0, hE1, -hE1), d/deta = (-hZ0, -hZ1, hZ1, hZ0)
             const double hE0 = gi == 0 ? HHI : HLO, hE1 = gi == 0 ? HLO : HHI;
