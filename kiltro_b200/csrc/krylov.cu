@@ -623,7 +623,7 @@ struct BodyStep {           // T = fixed ? td : T - dt*y
 // T = fixed ? applied : T - dt*y   (one theta-step update; also used by the partitioned transient loop)
 extern "C" int kb_transient_update(int64_t ndof, const int32_t *d_renum, const double *d_applied, const double *d_y,
                                    double dt, double *d_T, void *stream) {
-    if (!d_renum || !d_applied || !d_y || !d_T || ndof < 0) return KB_EINVAL;
+    if (!d_renum || !d_y || !d_T || ndof < 0) return KB_EINVAL;      // d_applied may be NULL when nothing is prescribed
     if (ndof == 0) return 0;
     const int grid = kb_grid(ndof, 256, 8);
     k_vec<0, BodyStep, NoFin><<<grid, 256, 0, (cudaStream_t)stream>>>(ndof, BodyStep{d_renum, d_applied, d_y, d_T, dt}, nullptr,
@@ -642,7 +642,8 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
                                 const int32_t *d_renum, const double *d_applied, double *d_T, double dt, int nsteps,
                                 const int32_t *h_snap_steps, int nsnap, double *d_snapshots, double rtol, int maxiter,
                                 void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream) {
-    if (!d_indptr || !d_indices || !d_Kff || !d_A || !d_Fm || !d_renum || !d_applied || !d_T || !d_workspace || !h_info ||
+    // d_applied may be NULL when no DOF is prescribed (it is only dereferenced at fixed DOFs)
+    if (!d_indptr || !d_indices || !d_Kff || !d_A || !d_Fm || !d_renum || !d_T || !d_workspace || !h_info ||
         ndof < 1 || nsteps < 0 || nsnap < 0 || (nsnap > 0 && (!h_snap_steps || !d_snapshots)))
         return KB_EINVAL;
     if (workspace_bytes < kb_transient_workspace_bytes(ndof, nnz)) return KB_EWORKSPACE;

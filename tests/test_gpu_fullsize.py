@@ -102,3 +102,31 @@ def test_steady_closed_form_fullsize(big):
     r = Kc.dot(T.reshape(-1))
     free = bc.renum >= 0
     assert float(r[free].abs().max()) < 1e-6 * float(Kc.data.abs().max()) * 500.0
+
+
+def test_transient_heat_conservation_fullsize(big):
+    """Config 3/5 at full size through an invariant: with no Dirichlet DOF and no loads, 1^T K = 0 for pure diffusion, so
+    the total heat 1^T M T^n is conserved by every theta-step (M dT = -dt K T  =>  1^T M dT = 0), and the solution obeys the
+    discrete maximum principle loosely (stays inside the initial range up to the explicit scheme's small overshoot)."""
+    K, mesh, _, mat = big
+    nn = mesh.nnodes
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    T0 = 100.0 + 50.0 * torch.rand((nn, 1), dtype=torch.float64, device="cuda", generator=g)
+    flags = torch.full((nn, 1), float("nan"), dtype=torch.float64, device="cuda")
+    import warnings
+    for theta in (0.0, 0.5):
+        bc = K.BoundaryCondition()
+        bc.SetInitialConditions(lambda: T0); bc.SetDirichletCriteria(lambda: flags)
+        fs = K.FEMSolver(analysis_type="transient", number_of_increments=6, theta=theta, verbose=False)
+        fs.return_device = True
+        fs.snapshot_increments = [0, 5]
+        form = K.HeatDiffusion(mesh)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = fs.Solve(formulation=form, mesh=mesh, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-12))
+        assert fs.solver_info["status"] == 0, fs.solver_info
+        M = K.Assemble(fs, form.function_spaces, form, mesh, mat, bc)[2]
+        h0, h5 = float(M.dot(S[:, 0]).sum()), float(M.dot(S[:, 1]).sum())
+        assert abs(h5 - h0) <= 1e-9 * abs(h0), (theta, h0, h5, fs.solver_info)
+        assert float(S[:, 1].min()) > 90.0 and float(S[:, 1].max()) < 160.0
+        assert float((S[:, 1] - S[:, 0]).abs().max()) > 1e-3          # something did happen
