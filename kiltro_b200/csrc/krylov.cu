@@ -386,16 +386,6 @@ struct FinCgAlpha {         // after q = A p, d0 = <p,q>: alpha = rho / <p,q>
         if (!isfinite(a) || pq == 0.0) done[0] = 2;
     }
 };
-struct BodyCgUpdate {       // x += alpha p ; r -= alpha q ; d0 = <r,r>
-    const double *__restrict__ sc, *__restrict__ p, *__restrict__ q; double *__restrict__ x, *__restrict__ r;
-    __device__ void operator()(int64_t i, double &d0, double &) const {
-        const double a = sc[S_ALPHA];
-        x[i] += a * p[i];
-        const double ri = r[i] - a * q[i];
-        r[i] = ri;
-        d0 += ri * ri;
-    }
-};
 struct FinCgBeta {          // beta = rho_new / rho ; rho = rho_new ; convergence test ; iteration count
     double *sc; int *done; int *iter;
     __device__ void operator()(double rr, double, double = 0.0, double = 0.0) const {
@@ -406,10 +396,6 @@ struct FinCgBeta {          // beta = rho_new / rho ; rho = rho_new ; convergenc
         else if (!(rr > sc[S_TOL2])) { done[0] = 1; done[1] = it; }
     }
 };
-struct BodyCgP {            // p = r + beta p
-    const double *__restrict__ sc, *__restrict__ r; double *__restrict__ p;
-    __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + sc[S_BETA] * p[i]; }
-};
 
 // ---- BiCGSTAB
 struct FinBiAlpha {         // after v = A p, d0 = <rhat,v>: alpha = rho / <rhat,v>
@@ -418,25 +404,6 @@ struct FinBiAlpha {         // after v = A p, d0 = <rhat,v>: alpha = rho / <rhat
         const double a = sc[S_RHO] / rv;
         sc[S_ALPHA] = a;
         if (!isfinite(a) || rv == 0.0) done[0] = 2;
-    }
-};
-struct BodyBiS {            // s = r - alpha v   (in place in r)
-    const double *__restrict__ sc, *__restrict__ v; double *__restrict__ r;
-    __device__ void operator()(int64_t i, double &, double &) const { r[i] -= sc[S_ALPHA] * v[i]; }
-};
-struct FinBiOmega {         // after t = A s, d0 = <s,t>, d1 = <t,t>: omega = <t,s>/<t,t> (0 when t = 0)
-    double *sc;
-    __device__ void operator()(double ts, double tt, double = 0.0, double = 0.0) const { sc[S_OMEGA] = tt > 0.0 ? ts / tt : 0.0; }
-};
-struct BodyBiUpdate {       // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
-    const double *__restrict__ sc, *__restrict__ p, *__restrict__ t, *__restrict__ rhat; double *__restrict__ x, *__restrict__ r;
-    __device__ void operator()(int64_t i, double &d0, double &d1) const {
-        const double a = sc[S_ALPHA], om = sc[S_OMEGA];
-        const double si = r[i];
-        x[i] += a * p[i] + om * si;
-        const double ri = si - om * t[i];
-        r[i] = ri;
-        d0 += rhat[i] * ri; d1 += ri * ri;
     }
 };
 // Merged update (one vector kernel instead of two): with <rhat,t> and <rhat,s> taken in the epilogue of t = A s,
@@ -459,22 +426,6 @@ struct FinBiRes {           // after the merged update: d0 = <r,r>
         const int it = ++iter[0];
         if (!(rr > sc[S_TOL2]) && isfinite(rr)) { done[0] = 1; done[1] = it; }
         else if (!isfinite(rr) || sc[S_AUX1] != 0.0) { done[0] = 2; done[1] = it; }
-    }
-};
-struct FinBiBeta {          // beta = (rho_new/rho)(alpha/omega) ; rho = rho_new ; convergence / breakdown ; iteration count
-    double *sc; int *done; int *iter;
-    __device__ void operator()(double rho_new, double rr, double = 0.0, double = 0.0) const {
-        const double beta = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
-        sc[S_BETA] = beta; sc[S_RHO] = rho_new; sc[S_RES2] = rr;
-        const int it = ++iter[0];
-        if (!(rr > sc[S_TOL2]) && isfinite(rr)) { done[0] = 1; done[1] = it; }
-        else if (!isfinite(beta) || !isfinite(rr) || rho_new == 0.0 || sc[S_OMEGA] == 0.0) { done[0] = 2; done[1] = it; }
-    }
-};
-struct BodyBiP {            // p = r + beta (p - omega v)
-    const double *__restrict__ sc, *__restrict__ r, *__restrict__ v; double *__restrict__ p;
-    __device__ void operator()(int64_t i, double &, double &) const {
-        p[i] = r[i] + sc[S_BETA] * (p[i] - sc[S_OMEGA] * v[i]);
     }
 };
 
@@ -717,38 +668,6 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
 namespace {
 struct FinStore { double *out; __device__ void operator()(double a, double b, double = 0.0, double = 0.0) const { out[0] = a; out[1] = b; } };
 struct BodyDot2 { const double *a, *b; __device__ void operator()(int64_t i, double &d0, double &d1) const { const double bi = b[i]; d0 += a[i] * bi; d1 += bi * bi; } };
-struct BodyAxpyP {          // r -= alpha v
-    const double *__restrict__ alpha, *__restrict__ v; double *__restrict__ r;
-    __device__ void operator()(int64_t i, double &, double &) const { r[i] -= alpha[0] * v[i]; }
-};
-struct BodyBiUpdateP {      // x += alpha p + omega s ; r = s - omega t ; d0 = <rhat,r> ; d1 = <r,r>
-    const double *__restrict__ alpha, *__restrict__ omega, *__restrict__ p, *__restrict__ t, *__restrict__ rhat; double *__restrict__ x, *__restrict__ r;
-    __device__ void operator()(int64_t i, double &d0, double &d1) const {
-        const double a = alpha[0], om = omega[0], si = r[i];
-        x[i] += a * p[i] + om * si;
-        const double ri = si - om * t[i];
-        r[i] = ri;
-        d0 += rhat[i] * ri; d1 += ri * ri;
-    }
-};
-struct BodyBiPP {           // p = r + beta (p - omega v)
-    const double *__restrict__ beta, *__restrict__ omega, *__restrict__ r, *__restrict__ v; double *__restrict__ p;
-    __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * (p[i] - omega[0] * v[i]); }
-};
-struct BodyCgUpdateP {      // x += alpha p ; r -= alpha q ; d0 = <r,r>
-    const double *__restrict__ alpha, *__restrict__ p, *__restrict__ q; double *__restrict__ x, *__restrict__ r;
-    __device__ void operator()(int64_t i, double &d0, double &) const {
-        const double a = alpha[0];
-        x[i] += a * p[i];
-        const double ri = r[i] - a * q[i];
-        r[i] = ri;
-        d0 += ri * ri;
-    }
-};
-struct BodyCgPP {           // p = r + beta p
-    const double *__restrict__ beta, *__restrict__ r; double *__restrict__ p;
-    __device__ void operator()(int64_t i, double &, double &) const { p[i] = r[i] + beta[0] * p[i]; }
-};
 struct BodyMulP {           // out = a .* b
     const double *a, *b; double *out;
     __device__ void operator()(int64_t i, double &, double &) const { out[i] = a[i] * b[i]; }
