@@ -213,7 +213,7 @@ def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier
     def step():
         KD.reassemble(sysm)
         return KD.solve_steady([sysm], comm, rtol=args.rtol, maxiter=args.maxiter or 100000,
-                               check_every=min(args.check_every, 25), method="bicgstab")
+                               check_every=min(args.check_every, 25), method="bicgstab", exchange=args.exchange)
 
     for _ in range(args.warmup):
         sols, info = step()
@@ -251,8 +251,11 @@ def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier
                 "config": {"workload": "S16 per GPU: synthetic 2D structured quad mesh %dx%d nodes (%d DOF total), steady "
                                        "convection-diffusion (consistent Galerkin, cell Pe 0.45 + 10%% noise), "
                                        "Jacobi-BiCGSTAB rtol %.0e, pattern cached" % (nxn, nyn, ndof, args.rtol),
-                           "ndof_per_gpu": nxn * nps, "parallelism": "row-block partition x%d, NCCL halo exchange (1 mesh row "
-                           "per neighbour per SpMV) + all-reduced dots" % world,
+                           "ndof_per_gpu": nxn * nps,
+                           "parallelism": "row-block partition x%d; per SpMV one halo mesh row per neighbour, per dot product a "
+                                          "P-way sum: %s" % (world, "written/summed by the kernels through NVLink peer memory "
+                                          "(NCCL only for the convergence check every 25 iterations)"
+                                          if info.get("exchange") == "peer" else "NCCL send/recv + all-reduce"),
                            "l2_policy": "inputs far larger than the 126 MB L2", "rtol": args.rtol},
                 "solver": {"method": info["method"], "iterations": info["iterations"],
                            "relative_residual": info["relative_residual"], "status": info["status"]},
@@ -279,6 +282,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-nodes-per-side", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo rows / dot products through NVLink peer memory written by the kernels (default) or NCCL")
     ap.add_argument("--idx32", action="store_true", help="keep 32-bit column indices in the solver's SpMV (default: 16-bit "
                     "offsets when the matrix band fits)")
     args = ap.parse_args()

@@ -218,12 +218,16 @@ int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const i
  * once by the caller.  Row-range views of a local CSR are expressed by offsetting d_indptr / d_y / vector pointers.
  * ------------------------------------------------------------------------------------------------------- */
 size_t kb_blocks_scratch_bytes(int64_t nnz);
-int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
-                 const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, double *d_out2,
-                 void *d_scratch, void *stream);                          /* y = A x ; out = {<w,y>, <y,y>} */
-int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_vals,
-                  const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
-                  double *d_out4, void *d_scratch, void *stream);         /* out = {<w,y>, <y,y>, <w2,y>, <w2,w>} */
+/* d_cols16 (optional, from kb_make_cols16): 16-bit column offsets col - row; when given, the kernel streams them instead
+ * of d_indices (10 instead of 12 bytes per non-zero) and d_x must point at the x entry of the FIRST ROW of the view. */
+int kb_make_cols16(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, int16_t *d_cols16, int32_t *d_flag,
+                   void *stream);                                         /* *d_flag = 1 when an offset does not fit */
+int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
+                 const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w,
+                 double *d_out2, void *d_scratch, void *stream);          /* y = A x ; out = {<w,y>, <y,y>} */
+int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
+                  const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w,
+                  const double *d_w2, double *d_out4, void *d_scratch, void *stream);   /* {<w,y>,<y,y>,<w2,y>,<w2,w>} */
 /* merged BiCGSTAB update: x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r> */
 int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,
                          const double *d_t, const double *d_v, double *d_x, double *d_r, double *d_p, double *d_out2,
@@ -259,6 +263,30 @@ int kb_scale_matrix(int64_t nrows, const int32_t *d_indptr, const int32_t *d_ind
 int kb_masked_matrix(int64_t ndof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
                      const double *d_M, const int32_t *d_renum, double c_k, double c_m, int identity_fixed,
                      double *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K9b peer-memory exchange (NVLink / NVSwitch): the partitioned BiCGSTAB iteration without NCCL calls
+ * A rank allocates one IPC-exportable region (control block of 128 words + the SpMV input vectors), all ranks exchange the
+ * 64-byte handles (any transport) and map each other's regions.  Kernels publish partial dot products into every rank's
+ * control block and write their boundary mesh rows straight into the neighbours' halo slots; consumers wait on sequence
+ * flags (csrc/peer.cuh).  Every wait times out into an error word (kb_peer_error) instead of hanging.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct kb_peer_ctx { int32_t nranks, rank; void *ctrl[8]; } kb_peer_ctx;   /* control blocks as mapped locally */
+int kb_peer_alloc(size_t bytes, void **d_ptr, unsigned char *h_handle64);          /* cudaMalloc + zero + IPC handle */
+int kb_peer_open(const unsigned char *h_handle64, void **d_ptr);
+int kb_peer_close(void *d_ptr);
+int kb_peer_free(void *d_ptr);
+int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *stream);           /* 0 ok, 1/2: a wait timed out */
+int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
+                 const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
+                 const kb_peer_ctx *ctx, uint64_t event, int wait_vec, uint64_t wait_seq, void *d_scratch, void *stream);
+int kb_peer_bicgstab_s(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho,
+                       const double *d_v, double *d_r, double *d_alpha_out, double *d_dn_dst, double *d_up_dst,
+                       uint64_t halo_seq, void *d_scratch, void *stream);
+int kb_peer_bicgstab_update_p(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho_in,
+                              double *d_rho_out, const double *d_alpha, const double *d_t, const double *d_v, double *d_x,
+                              double *d_r, double *d_p, double *d_dn_dst, double *d_up_dst, uint64_t halo_seq,
+                              double *d_out2, void *d_scratch, void *stream);
 
 #ifdef __cplusplus
 }

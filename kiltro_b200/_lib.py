@@ -17,6 +17,10 @@ class kb_material(ctypes.Structure):
     _fields_ = [("k", F64), ("rho", F64), ("c_v", F64), ("area", F64), ("q", F64)]
 
 
+class kb_peer_ctx(ctypes.Structure):
+    _fields_ = [("nranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("ctrl", ctypes.c_void_p * 8)]
+
+
 class kb_solve_info(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("residual", F64), ("rhs_norm", F64),
                 ("kernel_launches", I64)]
@@ -73,8 +77,9 @@ SIGNATURES = {
                                ctypes.POINTER(kb_solve_info), c_vp]),
     "kb_mesh_rectangle_strip": (I32, [F64, F64, F64, F64, I64, I64, I64, I64, c_vp, c_vp, c_vp]),
     "kb_blocks_scratch_bytes": (ctypes.c_size_t, [I64]),
-    "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_make_cols16": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_update_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_s2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_update_p2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -91,6 +96,17 @@ SIGNATURES = {
     "kb_diag_scale": (I32, [I64, c_vp, c_vp, c_vp, I32, c_vp, c_vp]),
     "kb_scale_matrix": (I32, [I64, c_vp, c_vp, c_vp, I32, c_vp, c_vp, c_vp]),
     "kb_masked_matrix": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, F64, I32, c_vp, c_vp]),
+    "kb_peer_alloc": (I32, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "kb_peer_open": (I32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "kb_peer_close": (I32, [c_vp]),
+    "kb_peer_free": (I32, [c_vp]),
+    "kb_peer_error": (I32, [ctypes.POINTER(kb_peer_ctx), ctypes.POINTER(I64), c_vp]),
+    "kb_peer_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_peer_ctx),
+                           ctypes.c_uint64, I32, ctypes.c_uint64, c_vp, c_vp]),
+    "kb_peer_bicgstab_s": (I32, [I64, I64, ctypes.POINTER(kb_peer_ctx), ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 ctypes.c_uint64, c_vp, c_vp]),
+    "kb_peer_bicgstab_update_p": (I32, [I64, I64, ctypes.POINTER(kb_peer_ctx), ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_vp]),
 }
 
 _LIB = None

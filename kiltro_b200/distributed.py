@@ -157,24 +157,31 @@ class LocalSystem(object):
     def __init__(self, part):
         self.part = part
         self.lib = _lib.load()
+        self.cols16 = None
 
     def _view(self, A_vals):
         """Row-range view (owned rows) of the local CSR for the SpMV kernel."""
         return A_vals
 
+    def xptr(self, x, row0):
+        """x argument of the SpMV kernels for a row view starting at local row `row0`: with 16-bit column offsets the
+        kernel addresses x relative to the first row of the view."""
+        return x.data_ptr() + (8 * row0 if self.cols16 is not None else 0)
+
     def spmv_dots(self, vals, x, y, w, out2):
         p = self.part
         _lib.check(self.lib.kb_spmv_dots(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
-                                         D.ptr(self.indices), D.ptr(vals), D.ptr(self.rowblk), D.ptr(x),
-                                         y.data_ptr() + 8 * p.own_off, w.data_ptr() + 8 * p.own_off, D.ptr(out2),
-                                         D.ptr(self.scratch), D.stream_ptr()))
+                                         D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(self.rowblk),
+                                         self.xptr(x, p.own_off), y.data_ptr() + 8 * p.own_off,
+                                         w.data_ptr() + 8 * p.own_off, D.ptr(out2), D.ptr(self.scratch), D.stream_ptr()))
 
     def spmv_dots4(self, vals, x, y, w, w2, out4):
         p = self.part
         _lib.check(self.lib.kb_spmv_dots4(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
-                                          D.ptr(self.indices), D.ptr(vals), D.ptr(self.rowblk), D.ptr(x),
-                                          y.data_ptr() + 8 * p.own_off, w.data_ptr() + 8 * p.own_off,
-                                          w2.data_ptr() + 8 * p.own_off, D.ptr(out4), D.ptr(self.scratch), D.stream_ptr()))
+                                          D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(self.rowblk),
+                                          self.xptr(x, p.own_off), y.data_ptr() + 8 * p.own_off,
+                                          w.data_ptr() + 8 * p.own_off, w2.data_ptr() + 8 * p.own_off, D.ptr(out4),
+                                          D.ptr(self.scratch), D.stream_ptr()))
 
     def spmv(self, vals, x, y):
         p = self.part
@@ -209,11 +216,12 @@ class LocalSystem(object):
         ip = self.indptr.data_ptr() + 4 * r0
         yp, wp = y.data_ptr() + 8 * r0, w.data_ptr() + 8 * r0
         if w2 is None:
-            _lib.check(self.lib.kb_spmv_dots(nr, nnz, ip, D.ptr(self.indices), D.ptr(vals), D.ptr(rb), D.ptr(x), yp, wp,
-                                             D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
+            _lib.check(self.lib.kb_spmv_dots(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(rb),
+                                             self.xptr(x, r0), yp, wp, D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
         else:
-            _lib.check(self.lib.kb_spmv_dots4(nr, nnz, ip, D.ptr(self.indices), D.ptr(vals), D.ptr(rb), D.ptr(x), yp, wp,
-                                              w2.data_ptr() + 8 * r0, D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
+            _lib.check(self.lib.kb_spmv_dots4(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(rb),
+                                              self.xptr(x, r0), yp, wp, w2.data_ptr() + 8 * r0, D.ptr(out),
+                                              D.ptr(self.scratch), D.stream_ptr()))
 
 
 def spmv_overlapped(systems, comm, vals, x, y, w, w2, out):
@@ -292,6 +300,10 @@ def reassemble(sysm):
                                          D.ptr(sysm.rowblk), D.stream_ptr()))
         sysm.scratch = D.zeros(lib.kb_blocks_scratch_bytes(sysm.nnz_own), torch.uint8)
         sysm.build_ranges()
+        # 16-bit column offsets (10 instead of 12 bytes per non-zero in the SpMV) when the local band fits
+        c16 = D.empty(K.nnz + 8, torch.int16); flag = D.zeros(1, torch.int32)
+        _lib.check(lib.kb_make_cols16(part.n_loc, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(c16), D.ptr(flag), D.stream_ptr()))
+        sysm.cols16 = c16 if (int(flag.item()) == 0 and part.nxn % 4 == 0 and K.indptr.data_ptr() % 16 == 0) else None
     n = part.n_loc
     # right-hand side of the steady problem on A' = [Kff 0; 0 I]:  F - K[:,fixed] T_D at free rows, T_D at fixed rows
     F = (-Fn).contiguous()
@@ -459,9 +471,138 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
     return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
 
 
+# ------------------------------------------------------------------------------------------------------ peer-memory path
+class _RawCuda(object):
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view IPC memory without copying."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _align256(x):
+    return (x + 255) // 256 * 256
+
+
+class PeerRegion(object):
+    """IPC-mapped memory of one rank (control block + the two SpMV input vectors p and r) and the mappings of every
+    other rank's region: what the peer-memory kernels (csrc/peer.cuh) write into.  Needs one process per GPU with NVLink
+    peer access (a B200 HGX node); collectives are only used to exchange the 64-byte IPC handles."""
+    CTRL_BYTES = 1024
+
+    def __init__(self, part, dist):
+        import ctypes
+        lib = _lib.load()
+        self.part, self.lib = part, lib
+        P, rank = part.world, part.rank
+        if P > 8:
+            raise ValueError("the peer-memory path supports up to 8 ranks")
+        self.stride = _align256(part.n_loc * 8)
+        nbytes = self.CTRL_BYTES + 2 * self.stride
+        base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.kb_peer_alloc(nbytes, ctypes.byref(base), handle))
+        self.base = [None] * P
+        self.base[rank] = base.value
+        info = [None] * P
+        dist.all_gather_object(info, (bytes(handle.raw), part.n_loc, part.own_off, part.n_own))
+        for r in range(P):
+            if r != rank:
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.kb_peer_open(info[r][0], ctypes.byref(ptr)))
+                self.base[r] = ptr.value
+        self.ctx = _lib.kb_peer_ctx()
+        self.ctx.nranks, self.ctx.rank = P, rank
+        for r in range(P):
+            self.ctx.ctrl[r] = self.base[r]
+        self.vec = [torch.as_tensor(_RawCuda(self.base[rank] + self.CTRL_BYTES + k * self.stride, part.n_loc), device="cuda")
+                    for k in range(2)]
+
+        def slot(r, k, offset_elems):
+            stride_r = _align256(info[r][1] * 8)
+            return self.base[r] + self.CTRL_BYTES + k * stride_r + 8 * offset_elems
+
+        # halo_above slot of rank-1 / halo_below slot of rank+1, for vector k (0 = p, 1 = r)
+        self.dn_dst = [slot(rank - 1, k, info[rank - 1][2] + info[rank - 1][3]) if rank > 0 else None for k in range(2)]
+        self.up_dst = [slot(rank + 1, k, 0) if rank < P - 1 else None for k in range(2)]
+        self.ev = 0          # dot-product events and halo sequence numbers run on across solves (flags are monotonic)
+        self.hseq = [0, 0]
+        dist.barrier()
+
+    def error(self):
+        e = _lib.I64(0)
+        _lib.check(self.lib.kb_peer_error(self.ctx, e, D.stream_ptr()))
+        return int(e.value)
+
+
+def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
+    """The partitioned BiCGSTAB iteration with no NCCL call inside: partial dot products and halo rows travel through
+    NVLink peer memory, written by the kernels themselves (kb_peer_*).  One part per process.  NCCL is used for the
+    setup residual and for the ||r|| all-reduce when convergence is looked at (every check_every iterations)."""
+    part, lib, st = sysm.part, sysm.lib, D.stream_ptr
+    n, nxn, off = part.n_own, part.nxn, part.own_off
+    z = lambda: D.zeros(part.n_loc)
+    p, r = region.vec[0], region.vec[1]
+    p.zero_(); r.zero_()
+    rhat, v, t = z(), z(), z()
+    dr = D.zeros(2)
+    rho = [D.zeros(1), D.zeros(1)]; alpha = D.zeros(1)
+    cur = 0
+    own = lambda vec: vec.data_ptr() + 8 * off
+    ip = sysm.indptr.data_ptr() + 4 * off
+    # r = b - A x ; rhat = p = r ; first halo of p through NCCL
+    comm.halo_exchange([part], [x])
+    sysm.spmv(Ahat, x, v)
+    _lib.check(lib.kb_residual(n, own(b), own(v), own(r), D.ptr(dr), D.ptr(sysm.scratch), st()))
+    comm.allreduce([dr])
+    rr0, bb = float(dr[0]), float(dr[1])
+    tol2 = rtol * rtol * bb
+    if not (rr0 > tol2):
+        return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    rhat.copy_(r); p.copy_(r); rho[0].copy_(dr[0:1])
+    comm.halo_exchange([part], [p])
+    torch.cuda.synchronize(); comm.barrier()            # every rank's setup is complete before peers start writing
+    it, rr, status, first = 0, rr0, 0, True
+    A = (D.ptr(sysm.indices), D.ptr(Ahat), D.ptr(sysm.rowblk), D.ptr(sysm.cols16))
+    while it < maxiter:
+        for _ in range(min(check_every, maxiter - it)):
+            region.ev += 1                               # v = A p ; {<rhat,v>}
+            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], A[1], A[2], sysm.xptr(p, off), own(v), own(rhat), None, region.ctx,
+                                        region.ev, -1 if first else 0, region.hseq[0], D.ptr(sysm.scratch), st()))
+            first = False
+            region.hseq[1] += 1                          # alpha ; s = r - alpha v ; boundary rows of s -> neighbours
+            _lib.check(lib.kb_peer_bicgstab_s(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), own(v), own(r), D.ptr(alpha),
+                                              region.dn_dst[1], region.up_dst[1], region.hseq[1], D.ptr(sysm.scratch), st()))
+            region.ev += 1                               # t = A s ; {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
+            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], A[1], A[2], sysm.xptr(r, off), own(t), own(r), own(rhat), region.ctx,
+                                        region.ev, 1, region.hseq[1], D.ptr(sysm.scratch), st()))
+            region.hseq[0] += 1                          # omega, rho, beta ; x, r, p ; boundary rows of p -> neighbours
+            _lib.check(lib.kb_peer_bicgstab_update_p(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), D.ptr(rho[cur ^ 1]),
+                                                     D.ptr(alpha), own(t), own(v), own(x), own(r), own(p), region.dn_dst[0],
+                                                     region.up_dst[0], region.hseq[0], D.ptr(dr), D.ptr(sysm.scratch), st()))
+            cur ^= 1
+            it += 1
+        comm.allreduce([dr])
+        rr = float(dr[0])
+        if region.error():
+            raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
+        if not np.isfinite(rr):
+            status = _lib.KB_EBREAKDOWN
+            break
+        if rr <= tol2:
+            break
+    else:
+        status = _lib.KB_ENOTCONV
+    if status == 0 and rr > tol2:
+        status = _lib.KB_ENOTCONV
+    torch.cuda.synchronize(); comm.barrier()
+    return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
+
+
 # ------------------------------------------------------------------------------------------------------ drivers
-def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto"):
-    """Partitioned steady solve.  Returns (list of owned-solution tensors (n_own,), info)."""
+def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto", exchange="nccl"):
+    """Partitioned steady solve.  Returns (list of owned-solution tensors (n_own,), info).
+    exchange: "nccl" (halo rows and dot products through torch.distributed) or "peer" (BiCGSTAB only, one part per process:
+    the kernels exchange them through NVLink peer memory, no collective inside the iteration)."""
     mats = [_masked(s, 1.0, 0.0, 1) for s in systems]
     sym = all(s.symmetric for s in systems) if method == "auto" else (method == "cg")
     mode = 1 if sym else 0
@@ -473,7 +614,15 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if mode == 1:
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(s.b), D.ptr(sc), D.ptr(bb), D.stream_ptr()))
         b.append(bb); x.append(D.zeros(s.part.n_loc))
-    info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, maxiter, check_every)
+    if exchange == "peer" and not sym and len(systems) == 1 and isinstance(comm, DistComm) and comm.world > 1:
+        s0 = systems[0]
+        if getattr(s0, "peer_region", None) is None:
+            s0.peer_region = PeerRegion(s0.part, comm.dist)
+        info = dist_bicgstab_peer(s0, comm, s0.peer_region, Ahat[0], b[0], x[0], rtol, maxiter, check_every)
+        info["exchange"] = "peer"
+    else:
+        info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, maxiter, check_every)
+        info["exchange"] = "nccl" if isinstance(comm, DistComm) else "local"
     info["method"] = "cg" if sym else "bicgstab"
     sols = []
     for s, sc, xh in zip(systems, scales, x):
