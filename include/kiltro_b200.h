@@ -117,14 +117,37 @@ int kb_tile_plan_build(const int32_t *d_elements, int64_t nelem, int npe, int64_
                        int32_t *d_tile_rows, int32_t *d_tile_row_ptr, int32_t *d_tile_elems, int32_t *d_tile_conn,
                        int32_t *d_tile_elem_ptr, uint32_t *d_pair_rec, int32_t *d_pair_ptr, int64_t *h_info,
                        void *stream);
-/* d_M may be NULL (steady).  d_velocity may be NULL. */
+/* d_M may be NULL (steady).  d_velocity may be NULL.  d_scratch: ntiles + 32 bytes (flags of the tiles holding a quad the
+ * fast element routine declines -- non-convex / inverted -- which a second, normally empty, launch redoes). */
 int kb_assemble_fused(int ndim, const double *d_points, const int32_t *d_elements, int64_t nelem, int64_t nnode,
                       const double *d_velocity, const kb_material *material, int mode, int petrov,
                       const int32_t *d_indptr, const int32_t *d_indices,
                       int64_t ntiles, const int32_t *d_tile_rows, const int32_t *d_tile_row_ptr,
                       const int32_t *d_tile_conn, const int32_t *d_tile_elem_ptr,
                       const uint32_t *d_pair_rec, const int32_t *d_pair_ptr,
-                      double *d_K, double *d_M, double *d_Flux, void *stream);
+                      double *d_K, double *d_M, double *d_Flux, void *d_scratch, void *stream);
+
+/* (c) fused path, template form (quad-4 meshes whose tiles repeat: everything Mesh.Rectangle generates,
+ *     MeshGeneration/Mesh.py:33-58, and row-block strips of it).  kb_tile_tmpl_build classifies the tiles of a plan by
+ *     their LOCAL structure (layout in csrc/tileplan.cuh) and stores one template per class; kb_assemble_fused_tmpl then
+ *     reads, per tile, only the tile-local connectivity and one (row, indptr) pair per run of rows.  Same summation order
+ *     and results as kb_assemble_fused.
+ *     kb_tile_tmpl_sizes -> h_sizes = {bytes per template, max templates, max runs per tile}.
+ *     kb_tile_tmpl_build: d_tile_class (ntiles bytes), d_trun_ptr (ntiles+1), d_trun_row (capacity nnode),
+ *     d_templates (max templates x bytes per template); h_info = {usable (1/0), templates, runs}; synchronises.
+ *     kb_assemble_fused_tmpl: d_scratch = ntiles + 32 bytes (flags of the tiles holding an element the fast element
+ *     routine declines -- non-convex / inverted quads -- which a second, normally empty, launch redoes). */
+int kb_tile_tmpl_sizes(int64_t *h_sizes);
+int kb_tile_tmpl_build(int npe, int64_t nnode, int64_t ntiles, const int32_t *d_indptr, const int32_t *d_tile_rows,
+                       const int32_t *d_tile_row_ptr, const int32_t *d_tile_elem_ptr, const uint32_t *d_pair_rec,
+                       const int32_t *d_pair_ptr, uint8_t *d_tile_class, int32_t *d_trun_ptr, int32_t *d_trun_row,
+                       void *d_templates, int64_t *h_info, void *stream);
+int kb_assemble_fused_tmpl(const double *d_points, int64_t nnode, const double *d_velocity,
+                           const kb_material *material, int mode, int petrov, const int32_t *d_indptr,
+                           int64_t ntiles, const int32_t *d_tile_conn, const int32_t *d_tile_elem_ptr,
+                           const uint8_t *d_tile_class, const int32_t *d_trun_ptr, const int32_t *d_trun_row,
+                           const void *d_templates, double *d_K, double *d_M, double *d_Flux, void *d_scratch,
+                           void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K4  boundary conditions                   replaces kiltro/BoundaryCondition.py

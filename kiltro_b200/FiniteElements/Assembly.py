@@ -3,7 +3,9 @@
 Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_condition) -> (K, Flux, M) with K / M as
 DeviceCSR on the pattern cached on fem_solver (FEMSolver.ComputeSparsityFEM) and Flux a device (ndof, 1) tensor.  The
 per-element Python loop of the reference (Assembly.py:46-72) becomes either
-  * the fused kernel (element matrices on chip, row-owner gather, csrc/assemble.cu), or
+  * the fused kernel (element matrices on chip; csrc/assemble_tmpl.cu when the tiles of the mesh repeat -- every
+    Mesh.Rectangle mesh -- else the generic csrc/assemble_fused.cu; fem_solver.assembly = "fused_generic" forces the
+    latter), or
   * the two-step seam K1 (kb_element_matrices) + K3 (kb_assemble_from_elements) when fem_solver.assembly == "two_pass".
 The dense AssemblyRobinForces pass whose result the reference discards (Assembly.py:90,121-175) is not run."""
 import torch
@@ -28,15 +30,15 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
     M = D.empty(sp.nnz) if transient else None
     Flux = D.empty((nnode * formulation.nvar, 1))
     method = getattr(fem_solver, "assembly", "auto")
-    if method not in ("auto", "fused", "two_pass"):
-        raise ValueError("assembly must be 'auto', 'fused' or 'two_pass'")
+    if method not in ("auto", "fused", "fused_generic", "two_pass"):
+        raise ValueError("assembly must be 'auto', 'fused', 'fused_generic' or 'two_pass'")
     use_fused = False
     if method != "two_pass" and formulation.nvar == 1:
         from .fused import assemble_fused, build_tile_plan
         if sp.tile_plan is None:
             sp.tile_plan = build_tile_plan(sp, mesh)             # symbolic, cached with the pattern
         use_fused = sp.tile_plan.fits
-        if method == "fused" and not use_fused:
+        if method in ("fused", "fused_generic") and not use_fused:
             raise _lib.KiltroB200Error("the tile plan of this mesh does not fit the fused assembly kernel: %r"
                                        % (sp.tile_plan.info,))
     fem_solver.assembly_used = "fused" if use_fused else "two_pass"

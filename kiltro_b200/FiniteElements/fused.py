@@ -11,6 +11,9 @@ class TilePlan(object):
         self.pair_rec = self.pair_ptr = None
         self.info = {}
         self.fits = False
+        # template form (csrc/tiletmpl.cu): usable when the tiles of the mesh repeat
+        self.templated = False
+        self.tile_class = self.trun_ptr = self.trun_row = self.templates = self.scratch = None
 
 
 def build_tile_plan(sp, mesh):
@@ -48,7 +51,32 @@ def build_tile_plan(sp, mesh):
                  "max_entries_per_tile": int(info[5]), "structured": bool(info[7]),
                  "rim_factor": float(info[1]) / max(nelem, 1)}
     plan.fits = bool(info[6])
+    plan.scratch = D.empty(plan.ntiles + 32, torch.uint8)
+    if plan.fits and npe == 4:
+        _build_templates(lib, plan, sp, nnode, npe)
     return plan
+
+
+def _build_templates(lib, plan, sp, nnode, npe):
+    """Symbolic phase, part 3: classify the tiles by local structure; one template per class (tiletmpl.cu)."""
+    sizes = (_lib.I64 * 3)()
+    _lib.check(lib.kb_tile_tmpl_sizes(sizes))
+    tile_class = D.empty(plan.ntiles, torch.uint8)
+    trun_ptr = D.empty(plan.ntiles + 1, torch.int32)
+    trun_row = D.empty(nnode, torch.int32)
+    templates = D.empty(int(sizes[0]) * int(sizes[1]), torch.uint8)
+    info = (_lib.I64 * 3)()
+    _lib.check(lib.kb_tile_tmpl_build(npe, nnode, plan.ntiles, D.ptr(sp.indptr), D.ptr(plan.tile_rows),
+                                      D.ptr(plan.tile_row_ptr), D.ptr(plan.tile_elem_ptr), D.ptr(plan.pair_rec),
+                                      D.ptr(plan.pair_ptr), D.ptr(tile_class), D.ptr(trun_ptr), D.ptr(trun_row),
+                                      D.ptr(templates), info, D.stream_ptr()))
+    plan.info["templates"] = int(info[1])
+    plan.info["template_runs"] = int(info[2])
+    plan.templated = bool(info[0])
+    if plan.templated:
+        plan.tile_class, plan.trun_ptr = tile_class, trun_ptr
+        plan.trun_row = trun_row[:max(int(info[2]), 1)].clone()
+        plan.templates = templates[:int(sizes[0]) * int(info[1])].clone()
 
 
 def assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux):
@@ -58,9 +86,18 @@ def assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux):
     el = mesh.device_elements()
     vel = formulation.device_velocity()
     mat = material.as_struct()
+    kind = getattr(fem_solver, "assembly", "auto")
+    if plan.templated and formulation.ndim == 2 and kind != "fused_generic":
+        fem_solver.assembly_used = "fused_template"
+        _lib.check(lib.kb_assemble_fused_tmpl(D.ptr(pts), int(mesh.nnodes), D.ptr(vel), mat, int(formulation.mode),
+                                              int(bool(formulation.petrov)), D.ptr(sp.indptr), plan.ntiles,
+                                              D.ptr(plan.tile_conn), D.ptr(plan.tile_elem_ptr), D.ptr(plan.tile_class),
+                                              D.ptr(plan.trun_ptr), D.ptr(plan.trun_row), D.ptr(plan.templates),
+                                              D.ptr(K), D.ptr(M), D.ptr(Flux), D.ptr(plan.scratch), D.stream_ptr()))
+        return
     _lib.check(lib.kb_assemble_fused(formulation.ndim, D.ptr(pts), D.ptr(el), int(el.shape[0]), int(mesh.nnodes),
                                      D.ptr(vel), mat, int(formulation.mode), int(bool(formulation.petrov)),
                                      D.ptr(sp.indptr), D.ptr(sp.indices), plan.ntiles, D.ptr(plan.tile_rows),
                                      D.ptr(plan.tile_row_ptr), D.ptr(plan.tile_conn), D.ptr(plan.tile_elem_ptr),
                                      D.ptr(plan.pair_rec), D.ptr(plan.pair_ptr), D.ptr(K), D.ptr(M), D.ptr(Flux),
-                                     D.stream_ptr()))
+                                     D.ptr(plan.scratch), D.stream_ptr()))

@@ -49,7 +49,12 @@ SIGNATURES = {
     "kb_tile_plan_build": (I32, [c_vp, I64, I32, I64, c_vp, c_vp, c_vp, c_vp, c_vp, I64, I64, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
     "kb_assemble_fused": (I32, [I32, c_vp, c_vp, I64, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, c_vp, I64,
-                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_tile_tmpl_sizes": (I32, [ctypes.POINTER(I64)]),
+    "kb_tile_tmpl_build": (I32, [I32, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 ctypes.POINTER(I64), c_vp]),
+    "kb_assemble_fused_tmpl": (I32, [c_vp, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, I64, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
     "kb_neumann_fluxes": (I32, [c_vp, I64, c_vp, c_vp]),
     "kb_apply_dirichlet_reduce": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, I64, c_vp, c_vp, c_vp,

@@ -59,8 +59,8 @@ template <> struct ElemIO<2> {
             if (HAS_U) cp_async16(s2 + (4 + a) * EMAX + tid, reinterpret_cast<const double2 *>(velocity) + n[a]);
         }
     }
-    template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[16],
+    template <bool HAS_U, bool MASS, bool GENERAL>
+    static __device__ __forceinline__ bool eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[16],
                                                 double (&fe)[4], double (&me)[16]) {
         const double2 *s2 = reinterpret_cast<const double2 *>(stage);
         double X[4][2], U[4][2];
@@ -71,7 +71,8 @@ template <> struct ElemIO<2> {
             if (HAS_U) { const double2 u = s2[(4 + a) * EMAX + tid]; U[a][0] = u.x; U[a][1] = u.y; }
             else { U[a][0] = 0.0; U[a][1] = 0.0; }
         }
-        quad4(X, U, o, ke, fe, me);
+        if (GENERAL) { quad4_general(X, U, o, ke, fe, me); return true; }
+        return quad4_fast(X, U, o, ke, fe, me);
     }
 };
 template <> struct ElemIO<1> {
@@ -88,13 +89,14 @@ template <> struct ElemIO<1> {
         cp_async8(stage + 1 * EMAX + tid, points + c.y);
         if (HAS_U) { cp_async8(stage + 2 * EMAX + tid, velocity + c.x); cp_async8(stage + 3 * EMAX + tid, velocity + c.y); }
     }
-    template <bool HAS_U, bool MASS>
-    static __device__ __forceinline__ void eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[4],
+    template <bool HAS_U, bool MASS, bool GENERAL>
+    static __device__ __forceinline__ bool eval(const double *stage, int tid, const ElemOpts &o, double (&ke)[4],
                                                 double (&fe)[2], double (&me)[4]) {
         double X[2] = {stage[0 * EMAX + tid], stage[1 * EMAX + tid]};
         double U[2] = {0.0, 0.0};
         if (HAS_U) { U[0] = stage[2 * EMAX + tid]; U[1] = stage[3 * EMAX + tid]; }
         line2(X, U, o, ke, fe, me);
+        return true;
     }
 };
 
@@ -120,14 +122,17 @@ template <int NDIM> struct Smem {
     static constexpr size_t bytes = oScan + 4 * 64;
 };
 
-template <int NDIM, bool HAS_U, bool MASS>
+// GENERAL = false: every tile, with the sum-factorised quad-4 routine; an element it declines (non-convex / inverted /
+// extreme scale) flags its tile in bad_tile and raises *nbad.  GENERAL = true: the fix-up launch that follows -- only
+// the flagged tiles, general element routine; exits at once when *nbad == 0 (the normal case).
+template <int NDIM, bool HAS_U, bool MASS, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, 2)
 k_assemble_fused(const double *__restrict__ points, const double *__restrict__ velocity, ElemOpts o,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                  const int32_t *__restrict__ tile_rows, const int32_t *__restrict__ tile_row_ptr,
                  const int32_t *__restrict__ tile_conn, const int32_t *__restrict__ tile_elem_ptr,
                  const uint32_t *__restrict__ pair_rec, const int32_t *__restrict__ pair_ptr, double *__restrict__ K,
-                 double *__restrict__ M, double *__restrict__ Flux, int ntiles) {
+                 double *__restrict__ M, double *__restrict__ Flux, int ntiles, uint8_t *bad_tile, int *nbad) {
     constexpr int NPE = ElemIO<NDIM>::NPE, CAP = NPE * NPE;
     typedef Smem<NDIM> L;
     typedef typename ElemIO<NDIM>::Conn Conn;
@@ -141,11 +146,17 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
     int *sScan = reinterpret_cast<int *>(smem_raw + L::oScan);
 
     const int tid = threadIdx.x;
-    int t = blockIdx.x;
+    const int G = gridDim.x;
+    if (GENERAL && *reinterpret_cast<volatile int *>(nbad) == 0) return;
+    auto next_tile = [&](int t) {
+        t += G;
+        if (GENERAL) while (t < ntiles && !bad_tile[t]) t += G;
+        return t;
+    };
+    int t = next_tile((int)blockIdx.x - G);
     if (t >= ntiles) return;
 
     // ---- prologue: everything the first tile needs
-    const int G = gridDim.x;
     int rb = __ldg(tile_row_ptr + t), nr = __ldg(tile_row_ptr + t + 1) - rb;
     int eb = __ldg(tile_elem_ptr + t), ne = __ldg(tile_elem_ptr + t + 1) - eb;
     if (tid < ne) {
@@ -161,8 +172,8 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
         jp1 = __ldg(pair_ptr + rb + tid + 1);
     }
 
-    for (; t < ntiles; t += G) {
-        const int tn = t + G;
+    for (; t < ntiles;) {
+        const int tn = next_tile(t);
         // extents of the next tile (consumed after phase A)
         int rb_n = 0, nr_n = 0, eb_n = 0, ne_n = 0;
         if (tn < ntiles) {
@@ -187,7 +198,10 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
         double me[CAP];
         if (tid < ne) {
             double ke[CAP], fe[NPE];
-            ElemIO<NDIM>::template eval<HAS_U, MASS>(sStage, tid, o, ke, fe, me);
+            if (!ElemIO<NDIM>::template eval<HAS_U, MASS, GENERAL>(sStage, tid, o, ke, fe, me)) {
+                bad_tile[t] = 1;                          // redone by the fix-up launch
+                *nbad = 1;
+            }
 #pragma unroll
             for (int i = 0; i < CAP; ++i) sKe[i * EMAX + tid] = ke[i];
 #pragma unroll
@@ -262,6 +276,7 @@ k_assemble_fused(const double *__restrict__ points, const double *__restrict__ v
             }
         }
         __syncthreads();                                  // the next tile overwrites the shared buffers
+        t = tn;
         rb = rb_n; nr = nr_n; eb = eb_n; ne = ne_n;
         row = row_n; rowp = rowp_n; jp0 = jp0_n; jp1 = jp1_n;
     }
@@ -271,20 +286,31 @@ template <int NDIM, bool HAS_U, bool MASS>
 int launch_fused(int64_t ntiles, cudaStream_t s, const double *points, const double *velocity, const ElemOpts &o,
                  const int32_t *indptr, const int32_t *indices, const int32_t *tile_rows, const int32_t *tile_row_ptr,
                  const int32_t *tile_conn, const int32_t *tile_elem_ptr, const uint32_t *pair_rec,
-                 const int32_t *pair_ptr, double *K, double *M, double *Flux) {
+                 const int32_t *pair_ptr, double *K, double *M, double *Flux, uint8_t *scratch) {
     static bool configured = false;
     constexpr size_t bytes = Smem<NDIM>::bytes;
     if (!configured) {
-        KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bytes));
+        KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = true;
     }
     const int64_t cap = (int64_t)kb_num_sms() * 2;           // persistent: 2 CTAs per SM
     const int grid = (int)(ntiles < cap ? ntiles : cap);
-    k_assemble_fused<NDIM, HAS_U, MASS><<<grid, THREADS, bytes, s>>>(
+    const size_t flag_bytes = ((size_t)ntiles + 15) / 16 * 16;
+    int *nbad = reinterpret_cast<int *>(scratch + flag_bytes);
+    if (NDIM == 2) KB_CUDA(cudaMemsetAsync(scratch, 0, flag_bytes + 16, s));
+    k_assemble_fused<NDIM, HAS_U, MASS, false><<<grid, THREADS, bytes, s>>>(
         points, velocity, o, indptr, indices, tile_rows, tile_row_ptr, tile_conn, tile_elem_ptr, pair_rec, pair_ptr, K, M,
-        Flux, (int)ntiles);
+        Flux, (int)ntiles, scratch, nbad);
     KB_LAUNCH_CHECK();
+    if (NDIM == 2) {                                          // line elements never decline
+        k_assemble_fused<NDIM, HAS_U, MASS, true><<<grid, THREADS, bytes, s>>>(
+            points, velocity, o, indptr, indices, tile_rows, tile_row_ptr, tile_conn, tile_elem_ptr, pair_rec, pair_ptr,
+            K, M, Flux, (int)ntiles, scratch, nbad);
+        KB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -296,9 +322,9 @@ extern "C" int kb_assemble_fused(int ndim, const double *d_points, const int32_t
                                  const int32_t *d_tile_rows, const int32_t *d_tile_row_ptr,
                                  const int32_t *d_tile_conn, const int32_t *d_tile_elem_ptr,
                                  const uint32_t *d_pair_rec, const int32_t *d_pair_ptr, double *d_K, double *d_M,
-                                 double *d_Flux, void *stream) {
+                                 double *d_Flux, void *d_scratch, void *stream) {
     if (!d_points || !d_elements || !material || !d_indptr || !d_indices || !d_tile_rows || !d_tile_row_ptr ||
-        !d_tile_conn || !d_tile_elem_ptr || !d_pair_rec || !d_pair_ptr || !d_K || !d_Flux)
+        !d_tile_conn || !d_tile_elem_ptr || !d_pair_rec || !d_pair_ptr || !d_K || !d_Flux || !d_scratch)
         return KB_EINVAL;
     if ((ndim != 1 && ndim != 2) || ntiles < 0 || nelem < 0 || nnode < 0) return KB_EINVAL;
     if (mode != KB_MODE_REFERENCE && mode != KB_MODE_CONSISTENT) return KB_EINVAL;
@@ -308,7 +334,7 @@ extern "C" int kb_assemble_fused(int ndim, const double *d_points, const int32_t
 #define KB_FUSED(ND, HU, MS)                                                                                      \
     return launch_fused<ND, HU, MS>(ntiles, s, d_points, d_velocity, o, d_indptr, d_indices, d_tile_rows,            \
                                     d_tile_row_ptr, d_tile_conn, d_tile_elem_ptr, d_pair_rec, d_pair_ptr, d_K, d_M,    \
-                                    d_Flux)
+                                    d_Flux, (uint8_t *)d_scratch)
     const bool hu = d_velocity != nullptr, ms = d_M != nullptr;
     if (ndim == 2) {
         if (hu && ms) KB_FUSED(2, true, true); else if (hu) KB_FUSED(2, true, false);

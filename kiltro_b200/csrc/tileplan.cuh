@@ -72,4 +72,31 @@ __host__ __device__ __forceinline__ int tile_row_start(const Geom &g, int t) {
     return t * g.R;
 }
 
+
+// ---- tile templates (tiletmpl.cu builds them, assemble_tmpl.cu consumes them)
+// On meshes whose numbering repeats (everything Mesh.Rectangle makes, row-block strips of it, ...) almost all tiles have
+// the same LOCAL structure: same rows-in-runs layout, same element slots, same (entry <- element-matrix components)
+// lists.  The builder hashes each tile's local plan, keeps one image per distinct plan (a "template") and a class id
+// per tile; the kernel keeps the current template in shared memory, so per tile only the run bases come from HBM.
+// A template lists, for every CSR entry of the tile (tile order), up to 4 sources as BYTE offsets into the kernel's
+// element-matrix staging area (component-major, KSTRIDE doubles per component; unused sources point at a zero word), in
+// ascending element order = the order of the reference's sequential `+=` (Assembly.py:46,60-61).
+constexpr int RUNMAX = 31;                 // runs of consecutive rows per tile
+constexpr int CMAX = 64;                   // distinct templates per mesh
+constexpr int KSTRIDE = EMAX + 1;          // doubles per component row (odd: spreads components over the banks)
+constexpr int KZERO = 16 * KSTRIDE;        // the zero word behind the 16 components
+constexpr int FSTRIDE = EMAX + 1;
+constexpr int FZERO = 4 * FSTRIDE;
+
+struct TileTmpl {
+    int nent, nrow, nrun, ne;
+    uint16_t run_ent[RUNMAX + 1];          // local entry offset of each run (+ total)
+    uint16_t run_row[RUNMAX + 1];          // local row offset of each run (+ nrow)
+    uint16_t ent_src[VMAX][4];             // byte offsets into the Ke staging
+    uint16_t row_src[RMAX][4];             // byte offsets into the Fe staging
+    uint8_t ent_run[VMAX];
+    uint8_t row_run[RMAX];
+};
+static_assert(sizeof(TileTmpl) % 16 == 0, "templates are copied with 16-byte words");
+
 }  // namespace kbtile

@@ -8,7 +8,7 @@ import bench
 nps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 mesh, vel, flags, material = bench.make_problem(K, torch, nps)
 form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
-for method in ("two_pass", "fused"):
+for method in ("two_pass", "fused_generic", "fused"):
     for at in ("steady", "transient"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
         bc = K.BoundaryCondition()
@@ -25,4 +25,4 @@ for method in ("two_pass", "fused"):
         byt = 16 * ne + 32 * nn + 8 * nnz + 4 * (nn + 1) + 4 * nnz + (8 * nnz if at == "transient" else 0)
         print("nps=%d %-9s %-9s %.3f ms  %.1f GB/s algorithmic (%.1f%% of 6543)  plan=%s" % (
             nps, method, at, ms, byt / ms * 1e-6, byt / ms * 1e-6 / 65.434,
-            getattr(fs.sparsity.tile_plan, "info", None) if method == "fused" else ""), flush=True)
+            getattr(fs.sparsity.tile_plan, "info", None) if method == "fused" else fs.assembly_used), flush=True)

@@ -45,7 +45,7 @@ def test_assembly_identities_fullsize(big):
     K, mesh, fs, mat = big
     form = K.HeatDiffusion(mesh)
     Kc, Flux, M = K.Assemble(fs, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
-    assert fs.assembly_used == "fused" and fs.sparsity.tile_plan.info["structured"]
+    assert fs.assembly_used == "fused_template" and fs.sparsity.tile_plan.info["structured"]
     nn = mesh.nnodes
     ones = torch.ones(nn, dtype=torch.float64, device="cuda")
     kmax = float(Kc.data.abs().max())

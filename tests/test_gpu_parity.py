@@ -280,13 +280,20 @@ def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
     form = getattr(K, cls)(m, velocity=vel)
     at = "transient" if transient else "steady"
     res = {}
-    for method in ("fused", "two_pass"):
+    used = {"fused": "fused_template", "fused_generic": "fused", "two_pass": "two_pass"}
+    for method in ("fused", "fused_generic", "two_pass"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
         Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
-        assert fs.assembly_used == method
+        assert fs.assembly_used == used[method]
         res[method] = (Kc, Flux, Mm)
         if method == "fused":
-            assert fs.sparsity.tile_plan.info["structured"]
+            info = fs.sparsity.tile_plan.info
+            assert info["structured"] and fs.sparsity.tile_plan.templated and 1 <= info["templates"] <= 9
+    # template kernel == generic fused kernel, bit for bit (same element routine, same summation order)
+    assert torch.equal(res["fused"][0].data, res["fused_generic"][0].data)
+    assert torch.equal(res["fused"][1], res["fused_generic"][1])
+    if transient:
+        assert torch.equal(res["fused"][2].data, res["fused_generic"][2].data)
     # same device function, same accumulation order; the two kernels may contract FMAs differently in the tanh/PG branch
     assert rel_max(K.to_numpy(res["fused"][0].data), K.to_numpy(res["two_pass"][0].data)) < 1e-14
     assert torch.equal(res["fused"][1], res["two_pass"][1])
@@ -299,6 +306,44 @@ def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
     assert rel_max(K.to_numpy(res["fused"][1]).ravel(), A["Flux"]) < VAL_TOL
     if transient:
         assert rel_max(K.to_numpy(res["fused"][2].data), A["M"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("cls,transient", [("HeatAdvectionDiffusion", True), ("TemperaturePG", False)])
+def test_fused_assembly_nonconvex_fixup(cls, transient):
+    """Non-convex quads (Jacobian determinant changes sign inside the element) are declined by the sum-factorised
+    element routine; their tiles are redone by the fix-up launch with the general routine.  All three paths must agree
+    with the oracle, which follows the reference (dV = |det J|, VariationalPrinciple.py:145)."""
+    from oracle import kiltro_oracle as O
+    K = _K()
+    nx, ny = 47, 33
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (1.0, 1.0), nx, ny)
+    P = m.device_points()
+    hx, hy = 1.0 / nx, 1.0 / ny
+    # pull a few interior nodes most of the way to their lower-left neighbour: the element above-right turns non-convex
+    for (i, j) in [(5, 7), (16, 16), (17, 16), (30, 2), (44, 31), (15, 15)]:
+        n = j * (nx + 1) + i
+        P[n, 0] -= 0.8 * hx; P[n, 1] -= 0.8 * hy
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    vel = torch.randn(P.shape, dtype=torch.float64, device="cuda", generator=g) * 2.0 + 1.0
+    matv = (0.7, 1.9, 0.6, 1.3, 0.0)
+    at = "transient" if transient else "steady"
+    form = getattr(K, cls)(m, velocity=vel)
+    mode = "consistent" if cls.startswith("Heat") else "reference"
+    A = O.assemble(K.to_numpy(P), m.elements, K.to_numpy(vel), matv, mode, cls.endswith("PG"), transient)
+    res = {}
+    for method in ("fused", "fused_generic", "two_pass"):
+        fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
+        Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
+        res[method] = Kc
+        assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL, method
+        if transient:
+            assert rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL, method
+    assert torch.equal(res["fused"].data, res["fused_generic"].data)
+    # the tile flags say the fix-up launch really ran
+    fs = K.FEMSolver(analysis_type=at, verbose=False, assembly="fused")
+    K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
+    flags = K.to_numpy(fs.sparsity.tile_plan.scratch)
+    assert flags[:fs.sparsity.tile_plan.ntiles].sum() >= 4
 
 
 @pytest.mark.parametrize("name", ["quad_cons", "quad_scrambled_pg", "line_pg", "line_cons"])
