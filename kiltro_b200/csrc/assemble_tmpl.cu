@@ -33,6 +33,23 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
+// split barrier (mbarrier, one arrival per warp): "every warp has finished reading the shared buffers of the previous
+// tile".  Arrive right after phase BC, wait only just before the element matrices of the next tile are stored -- the
+// whole fp64 element computation of a warp overlaps the phase BC of the slower warps.
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_addr(b)), "r"(parity) : "memory");
+}
+
 struct SmemT {
     double ke[16 * KSTRIDE + 1];               // [component][slot], + the zero word at KZERO
     double fe[4 * FSTRIDE + 1];                // + zero word at FZERO
@@ -40,6 +57,7 @@ struct SmemT {
     TileTmpl tmpl;
     int delta[RUNMAX + 1];                     // per run: global entry position - local entry position
     int rdelta[RUNMAX + 1];                    // per run: global row - local row
+    uint64_t bar_free;                         // split barrier: shared buffers of the previous tile are free
 };
 
 template <bool HAS_U>
@@ -95,7 +113,9 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
     };
     int t = next_tile((int)blockIdx.x - G);
     if (t >= ntiles) return;
-    if (tid == 0) { sm.ke[KZERO] = 0.0; sm.fe[FZERO] = 0.0; }
+    if (tid == 0) { sm.ke[KZERO] = 0.0; sm.fe[FZERO] = 0.0; mbar_init(&sm.bar_free, THREADS / 32); }
+    bool pending = false;                                   // an arrival round of bar_free not yet waited for
+    uint32_t parity = 0;
 
     // ---- prologue: tile t completely, the extents of the tile after it
     int eb = __ldg(tile_elem_ptr + t), ne = __ldg(tile_elem_ptr + t + 1) - eb;
@@ -105,7 +125,7 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
     int frow = 0;
     {
         const int rp = __ldg(trun_ptr + t), nrun = __ldg(trun_ptr + t + 1) - rp;
-        if (tid < nrun) frow = __ldg(trun_row + rp + tid);
+        frow = __ldg(trun_row + rp + min(tid, max(nrun - 1, 0)));
     }
     int tn = next_tile(t);
     int eb_n = 0, ne_n = 0, cls_n = 0, rp_n = 0, nrun_n = 0;
@@ -121,10 +141,10 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
         // ---- issue now what is consumed after phase A: the next tile's connectivity and run rows (their addresses were
         // fetched a tile ago), this tile's row pointers, and the extents of the tile after the next
         const int tnn = tn < ntiles ? next_tile(tn) : tn;
-        int4 conn_n = make_int4(0, 0, 0, 0);
-        int frow_n = 0, ip = 0;
-        if (tid < ne_n) conn_n = ldg_pin4(tile_conn + 4 * (int64_t)(eb_n + tid));
-        if (tid < nrun_n) frow_n = ldg_pin(trun_row + rp_n + tid);
+        // (unconditional, index clamped: a predicated load plus a zero in the other branch makes the zeroing wait for
+        // the load -- same destination registers)
+        const int4 conn_n = ldg_pin4(tile_conn + 4 * (int64_t)(eb_n + min(tid, max(ne_n - 1, 0))));
+        const int frow_n = ldg_pin(trun_row + rp_n + min(tid, max(nrun_n - 1, 0)));
         int eb_nn = 0, ne_nn = 0, cls_nn = 0, rp_nn = 0, nrun_nn = 0;
         if (tnn < ntiles) {
             eb_nn = ldg_pin(tile_elem_ptr + tnn); ne_nn = ldg_pin(tile_elem_ptr + tnn + 1);
@@ -132,7 +152,8 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
             rp_nn = ldg_pin(trun_ptr + tnn); nrun_nn = ldg_pin(trun_ptr + tnn + 1);
         }
         if (cls != cur) {                                   // uniform: (re)load the template of this tile's class
-            __syncthreads();
+            if (pending) { mbar_wait(&sm.bar_free, parity); parity ^= 1u; pending = false; }
+            __syncthreads();                                // (also publishes the barrier init on the first tile)
             const uint4 *src = reinterpret_cast<const uint4 *>(templates + cls);
             uint4 *dst = reinterpret_cast<uint4 *>(&sm.tmpl);
             for (int i = tid; i < (int)(sizeof(TileTmpl) / 16); i += THREADS) dst[i] = __ldg(src + i);
@@ -140,7 +161,7 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
             __syncthreads();
         }
         const int nrun = sm.tmpl.nrun, nent = sm.tmpl.nent, nrow = sm.tmpl.nrow;
-        if (tid < nrun) ip = ldg_pin(indptr + frow);
+        const int ip = ldg_pin(indptr + frow);              // frow is a valid row (or 0) in every thread
 
         // ---- phase A: element matrices -> shared memory
         cp_async_wait_all();                                // this thread's gathers (issued one tile ago) have landed
@@ -160,13 +181,17 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
                 bad_tile[t] = 1;                            // redone by the fix-up launch
                 *nbad = 1;
             }
+            if (pending) mbar_wait(&sm.bar_free, parity);   // the previous tile's phase BC is over in every warp
 #pragma unroll
             for (int i = 0; i < 16; ++i) sm.ke[i * KSTRIDE + tid] = ke[i];
             if (has_q) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sm.fe[i * FSTRIDE + tid] = fe[i];
             }
+        } else if (pending) {
+            mbar_wait(&sm.bar_free, parity);
         }
+        if (pending) { parity ^= 1u; pending = false; }
         // the staging slots of this thread are free again: start the gathers of its element of the next tile
         if (tid < ne_n) gather_async<HAS_U>(sm.stage, tid, points, velocity, conn_n);
         cp_async_commit();
@@ -177,7 +202,7 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
         for (int pass = 0; pass < (MASS ? 2 : 1); ++pass) {
             // ---- phase BC: one thread per CSR entry
             double *out = pass == 0 ? K : M;
-#pragma unroll 2
+#pragma unroll 4
             for (int i = tid; i < nent; i += THREADS) {
                 const uint2 sr = *reinterpret_cast<const uint2 *>(&sm.tmpl.ent_src[i][0]);
                 const int dl = sm.delta[sm.tmpl.ent_run[i]];
@@ -207,7 +232,9 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
                 __syncthreads();
             }
         }
-        __syncthreads();                                    // the next tile overwrites the shared buffers
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.bar_free);     // this warp no longer reads the shared buffers of tile t
+        pending = true;
         t = tn; tn = tnn;
         eb = eb_n; ne = ne_n; cls = cls_n; frow = frow_n;
         eb_n = eb_nn; ne_n = ne_nn - eb_nn; cls_n = cls_nn; rp_n = rp_nn; nrun_n = nrun_nn - rp_nn;
