@@ -135,6 +135,7 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
         rp_n = __ldg(trun_ptr + tn); nrun_n = __ldg(trun_ptr + tn + 1) - rp_n;
     }
     const uint32_t ke_base = smem_addr(sm.ke), fe_base = smem_addr(sm.fe);
+    if (fe_base + (uint32_t)sizeof(sm.fe) > 0xffffu) __trap();            // source addresses are kept in 16 bits
     const bool has_q = (o.area * o.q) != 0.0;
 
     while (t < ntiles) {
@@ -158,6 +159,14 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
             uint4 *dst = reinterpret_cast<uint4 *>(&sm.tmpl);
             for (int i = tid; i < (int)(sizeof(TileTmpl) / 16); i += THREADS) dst[i] = __ldg(src + i);
             cur = cls;
+            __syncthreads();
+            // turn the byte offsets of the shared copy into shared-window addresses (they still fit 16 bits)
+            {
+                uint32_t *e = reinterpret_cast<uint32_t *>(&sm.tmpl.ent_src[0][0]);
+                for (int i = tid; i < VMAX * 2; i += THREADS) e[i] += ke_base * 0x10001u;
+                uint32_t *r = reinterpret_cast<uint32_t *>(&sm.tmpl.row_src[0][0]);
+                for (int i = tid; i < RMAX * 2; i += THREADS) r[i] += fe_base * 0x10001u;
+            }
             __syncthreads();
         }
         const int nrun = sm.tmpl.nrun, nent = sm.tmpl.nent, nrow = sm.tmpl.nrow;
@@ -206,20 +215,20 @@ k_assemble_tmpl(const double *__restrict__ points, const double *__restrict__ ve
             for (int i = tid; i < nent; i += THREADS) {
                 const uint2 sr = *reinterpret_cast<const uint2 *>(&sm.tmpl.ent_src[i][0]);
                 const int dl = sm.delta[sm.tmpl.ent_run[i]];
-                double v = lds_f64(ke_base + (sr.x & 0xffffu));
-                v += lds_f64(ke_base + (sr.x >> 16));
-                v += lds_f64(ke_base + (sr.y & 0xffffu));
-                v += lds_f64(ke_base + (sr.y >> 16));
+                double v = lds_f64(sr.x & 0xffffu);
+                v += lds_f64(sr.x >> 16);
+                v += lds_f64(sr.y & 0xffffu);
+                v += lds_f64(sr.y >> 16);
                 __stcs(out + (int64_t)(i + dl), v);
             }
             if (pass == 0 && tid < nrow) {                  // source vector                         Assembly.py:69-72
                 double f = 0.0;
                 if (has_q) {
                     const uint2 sr = *reinterpret_cast<const uint2 *>(&sm.tmpl.row_src[tid][0]);
-                    f = lds_f64(fe_base + (sr.x & 0xffffu));
-                    f += lds_f64(fe_base + (sr.x >> 16));
-                    f += lds_f64(fe_base + (sr.y & 0xffffu));
-                    f += lds_f64(fe_base + (sr.y >> 16));
+                    f = lds_f64(sr.x & 0xffffu);
+                    f += lds_f64(sr.x >> 16);
+                    f += lds_f64(sr.y & 0xffffu);
+                    f += lds_f64(sr.y >> 16);
                 }
                 Flux[tid + sm.rdelta[sm.tmpl.row_run[tid]]] = f;
             }

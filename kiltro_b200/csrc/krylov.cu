@@ -13,6 +13,8 @@
 // which removes two vector reads and one write per iteration compared with applying D^-1 inside the loop.
 #include <math.h>
 #include <string.h>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
@@ -50,7 +52,7 @@ void prof_collect(bool keep) {
 }
 
 // device scalar slots
-enum { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RES2, S_TOL2, S_AUX0, S_AUX1, S_COUNT = 16 };
+enum { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RES2, S_TOL2, S_AUX0, S_AUX1, S_R0N2, S_WHY, S_COUNT = 16 };   // S_R0N2: <r,r> at the (re)start = |rhat|^2
 
 struct Work {
     double *vals_hat, *scale, *v0, *v1, *v2, *v3, *v4, *v5, *partials, *sc;
@@ -369,7 +371,7 @@ struct BodyResidual {       // r = b - q ; p = r ; rhat = r ; d0 = <r,r> ; d1 = 
 struct FinInit {            // rho = <r,r> ; tol2 = max(rtol^2 <b,b>, tiny) ; done if already converged
     double *sc; int *done; double rtol2;
     __device__ void operator()(double rr, double bb, double = 0.0, double = 0.0) const {
-        sc[S_RHO] = rr; sc[S_RES2] = rr; sc[S_AUX0] = bb;
+        sc[S_RHO] = rr; sc[S_RES2] = rr; sc[S_AUX0] = bb; sc[S_R0N2] = rr;
         const double tol2 = rtol2 * bb;
         sc[S_TOL2] = tol2;
         sc[S_ALPHA] = 0.0; sc[S_OMEGA] = 1.0; sc[S_BETA] = 0.0;
@@ -402,12 +404,24 @@ struct FinCgBeta {          // beta = rho_new / rho ; rho = rho_new ; convergenc
 };
 
 // ---- BiCGSTAB
-struct FinBiAlpha {         // after v = A p, d0 = <rhat,v>: alpha = rho / <rhat,v>
+// Breakdown guards (done = 2 -> the host restarts from the true residual of the current iterate, rhat = r):
+//   * exact breakdown: <rhat,v> = 0, rho = 0, omega = 0 or a non-finite scalar;
+//   * spike: the step alpha v about to be applied is 1e5 times longer than the residual it is meant to reduce.  In
+//     fp64 BiCGSTAB <rhat,v> and rho sink to rounding noise on transport-like problems (the residual front and the
+//     shadow Krylov vectors travel in opposite directions: seen on the uniform-velocity closed-form case at 16 M DOF);
+//     the iteration usually survives on noise, but one near-zero <rhat,v> produces an alpha of size 1/eps that wrecks
+//     the iterate beyond recovery.  The flag is raised BEFORE the update (the following kernels see done != 0), so the
+//     iterate the restart begins from is still good;
+//   * divergence: the recurrence residual has grown 1e5-fold over the residual the cycle started from.
+// (A scale-free test on cos(rhat, r) does not work: rho legitimately decays relative to |rhat||r|.)
+constexpr double KB_GROWTH2_MAX = 1.0e10;
+struct FinBiAlpha {         // after v = A p, d = {<rhat,v>, <v,v>}: alpha = rho / <rhat,v>
     double *sc; int *done;
-    __device__ void operator()(double rv, double, double = 0.0, double = 0.0) const {
+    __device__ void operator()(double rv, double vv, double = 0.0, double = 0.0) const {
         const double a = sc[S_RHO] / rv;
         sc[S_ALPHA] = a;
-        if (!isfinite(a) || rv == 0.0) done[0] = 2;
+        if (!isfinite(a) || rv == 0.0) { done[0] = 2; sc[S_WHY] = 1.0; }
+        else if (a * a * vv > KB_GROWTH2_MAX * sc[S_RES2]) { done[0] = 2; sc[S_WHY] = 2.0; }
     }
 };
 // Merged update (one vector kernel instead of two): with <rhat,t> and <rhat,s> taken in the epilogue of t = A s,
@@ -421,6 +435,7 @@ struct FinBiOmega2 {        // d = {<s,t>, <t,t>, <rhat,t>, <rhat,s>}
         const double beta = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / om);
         sc[S_OMEGA] = om; sc[S_BETA] = beta; sc[S_RHO] = rho_new;
         sc[S_AUX1] = (isfinite(beta) && rho_new != 0.0 && om != 0.0) ? 0.0 : 1.0;     // breakdown unless converged below
+        if (sc[S_AUX1] != 0.0) sc[S_WHY] = 3.0;
     }
 };
 struct FinBiRes {           // after the merged update: d0 = <r,r>
@@ -429,7 +444,10 @@ struct FinBiRes {           // after the merged update: d0 = <r,r>
         sc[S_RES2] = rr;
         const int it = ++iter[0];
         if (!(rr > sc[S_TOL2]) && isfinite(rr)) { done[0] = 1; done[1] = it; }
-        else if (!isfinite(rr) || sc[S_AUX1] != 0.0) { done[0] = 2; done[1] = it; }
+        else if (!isfinite(rr) || sc[S_AUX1] != 0.0 || rr > KB_GROWTH2_MAX * sc[S_R0N2]) {
+            done[0] = 2; done[1] = it;
+            if (sc[S_AUX1] == 0.0) sc[S_WHY] = isfinite(rr) ? 5.0 : 6.0;
+        }
     }
 };
 
@@ -496,7 +514,7 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
     const double rtol2 = rtol * rtol;
     double prev_true = INFINITY;
     bool recurrence_converged = false;
-    for (int restart = 0; restart < 8 && total_iters < maxiter; ++restart) {
+    for (int restart = 0; restart < 16 && total_iters < maxiter; ++restart) {
         // (re)start from the TRUE residual: r = bh - Ahat xh ; p = r ; rhat = r ; rho = <r,r>
         if ((rc = launch_spmv<0>(n, nnz, indptr, indices, w.vals_hat, w, xh, q, nullptr, nullptr, NoFinal{}, s))) return rc;
         if ((rc = launch_vec<1>(n, BodyResidual{bh, q, r, p, METHOD == 1 ? rhat : nullptr},
@@ -505,9 +523,9 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
         const double true_rr = hs.sc[S_RES2];
         if (hs.done[0] == 1) { status = 0; break; }                       // true residual meets the tolerance
         if (hs.done[0] == 2) { status = KB_EBREAKDOWN; break; }           // non-finite residual
-        if (recurrence_converged && !(true_rr < 0.25 * prev_true)) {      // attainable accuracy reached: the recurrence
-            status = 0; break;                                           // converged but fp64 rounding floors ||b - A x||
-        }
+        // attainable accuracy reached: the recurrence converged but fp64 rounding floors ||b - A x|| -- accepted only
+        // near the tolerance (within 1e3 in norm); a recurrence that "converged" on a wrecked iterate is not
+        if (recurrence_converged && !(true_rr < 0.25 * prev_true) && true_rr <= 1.0e6 * hs.sc[S_TOL2]) { status = 0; break; }
         prev_true = true_rr;
         recurrence_converged = false;
         bool stop = false;
@@ -534,13 +552,16 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
             if (g_prof.on) prof_collect(hs.done[0] == 0);
             if (hs.done[0] != 0) stop = true;
         }
+        if (getenv("KB_DEBUG_SOLVER"))
+            fprintf(stderr, "[kb solver] cycle %d: iters %d done %d why %.0f rho %.3e alpha %.3e omega %.3e beta %.3e rr %.3e r0n2 %.3e tol2 %.3e\n",
+                    restart, total_iters, hs.done[0], hs.sc[S_WHY], hs.sc[S_RHO], hs.sc[S_ALPHA], hs.sc[S_OMEGA], hs.sc[S_BETA],
+                    hs.sc[S_RES2], hs.sc[S_R0N2], hs.sc[S_TOL2]);
         if (hs.done[0] == 1) recurrence_converged = true;                 // verify against the true residual above
         else if (hs.done[0] == 2) status = KB_EBREAKDOWN;                 // restart from the current iterate
         else break;                                                       // maxiter exhausted
         k_clear_done<<<1, 1, 0, s>>>(w.done);
         KB_LAUNCH_CHECK();
     }
-    if (recurrence_converged && status != 0 && total_iters >= maxiter) status = 0;
     // true residual of the scaled system with the final iterate (for BiCGSTAB this is b - A x itself)
     if ((rc = launch_spmv<0>(n, nnz, indptr, indices, w.vals_hat, w, xh, q, nullptr, nullptr, NoFinal{}, s))) return rc;
     if ((rc = launch_vec<1>(n, BodyResidual{bh, q, r, p, nullptr}, FinInit{w.sc, w.iter + 2, rtol2}, w, nullptr, s))) return rc;
@@ -553,6 +574,8 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
     // the iterate is judged by its TRUE residual: within a factor 10 of the requested tolerance counts as converged
     // (restarts that end in a breakdown at the fp64 floor, or a recurrence residual that drifted, do not change that)
     if (status != 0 && hs.sc[S_RES2] <= 100.0 * rtol2 * hs.sc[S_AUX0]) status = 0;
+    if (status == 0 && !(hs.sc[S_RES2] <= 1.0e6 * rtol2 * hs.sc[S_AUX0]) && hs.sc[S_AUX0] > 0.0)
+        status = isfinite(hs.sc[S_RES2]) ? KB_ENOTCONV : KB_EBREAKDOWN;   // never report success on a wrecked iterate
     info->status = status;
     info->kernel_launches = g_kb_launches - launches0;
     return 0;
