@@ -32,6 +32,10 @@ extern "C" {
 #define KB_MODE_REFERENCE  0 /* scalar broadcast, what Temperature/TemperaturePG compute: VariationalPrinciple.py:152,156,164-173 */
 #define KB_MODE_CONSISTENT 1 /* W (x) (u.grad N): MaterialBase.py:42-58 (the examples' HeatAdvectionDiffusion) */
 
+/* element operators of kb_element_operator */
+#define KB_OP_ROBIN 1        /* AssemblyRobinForces, FiniteElements/Assembly.py:121-175 */
+#define KB_OP_CHARGALERKIN 2 /* GetElementalCharacteristicGalerkin, VariationalPrinciple.py:264-308 */
+
 /* material constants, MaterialBase.py:4-39 */
 typedef struct kb_material { double k, rho, c_v, area, q; } kb_material;
 
@@ -148,6 +152,21 @@ int kb_assemble_fused_tmpl(const double *d_points, int64_t nnode, const double *
                            const uint8_t *d_tile_class, const int32_t *d_trun_ptr, const int32_t *d_trun_row,
                            const void *d_templates, double *d_K, double *d_M, double *d_Flux, void *d_scratch,
                            void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K10 element operators of the "next" rows (seam form: element matrices to HBM, then kb_assemble_from_elements)
+ *   KB_OP_ROBIN         replaces AssemblyRobinForces (FiniteElements/Assembly.py:121-175): Ke = h sum_g N (x) N dV,
+ *                       Fe as shipped (:157,164); p0 = h (boundary_condition.applied_robin_convection), p1 = T_inf
+ *                       (ground_robin_convection); d_velocity ignored.
+ *   KB_OP_CHARGALERKIN  replaces AssembleCharacteristicGalerkin (Assembly.py:95-117) over
+ *                       GetElementalCharacteristicGalerkin (VariationalPrinciple.py:264-308): Ke = sum_g (u.grad N) (x)
+ *                       (u.grad N) dV, Fe = p0 sum_g (u.grad N) dV with p0 = material.q * material.area; p1 unused.
+ *   d_Ke (nelem x npe^2, row-major), d_Fe (nelem x npe).
+ * kb_axpby: out = a x + b y (y may be NULL); folds an operator into K / F on the shared sparsity pattern.
+ * ------------------------------------------------------------------------------------------------------- */
+int kb_element_operator(int ndim, int op, const double *d_points, const int32_t *d_elements, int64_t nelem,
+                        const double *d_velocity, double p0, double p1, double *d_Ke, double *d_Fe, void *stream);
+int kb_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K4  boundary conditions                   replaces kiltro/BoundaryCondition.py

@@ -32,7 +32,8 @@ class FEMSolver(object):
                  number_of_load_increments=1, print_incremental_log=False,
                  memory_store_frequency=1, recompute_sparsity_pattern=False,
                  squeeze_sparsity_pattern=False, number_of_increments=None, theta=0.0, time_step=None,
-                 time_step_factor=0.1, include_heat_source=False, assembly="auto", verbose=True):
+                 time_step_factor=0.1, include_heat_source=False, include_robin=False,
+                 characteristic_galerkin=False, assembly="auto", verbose=True):
         # FEMSolver.py:14-28 (+ the examples' number_of_increments=, examples/transient_2d.py:73-74)
         self.analysis_type = analysis_type
         self.analysis_nature = analysis_nature
@@ -48,7 +49,11 @@ class FEMSolver(object):
         self.time_step = time_step
         self.time_step_factor = float(time_step_factor)          # FEMSolver.py:144 uses 0.1
         self.include_heat_source = include_heat_source           # the reference drops Flux from the RHS
-        self.assembly = assembly                                  # "auto" | "fused" | "two_pass"
+        # code the reference ships but never reaches (Assembly.py:90 discards the Robin term,
+        # FEMSolver.py:264-266,287-292 comments the characteristic-Galerkin correction out) -- opt-in here
+        self.include_robin = include_robin
+        self.characteristic_galerkin = characteristic_galerkin
+        self.assembly = assembly                                  # "auto" | "fused" | "fused_generic" | "two_pass"
         self.verbose = verbose
         self.sparsity = None
         self.timings = {}
@@ -126,6 +131,15 @@ class FEMSolver(object):
             Residual = NodalFluxes.clone()                                                   # :179,186
             if self.include_heat_source:
                 Residual += LoadFactor * Flux          # opt-in: the reference computes Flux and drops it
+            if self.include_robin:
+                # opt-in Newton cooling h (T - T_inf) over the domain: (K + K_e) T = b + Flux_e.  The reference assembles
+                # K_e, Flux_e here (Assembly.py:90) and drops them; its only consumer (BoundaryCondition.py:143-153) is
+                # unreachable, so the sign convention is the physical one.
+                from .FiniteElements.Assembly import AssemblyRobinForces
+                K_e, Flux_e = AssemblyRobinForces(self, function_spaces[0], mesh, material, boundary_condition)
+                _lib.check(_lib.load().kb_axpby(K.nnz, 1.0, D.ptr(K.data), 1.0, D.ptr(K_e.data), D.ptr(K.data),
+                                                D.stream_ptr()))
+                Residual += LoadFactor * Flux_e
             ev[1].record()
             K_b, F_b = boundary_condition.ApplyDirichletGetReducedMatrices(K, Residual, AppliedDirichletInc)[:2]   # :190
             ev[2].record()

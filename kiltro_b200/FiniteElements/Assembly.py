@@ -8,12 +8,13 @@ per-element Python loop of the reference (Assembly.py:46-72) becomes either
     latter), or
   * the two-step seam K1 (kb_element_matrices) + K3 (kb_assemble_from_elements) when fem_solver.assembly == "two_pass".
 The dense AssemblyRobinForces pass whose result the reference discards (Assembly.py:90,121-175) is not run."""
+import numpy as np
 import torch
 
 from .. import _lib, device as D
 from ..sparse import DeviceCSR
 
-__all__ = ['Assemble']
+__all__ = ['Assemble', 'AssemblyRobinForces', 'AssembleCharacteristicGalerkin']
 
 
 def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_condition):
@@ -56,3 +57,48 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
     fem_solver.ijv = (sp.indptr.numel() * 4 + sp.indices.numel() * 4 + K.numel() * 8) / 1024. / 1024.
     mass = DeviceCSR(M, sp.indices, sp.indptr, shape, symmetric=True) if transient else []
     return convection, Flux, mass
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8(f) rows n2, n3
+def _assemble_operator(fem_solver, mesh, op, p0, p1, velocity):
+    """Element operator (csrc/operators.cu) -> CSR values on the cached pattern (csrc/assemble_gather.cu)."""
+    lib = _lib.load()
+    if fem_solver.sparsity is None:                              # same cache as ComputeSparsityFEM (FEMSolver.py:313-325)
+        from .ComputeSparsityPattern import ComputeSparsityPatternDevice
+        fem_solver.sparsity = ComputeSparsityPatternDevice(mesh, 1)
+        fem_solver.is_sparsity_pattern_computed = True
+    sp = fem_solver.sparsity
+    if sp.nvar != 1:
+        raise ValueError("only nvar = 1 is available")
+    pts, el = mesh.device_points(), mesh.device_elements()
+    ne, npe = int(el.shape[0]), int(el.shape[1])
+    nnode = int(mesh.nnodes)
+    Ke = D.empty((ne, npe * npe)); Fe = D.empty((ne, npe))
+    _lib.check(lib.kb_element_operator(int(mesh.ndim), op, D.ptr(pts), D.ptr(el), ne, D.ptr(velocity), float(p0),
+                                       float(p1), D.ptr(Ke), D.ptr(Fe), D.stream_ptr()))
+    V = D.empty(sp.nnz); F = D.empty((nnode, 1))
+    _lib.check(lib.kb_assemble_from_elements(npe, nnode, sp.nnz, D.ptr(sp.seg_ptr), D.ptr(sp.gather_src),
+                                             D.ptr(sp.diag_pos), D.ptr(Ke), D.ptr(None), D.ptr(Fe), D.ptr(V), D.ptr(None),
+                                             D.ptr(F), D.stream_ptr()))
+    return DeviceCSR(V, sp.indices, sp.indptr, (nnode, nnode), symmetric=True), F
+
+
+def AssemblyRobinForces(fem_solver, function_space, mesh, material, boundary_condition):
+    """kiltro/FiniteElements/Assembly.py:121-175: the Newton-cooling (lateral convection) term, K_e = sum_e h int N (x) N dV
+    and Flux_e (as shipped, see csrc/element.cuh), with h = boundary_condition.applied_robin_convection and
+    T_inf = boundary_condition.ground_robin_convection.  Sparse on the cached pattern instead of dense (npoints^2)."""
+    h, tinf = boundary_condition.applied_robin_convection, boundary_condition.ground_robin_convection
+    if not np.isscalar(h) or not np.isscalar(tinf):
+        raise ValueError("applied_robin_convection / ground_robin_convection must be scalars (as in the reference)")
+    return _assemble_operator(fem_solver, mesh, _lib.KB_OP_ROBIN, h, tinf, None)
+
+
+def AssembleCharacteristicGalerkin(function_spaces, formulation, mesh, material, boundary_condition, fem_solver=None):
+    """kiltro/FiniteElements/Assembly.py:95-117 over GetElementalCharacteristicGalerkin (VariationalPrinciple.py:264-308):
+    K_u = sum_e int (u.grad N) (x) (u.grad N) dV, Flux_u = sum_e q area int (u.grad N) dV.  Sparse instead of dense.
+    fem_solver (optional, extension): the solver whose cached sparsity pattern is reused."""
+    if fem_solver is None:
+        from ..FEMSolver import FEMSolver
+        fem_solver = FEMSolver(verbose=False)
+    return _assemble_operator(fem_solver, mesh, _lib.KB_OP_CHARGALERKIN, material.q * material.area, 0.0,
+                              formulation.device_velocity())

@@ -7,7 +7,7 @@ PostProcess.  Computation happens in libkiltro_b200.so (hand-written sm_100a CUD
 from .MeshGeneration import Mesh
 from .BoundaryCondition import BoundaryCondition
 from .FunctionSpace import FunctionSpace
-from .FiniteElements import Assemble, ComputeSparsityPattern
+from .FiniteElements import Assemble, ComputeSparsityPattern, AssemblyRobinForces, AssembleCharacteristicGalerkin
 from .FiniteElements.ComputeSparsityPattern import ComputeSparsityPatternDevice, SparsityPattern
 from .FEMSolver import FEMSolver, LinearSolver
 from .MaterialBase import Material, FourierConduction
@@ -18,6 +18,6 @@ from .sparse import DeviceCSR
 from .device import to_numpy
 
 __all__ = ["Mesh", "BoundaryCondition", "FunctionSpace", "Assemble", "ComputeSparsityPattern",
-           "ComputeSparsityPatternDevice", "SparsityPattern", "FEMSolver", "LinearSolver", "Material",
+           "ComputeSparsityPatternDevice", "SparsityPattern", "AssemblyRobinForces", "AssembleCharacteristicGalerkin", "FEMSolver", "LinearSolver", "Material",
            "FourierConduction", "VariationalPrinciple", "Temperature", "TemperaturePG", "HeatDiffusion",
            "HeatAdvectionDiffusion", "HeatAdvectionDiffusionPG", "PostProcess", "DeviceCSR", "to_numpy"]

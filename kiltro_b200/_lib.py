@@ -28,6 +28,8 @@ class kb_solve_info(ctypes.Structure):
 
 KB_MODE_REFERENCE = 0
 KB_MODE_CONSISTENT = 1
+KB_OP_ROBIN = 1
+KB_OP_CHARGALERKIN = 2
 KB_ENOTCONV = -5
 KB_EBREAKDOWN = -4
 
@@ -55,6 +57,8 @@ SIGNATURES = {
                                  ctypes.POINTER(I64), c_vp]),
     "kb_assemble_fused_tmpl": (I32, [c_vp, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, I64, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_element_operator": (I32, [I32, I32, c_vp, c_vp, I64, c_vp, F64, F64, c_vp, c_vp, c_vp]),
+    "kb_axpby": (I32, [I64, F64, c_vp, F64, c_vp, c_vp, c_vp]),
     "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
     "kb_neumann_fluxes": (I32, [c_vp, I64, c_vp, c_vp]),
     "kb_apply_dirichlet_reduce": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, I64, c_vp, c_vp, c_vp,

@@ -424,4 +424,110 @@ KB_HD void line2(const double (&X)[2], const double (&U)[2], const ElemOpts &o,
     }
 }
 
+// ---------------------------------------------------------------------------------------------- SURVEY 8(f) operators
+// n2  Robin / Newton-cooling term, AssemblyRobinForces (FiniteElements/Assembly.py:121-175): a volume integral over every
+//     element, Ke = h sum_g N (x) N dV_g (:155,163).  The source vector is reproduced as shipped: the Gauss loop adds
+//     gf[counter] = h T_inf Bases[counter, :] (:157,164), so Fe[i] = h T_inf sum_g Bases[g][i] dV_g (node and Gauss
+//     indices swapped -- equal to the intended sum on undistorted elements).
+// n3  characteristic-Galerkin operator, GetElementalCharacteristicGalerkin (VariationalPrinciple.py:264-308):
+//     Ke = sum_g (u.grad N) (x) (u.grad N) dV_g (:300,305), Fe = q area sum_g (u.grad N) dV_g (:302,306), u = mean velocity.
+KB_HD void quad4_geometry(const double (&X)[4][2], double (&G0)[4][4], double (&G1)[4][4], double (&dV)[4]) {
+    constexpr double HHI = 0.5 * NHI, HLO = 0.5 * NLO;
+    const double e01x = X[1][0] - X[0][0], e01y = X[1][1] - X[0][1];
+    const double e32x = X[2][0] - X[3][0], e32y = X[2][1] - X[3][1];
+    const double e03x = X[3][0] - X[0][0], e03y = X[3][1] - X[0][1];
+    const double e12x = X[2][0] - X[1][0], e12y = X[2][1] - X[1][1];
+    const double Jzx[2] = {HHI * e01x + HLO * e32x, HLO * e01x + HHI * e32x};
+    const double Jzy[2] = {HHI * e01y + HLO * e32y, HLO * e01y + HHI * e32y};
+    const double Jex[2] = {HHI * e03x + HLO * e12x, HLO * e03x + HHI * e12x};
+    const double Jey[2] = {HHI * e03y + HLO * e12y, HLO * e03y + HHI * e12y};
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+        for (int gj = 0; gj < 2; ++gj) {
+            const int g = 2 * gi + gj;
+            const double J00 = Jzx[gi], J01 = Jzy[gi], J10 = Jex[gj], J11 = Jey[gj];
+            const double det = J00 * J11 - J01 * J10, idet = 1.0 / det;
+            dV[g] = fabs(det);
+            const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;
+            const double hE0 = gi == 0 ? HHI : HLO, hE1 = gi == 0 ? HLO : HHI;
+            const double hZ0 = gj == 0 ? HHI : HLO, hZ1 = gj == 0 ? HLO : HHI;
+            const double z[4] = {-hE0, hE0, hE1, -hE1}, e[4] = {-hZ0, -hZ1, hZ1, hZ0};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { G0[g][a] = i00 * z[a] + i01 * e[a]; G1[g][a] = i10 * z[a] + i11 * e[a]; }
+        }
+}
+
+// Bases[a][g] of the quad (FunctionSpace.py:53-59): Bases[:, 0] = B0, the other Gauss points permute it
+KB_HD double quad4_basis(int a, int g) {
+    const double B0[4] = {NHI * NHI, NHI * NLO, NLO * NLO, NLO * NHI};
+    constexpr int PERM[4][4] = {{0, 1, 2, 3}, {1, 0, 3, 2}, {3, 2, 1, 0}, {2, 3, 0, 1}};
+    return B0[PERM[g][a]];
+}
+
+KB_HD void quad4_robin(const double (&X)[4][2], double h, double t_inf, double (&Ke)[16], double (&Fe)[4]) {
+    double G0[4][4], G1[4][4], dV[4];
+    quad4_geometry(X, G0, G1, dV);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            double m = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) m += (h * (quad4_basis(a, g) * quad4_basis(b, g))) * dV[g];
+            Ke[4 * a + b] = m;
+        }
+        double f = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) f += (h * t_inf * quad4_basis(g, a)) * dV[g];     // as shipped: Bases[g][a]
+        Fe[a] = f;
+    }
+}
+
+KB_HD void quad4_chargalerkin(const double (&X)[4][2], const double (&U)[4][2], double qa, double (&Ke)[16],
+                              double (&Fe)[4]) {
+    double G0[4][4], G1[4][4], dV[4];
+    quad4_geometry(X, G0, G1, dV);
+    const double ub0 = (U[0][0] + U[1][0] + U[2][0] + U[3][0]) * 0.25;
+    const double ub1 = (U[0][1] + U[1][1] + U[2][1] + U[3][1]) * 0.25;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Ke[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) Fe[a] = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        double ug[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ug[a] = ub0 * G0[g][a] + ub1 * G1[g][a];            // USpatialGradient   :296
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Ke[4 * a + b] += (ug[a] * ug[b]) * dV[g];
+            Fe[a] += (qa * ug[a]) * dV[g];
+        }
+    }
+}
+
+KB_HD void line2_robin(const double (&X)[2], double h, double t_inf, double (&Ke)[4], double (&Fe)[2]) {
+    const double dV = fabs(0.5 * (X[1] - X[0]));                                          // both Gauss points
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) Ke[2 * a + b] = (h * (N1(a, 0) * N1(b, 0))) * dV + (h * (N1(a, 1) * N1(b, 1))) * dV;
+        Fe[a] = (h * t_inf * N1(0, a)) * dV + (h * t_inf * N1(1, a)) * dV;
+    }
+}
+
+KB_HD void line2_chargalerkin(const double (&X)[2], const double (&U)[2], double qa, double (&Ke)[4], double (&Fe)[2]) {
+    const double J = -0.5 * X[0] + 0.5 * X[1], iJ = 1.0 / J, dV = fabs(J);
+    const double ub = (U[0] + U[1]) * 0.5;
+    const double ug[2] = {ub * (-0.5 * iJ), ub * (0.5 * iJ)};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) Ke[2 * a + b] = (ug[a] * ug[b]) * dV + (ug[a] * ug[b]) * dV;
+        Fe[a] = (qa * ug[a]) * dV + (qa * ug[a]) * dV;
+    }
+}
+
 }  // namespace kbel

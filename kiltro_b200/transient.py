@@ -43,6 +43,18 @@ def run_transient(fem_solver, function_spaces, formulation, solver, mesh, materi
     F = -F - NeumannFluxes
     if fem_solver.include_heat_source:
         F = F - Flux
+    if getattr(fem_solver, "characteristic_galerkin", False):
+        # T[in]^{n+1} = T[in]^n - dt (M^-1)[in,in] (K_b T + F_b) + dt^2/2 (M^-1)[in,in] (Ku_b T + Fu_b)   (FEMSolver.py:287-292,
+        # commented out upstream)  ==  the explicit step on K - dt/2 K_u and F - dt/2 Flux_u; K_u is not lifted
+        # (GetReducedMatrices, BoundaryCondition.py:156-167), so the Dirichlet term above came from K alone.
+        if theta != 0.0:
+            raise ValueError("characteristic_galerkin=True is the explicit scheme of the reference: use theta=0")
+        from .FiniteElements.Assembly import AssembleCharacteristicGalerkin
+        K_u, Flux_u = AssembleCharacteristicGalerkin(function_spaces, formulation, mesh, material, bc, fem_solver=fem_solver)
+        Keff = D.empty(K.nnz)
+        _lib.check(lib.kb_axpby(K.nnz, 1.0, D.ptr(K.data), -0.5 * dt, D.ptr(K_u.data), D.ptr(Keff), D.stream_ptr()))
+        K = type(K)(Keff, K.indices, K.indptr, K.shape, symmetric=K.symmetric)
+        F = F - 0.5 * dt * Flux_u
     Fm = D.empty(ndof)
     F = F.contiguous()
     _lib.check(lib.kb_mask_free(ndof, D.ptr(bc.renum), D.ptr(F), D.ptr(Fm), D.stream_ptr()))

@@ -43,3 +43,29 @@ extern "C" int host_line2(const double *points, const int *elements, long nelem,
     }
     return 0;
 }
+
+// op: 1 = Robin (p0 = h, p1 = T_inf), 2 = characteristic-Galerkin (p0 = q * area); npe = 4 (quad) or 2 (line)
+extern "C" int host_operator(int npe, int op, const double *points, const int *elements, long nelem, const double *velocity,
+                             double p0, double p1, double *Ke, double *Fe) {
+    for (long e = 0; e < nelem; ++e) {
+        if (npe == 4) {
+            double X[4][2], U[4][2], ke[16], fe[4];
+            for (int a = 0; a < 4; ++a) {
+                const int n = elements[4 * e + a];
+                X[a][0] = points[2 * n]; X[a][1] = points[2 * n + 1];
+                U[a][0] = velocity ? velocity[2 * n] : 0.0; U[a][1] = velocity ? velocity[2 * n + 1] : 0.0;
+            }
+            if (op == 1) quad4_robin(X, p0, p1, ke, fe); else quad4_chargalerkin(X, U, p0, ke, fe);
+            for (int i = 0; i < 16; ++i) Ke[16 * e + i] = ke[i];
+            for (int i = 0; i < 4; ++i) Fe[4 * e + i] = fe[i];
+        } else {
+            const int n0 = elements[2 * e], n1 = elements[2 * e + 1];
+            double X[2] = {points[n0], points[n1]}, U[2] = {velocity ? velocity[n0] : 0.0, velocity ? velocity[n1] : 0.0};
+            double ke[4], fe[2];
+            if (op == 1) line2_robin(X, p0, p1, ke, fe); else line2_chargalerkin(X, U, p0, ke, fe);
+            for (int i = 0; i < 4; ++i) Ke[4 * e + i] = ke[i];
+            for (int i = 0; i < 2; ++i) Fe[2 * e + i] = fe[i];
+        }
+    }
+    return 0;
+}

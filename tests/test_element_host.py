@@ -119,3 +119,29 @@ def test_line2_host_matches_reference_golden(host, name):
     host.host_line2(_p(pts), _p(el), ctypes.c_long(ne), _p(vel), _p(mat), ctypes.c_int(MODE[mode]),
                     ctypes.c_int(int(petrov)), ctypes.c_int(1), _p(Ke), _p(Fe), _p(Me))
     assert rel_max(Ke, c["Ke"]) < VAL_TOL and rel_max(Fe, c["Fe"]) < VAL_TOL and rel_max(Me, c["Me"]) < VAL_TOL
+
+
+NEXT = Golden("next")
+
+
+@pytest.mark.parametrize("name", NEXT.cases())
+def test_operator_routines_host_match_reference_golden(host, name):
+    """quad4_robin / quad4_chargalerkin / line2_*  compiled for the host, assembled with the oracle's
+    scatter, against the dense matrices of the reference's AssemblyRobinForces / AssembleCharacteristicGalerkin."""
+    import scipy.sparse as sp
+    from oracle import kiltro_oracle as O
+    c = NEXT.case(name)
+    el = np.ascontiguousarray(c["elements"], dtype=np.int32)
+    ne, npe = el.shape
+    pts = np.ascontiguousarray(c["points"], dtype=np.float64).ravel()
+    vel = np.ascontiguousarray(c["velocity"], dtype=np.float64).ravel()
+    nn = c["points"].shape[0]
+    k, rho, cv, area, q = c["material"]
+    for op, p0, p1, Kref, Fref in ((1, float(c["robin_h"]), float(c["robin_tinf"]), c["K_robin"], c["F_robin"]),
+                                   (2, q * area, 0.0, c["K_cg"], c["F_cg"])):
+        Ke = np.zeros((ne, npe * npe)); Fe = np.zeros((ne, npe))
+        host.host_operator(ctypes.c_int(npe), ctypes.c_int(op), _p(pts), _p(el), ctypes.c_long(ne), _p(vel),
+                           ctypes.c_double(p0), ctypes.c_double(p1), _p(Ke), _p(Fe))
+        A = O.assemble_values(c["elements"], nn, Ke, Fe)
+        Kd = sp.csr_matrix((A["data"], A["indices"], A["indptr"]), shape=(nn, nn)).toarray()
+        assert rel_max(Kd, Kref) < VAL_TOL and rel_max(A["F"], Fref) < VAL_TOL, op

@@ -633,3 +633,89 @@ def test_line_mesh_steady_large_vs_oracle():
     ref = O.steady_solve(pts, el, vel, (1.0, 1.0, 1.0, 1.0, 0.0), d, None, "consistent", False)
     assert solver.info["status"] == 0, solver.info
     assert rel_l2(sol.sol.ravel(), ref) < SOL_TOL, solver.info
+
+
+# ------------------------------------------------------------------------------------------------- SURVEY 8(f) rows n2, n3
+NEXT = Golden("next")
+
+
+@pytest.mark.parametrize("name", NEXT.cases())
+def test_robin_and_characteristic_galerkin_operators_golden(name):
+    """kb_element_operator + kb_assemble_from_elements against the dense matrices the reference's own
+    AssemblyRobinForces (Assembly.py:121-175) and AssembleCharacteristicGalerkin (Assembly.py:95-117) produce."""
+    K = _K()
+    c = NEXT.case(name)
+    m = make_mesh(c["points"], c["elements"])
+    mat = material_for(c["material"], m.ndim)
+    form = K.TemperaturePG(m, velocity=c["velocity"])
+    fs = K.FEMSolver(verbose=False)
+    bc = K.BoundaryCondition()
+    bc.SetRobinCriteria(lambda: {"type": "Convection", "flags": None, "data": float(c["robin_h"])})
+    bc.ground_robin_convection = float(c["robin_tinf"])
+    Kr, Fr = K.AssemblyRobinForces(fs, form.function_spaces[0], m, mat, bc)
+    assert rel_max(Kr.toarray(), c["K_robin"]) < VAL_TOL and rel_max(K.to_numpy(Fr).ravel(), c["F_robin"]) < VAL_TOL
+    Ku, Fu = K.AssembleCharacteristicGalerkin(form.function_spaces, form, m, mat, bc, fem_solver=fs)
+    assert rel_max(Ku.toarray(), c["K_cg"]) < VAL_TOL and rel_max(K.to_numpy(Fu).ravel(), c["F_cg"]) < VAL_TOL
+    # same pattern object as the stiffness matrix (what makes folding them into K a vector operation)
+    assert Kr.indices.data_ptr() == fs.sparsity.indices.data_ptr() and Ku.indptr.data_ptr() == fs.sparsity.indptr.data_ptr()
+
+
+def test_steady_with_robin_term():
+    """include_robin=True: (K + K_e) T = b + Flux_e on the free DOFs, against a dense NumPy solve on the oracle's matrices."""
+    from oracle import kiltro_oracle as O
+    from scipy.sparse import csr_matrix
+    K = _K()
+    c = NEXT.case("quad")
+    pts, el, vel = c["points"], c["elements"], c["velocity"]
+    nn = pts.shape[0]
+    matv = tuple(c["material"])
+    h, tinf = 4.0, 300.0
+    flags = np.full((nn, 1), np.nan); flags[pts[:, 0] == 0.0, 0] = 350.0; flags[pts[:, 0] == pts[:, 0].max(), 0] = 280.0
+    m = make_mesh(pts, el)
+    form = K.HeatAdvectionDiffusion(m, velocity=vel)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags.copy())
+    bc.applied_robin_convection = h; bc.ground_robin_convection = tinf
+    fs = K.FEMSolver(verbose=False, include_robin=True)
+    sol = fs.Solve(formulation=form, mesh=m, material=material_for(matv, 2), boundary_condition=bc,
+                   solver=K.LinearSolver(tol=1e-13))
+    assert fs.solver_info["status"] == 0
+    A = O.assemble(pts, el, vel, matv, "consistent", False, False)
+    Ke, Fe = O.robin_matrices(pts, el, h, tinf)
+    R = O.assemble_values(el, nn, Ke, Fe)
+    Kd = csr_matrix((A["K"] + R["data"], A["indices"], A["indptr"]), shape=(nn, nn)).toarray()
+    cin, cout, td = O.dirichlet_split(flags)
+    T = np.zeros(nn); T[cout] = td
+    T[cin] = np.linalg.solve(Kd[np.ix_(cin, cin)], R["F"][cin] - Kd[np.ix_(cin, cout)] @ td)
+    assert rel_l2(sol.sol[:, 0, 0], T) < SOL_TOL
+    # the term matters: without it the solution is different
+    fs0 = K.FEMSolver(verbose=False)
+    bc0 = K.BoundaryCondition(); bc0.SetDirichletCriteria(lambda: flags.copy())
+    sol0 = fs0.Solve(formulation=form, mesh=m, material=material_for(matv, 2), boundary_condition=bc0,
+                     solver=K.LinearSolver(tol=1e-13))
+    assert rel_l2(sol0.sol[:, 0, 0], T) > 1e-4
+
+
+@pytest.mark.parametrize("name", ["distorted_consistent", "ex2d_dt010"])
+def test_transient_characteristic_galerkin(name):
+    """characteristic_galerkin=True: the explicit step with the dt^2/2 M^-1 (K_u T + F_u) correction the reference
+    carries commented out (FEMSolver.py:264-266,287-292), against the dense restatement in the oracle."""
+    from oracle import kiltro_oracle as O
+    c = TRA.case(name)
+    K, m, form, mat, bc, fs = _transient_setup(c, name, snaps="all", nincr=21)
+    fs.characteristic_galerkin = True
+    vel = c["velocity"] if np.any(c["velocity"]) else np.zeros_like(c["points"])
+    mode = "consistent" if name.endswith("consistent") else "reference"
+    ref = O.transient_characteristic_galerkin(c["points"], c["elements"], vel, tuple(c["material"]), c["dirichlet_flags"],
+                                              c["neumann_flags"] if "neumann_flags" in c else None, c["initial"], 21,
+                                              float(c["dt"]), mode=mode)
+    T = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    assert T.shape == ref.shape and rel_l2(T, ref) < SOL_TOL, fs.solver_info
+    if np.any(c["velocity"]):
+        plain = O.transient_forward_euler(c["points"], c["elements"], vel, tuple(c["material"]), c["dirichlet_flags"],
+                                          c["neumann_flags"] if "neumann_flags" in c else None, c["initial"], 21,
+                                          float(c["dt"]), mode=mode)
+        assert rel_l2(plain, ref) > 1e-9                   # the correction is not a no-op when there is advection
+    with pytest.raises(ValueError):
+        K2, m2, form2, mat2, bc2, fs2 = _transient_setup(c, name, theta=0.5, nincr=5)
+        fs2.characteristic_galerkin = True
+        fs2.Solve(formulation=form2, mesh=m2, material=mat2, boundary_condition=bc2, solver=K.LinearSolver())
