@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
+#include "spmv_pat.cuh"
 #include "peer.cuh"
 
 using namespace kbspmv;
@@ -59,6 +60,11 @@ struct Work {
     int16_t *cols16;    // 16-bit column offsets (col - row) of the scaled copy, valid when *bandflag == 0
     int *bandflag;      // device: set to 1 by the setup pass when some |col - row| does not fit 16 bits
     bool use16 = false; // host copy of the decision (re-read from bandflag after setup)
+    // row-pattern form (spmv_pat.cuh): one byte per row + a dictionary of <= 256 column-offset patterns
+    uint8_t *row_pat;   // (n rounded up to 16) + 16 bytes, zero-filled tail
+    unsigned long long *pat_keys;   // P_SLOTS hash keys (0 = empty slot)
+    pat_off_t *pat_tab; // P_SLOTS x P_MAXLEN offsets; valid when bandflag[1] == 0
+    bool usepat = false;
     int32_t *rowblk;
     unsigned int *ticket;
     int *done;          // done[0]: 0 running, 1 converged, 2 breakdown ; done[1]: iteration at which it was set
@@ -82,6 +88,9 @@ size_t carve(Work *w, char *base, int64_t n, int64_t nnz) {
     TAKE(v3, double, n + 1); TAKE(v4, double, n + 1); TAKE(v5, double, n + 1);
     TAKE(cols16, int16_t, nnz > 0 ? nnz + 8 : 8);
     TAKE(bandflag, int, 4);
+    TAKE(row_pat, uint8_t, n + 48);
+    TAKE(pat_keys, unsigned long long, P_SLOTS);
+    TAKE(pat_tab, pat_off_t, P_SLOTS * P_MAXLEN);
     TAKE(partials, double, nvec_blocks);
     TAKE(sc, double, S_COUNT);
     TAKE(rowblk, int32_t, nblk + 1);
@@ -304,7 +313,62 @@ struct HCgP {               // p = r + beta p
 
 // SpMV launcher: persistent TMA-fed kernel when the CSR arrays are 16-byte aligned, one-shot CSR-stream kernel otherwise
 int g_force_simple_spmv = 0;
+int g_no_patterns = 0;   // 1 disables the row-pattern form of the SpMV (kb_spmv_force_no_patterns)
 int g_force_idx32 = 0;   // 1 keeps 32-bit column indices even when the 16-bit offset form is available (kb_spmv_force_idx32)
+
+// ---- row-pattern dictionary (spmv_pat.cuh): built on device from the CSR pattern, once per solver setup
+__device__ __forceinline__ unsigned long long pat_mix(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+// Every row hashes its (length, col - row ...) tuple and claims / finds a slot of a 256-entry open-addressing table; the
+// slot number is the row's pattern id.  flag[1] is raised when a row is longer than P_MAXLEN or the table overflows.
+__global__ void __launch_bounds__(256) k_pattern_insert(int64_t n, const int32_t *__restrict__ indptr,
+                                                        const int32_t *__restrict__ indices,
+                                                        unsigned long long *__restrict__ keys, pat_off_t *__restrict__ tab,
+                                                        uint8_t *__restrict__ row_pat, int *__restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int p0 = indptr[i], len = indptr[i + 1] - p0;
+        if (len > P_MAXLEN) { flag[1] = 1; row_pat[i] = 0; continue; }
+        unsigned long long h = pat_mix(0x9e3779b97f4a7c15ull + (unsigned long long)len);
+        bool wide = false;
+        for (int k = 0; k < len; ++k) {
+            const int d = indices[p0 + k] - (int)i;
+            wide |= (d < -32768 || d > 32767);
+            h = pat_mix(h ^ (unsigned long long)(unsigned int)d);
+        }
+        if (wide) { flag[1] = 1; row_pat[i] = 0; continue; }
+        h |= 1ull;                                              // 0 is the empty marker
+        int slot = (int)(h % P_SLOTS), found = -1;
+        for (int probe = 0; probe < P_SLOTS; ++probe) {
+            const unsigned long long prev = atomicCAS(keys + slot, 0ull, h);
+            if (prev == 0ull) {                                 // claimed: this row defines the pattern
+                for (int k = 0; k < P_MAXLEN; ++k) tab[slot * P_MAXLEN + k] = (pat_off_t)(k < len ? indices[p0 + k] - (int)i : 0);
+                found = slot; break;
+            }
+            if (prev == h) { found = slot; break; }
+            slot = (slot + 1) % P_SLOTS;
+        }
+        if (found < 0) { flag[1] = 1; found = 0; }
+        row_pat[i] = (uint8_t)found;
+    }
+}
+// Second pass (after the table is complete): every row checks its offsets against the slot it was given -- a hash
+// collision between different patterns raises flag[1] instead of producing a wrong matrix.
+__global__ void __launch_bounds__(256) k_pattern_verify(int64_t n, const int32_t *__restrict__ indptr,
+                                                        const int32_t *__restrict__ indices, const pat_off_t *__restrict__ tab,
+                                                        const uint8_t *__restrict__ row_pat, int *__restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int p0 = indptr[i], len = indptr[i + 1] - p0;
+        if (len > P_MAXLEN) { bad = true; continue; }
+        const pat_off_t *po = tab + (int)row_pat[i] * P_MAXLEN;
+        for (int k = 0; k < len; ++k) bad |= ((int)__ldg(po + k) != indices[p0 + k] - (int)i);
+    }
+    if (bad) flag[1] = 1;
+}
 
 template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
@@ -346,6 +410,19 @@ template <int DOTS, class Final>
 int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                 const Work &w, const double *x, double *y, const double *dotw, const int *done, Final fin,
                 cudaStream_t s, const double *dotw2 = nullptr) {
+    if (w.usepat) {                                     // row-pattern form: 8 bytes per non-zero cross HBM
+        static bool configured = false;                 // one flag per template instantiation
+        constexpr size_t bytes = pat_smem_bytes();
+        if (!configured) {
+            KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured = true;
+        }
+        const int64_t nblk = num_blocks(nnz);
+        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, w.row_pat, w.pat_tab, vals, w.rowblk, x, y,
+                                                                        dotw, w.partials, w.ticket, done, fin, dotw2);
+        KB_LAUNCH_CHECK();
+        return 0;
+    }
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
                                         fin, s, w.use16 ? w.cols16 : nullptr, dotw2);
 }
@@ -497,12 +574,21 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
         k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat,
                                                              g_force_idx32 ? nullptr : w.cols16, w.bandflag);
         KB_LAUNCH_CHECK();
+        if (!g_force_idx32 && !g_no_patterns) {                // row-pattern dictionary (bandflag[1] = not expressible)
+            KB_CUDA(cudaMemsetAsync(w.pat_keys, 0, sizeof(unsigned long long) * P_SLOTS, s));
+            KB_CUDA(cudaMemsetAsync(w.row_pat, 0, (size_t)n + 48, s));
+            k_pattern_insert<<<g, 256, 0, s>>>(n, indptr, indices, w.pat_keys, w.pat_tab, w.row_pat, w.bandflag);
+            KB_LAUNCH_CHECK();
+            k_pattern_verify<<<g, 256, 0, s>>>(n, indptr, indices, w.pat_tab, w.row_pat, w.bandflag);
+            KB_LAUNCH_CHECK();
+        }
     }
-    if (!g_force_idx32) {   // 16-bit column offsets are used when the band fits (decided once per setup; one small readback)
-        int flag = 1;
-        KB_CUDA(cudaMemcpyAsync(&flag, w.bandflag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!g_force_idx32) {   // index form of the SpMV, decided once per setup (one small readback): row patterns when the
+        int flag[2] = {1, 1};   // matrix has <= 256 of them, else 16-bit column offsets when the band fits, else 32-bit
+        KB_CUDA(cudaMemcpyAsync(flag, w.bandflag, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
         KB_CUDA(cudaStreamSynchronize(s));
-        w.use16 = (flag == 0) && !g_force_idx32 && !g_force_simple_spmv && tma_eligible(indptr, w.cols16, w.vals_hat);
+        w.use16 = (flag[0] == 0) && !g_force_simple_spmv && tma_eligible(indptr, w.cols16, w.vals_hat);
+        w.usepat = (flag[1] == 0) && !g_no_patterns && !g_force_simple_spmv && tma_eligible(indptr, w.row_pat, w.vals_hat);
     }
     int rc;
     // xh = x / scale ; bh = scaled rhs
@@ -1194,6 +1280,7 @@ extern "C" int kb_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, cons
 extern "C" void kb_spmv_force_simple(int on) { g_force_simple_spmv = on; }
 /* development switch: 1 keeps 32-bit column indices in the solvers even when the 16-bit offset form is available */
 extern "C" void kb_spmv_force_idx32(int on) { g_force_idx32 = on; }
+extern "C" void kb_spmv_force_no_patterns(int on) { g_no_patterns = on; }
 
 extern "C" size_t kb_krylov_workspace_bytes(int64_t nrows, int64_t nnz) { return carve(nullptr, nullptr, nrows, nnz); }
 

@@ -719,3 +719,46 @@ def test_transient_characteristic_galerkin(name):
         K2, m2, form2, mat2, bc2, fs2 = _transient_setup(c, name, theta=0.5, nincr=5)
         fs2.characteristic_galerkin = True
         fs2.Solve(formulation=form2, mesh=m2, material=mat2, boundary_condition=bc2, solver=K.LinearSolver())
+
+
+# ------------------------------------------------------------------------------------------------- K5 index forms
+@pytest.mark.parametrize("case", ["rect_bicgstab", "rect_cg", "line", "scrambled"])
+def test_spmv_index_forms_bitwise(case):
+    """The three index forms of the solver's SpMV -- row patterns (8 B/nnz), 16-bit column offsets (10 B/nnz), 32-bit
+    indices (12 B/nnz) -- stream different bytes but multiply and add in the same order: iterates, iteration counts and
+    solutions are bit-identical.  A scrambled numbering has too many row patterns and silently uses the offset form."""
+    from oracle import kiltro_oracle as O
+    from kiltro_b200 import _lib
+    K = _K()
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    if case == "line":
+        m = K.Mesh(element_type="line"); m.Line(0.0, 1.0, 3000)
+        vel = np.full((m.nnodes, 1), 40.0)
+        d = np.full((m.nnodes, 1), np.nan); d[0] = 1.0; d[-1] = 2.0
+        form = K.HeatAdvectionDiffusion(m, velocity=vel); ndim = 1
+    else:
+        pts, el = O.mesh_rectangle((0, 0), (1, 1), 93, 71)
+        if case == "scrambled":
+            perm = rng.permutation(pts.shape[0]); inv = np.empty_like(perm); inv[perm] = np.arange(perm.size)
+            pts = pts[perm]; el = inv[el]
+        m = make_mesh(pts, el)
+        vel = np.zeros(pts.shape); vel[:, 0] = 60.0; vel += 6.0 * rng.standard_normal(pts.shape)
+        d = np.full((pts.shape[0], 1), np.nan); d[pts[:, 0] == 0.0] = 100.0; d[pts[:, 0] == 1.0] = 500.0
+        form = K.HeatDiffusion(m) if case == "rect_cg" else K.HeatAdvectionDiffusion(m, velocity=vel); ndim = 2
+    mat = material_for((1.0, 1.0, 1.0, 1.0, 0.0), ndim)
+    out = {}
+    try:
+        for mode in ("pattern", "offset16", "index32"):
+            lib.kb_spmv_force_no_patterns(0 if mode == "pattern" else 1)
+            lib.kb_spmv_force_idx32(1 if mode == "index32" else 0)
+            bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d.copy())
+            solver = K.LinearSolver(tol=1e-12, maxiter=30000, check_every=7)
+            sol = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=solver)
+            assert solver.info["status"] == 0, (mode, solver.info)
+            out[mode] = (sol.sol_device.clone(), solver.info["iterations"])
+    finally:
+        lib.kb_spmv_force_no_patterns(0); lib.kb_spmv_force_idx32(0)
+    for mode in ("offset16", "index32"):
+        assert out[mode][1] == out["pattern"][1], (mode, out[mode][1], out["pattern"][1])
+        assert torch.equal(out[mode][0], out["pattern"][0]), mode
