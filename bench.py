@@ -390,15 +390,17 @@ def main():
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "k_spmv_tma (persistent TMA-fed CSR SpMV + fused dots, inside BiCGSTAB)",
+        form_name = "32-bit indices forced" if args.idx32 else "row patterns: 8 B/nnz + 5 B/row"
+        roof = {"bound": "hbm", "kernel": "k_spmv_pat (persistent TMA-fed CSR SpMV, row-pattern form, + fused dots, inside BiCGSTAB)"
+                if not args.idx32 else "k_spmv_tma (persistent TMA-fed CSR SpMV + fused dots, inside BiCGSTAB)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "avg_launch_ms": spmv_ms, "launches_timed": int(ns.value),
                 "algorithmic_bytes_per_launch": algorithmic_bytes_spmv(nfree, nnz_b),
                 "note": "achieved = SURVEY 8(d) algorithmic bytes (12 B/nnz + 20 B/row) / CUDA-event time of the SpMV launches "
-                        "inside the timed solver loop; the kernel stores column indices as 16-bit row offsets when the band "
-                        "fits (%s here), so fewer bytes than the algorithmic count actually cross HBM (see traffic)"
-                        % ("32-bit forced" if args.idx32 else "16-bit")}
+                        "inside the timed solver loop; the kernel does not stream column indices at all when the rows of the "
+                        "matrix repeat <= 256 offset patterns (%s here), so fewer bytes than the algorithmic count cross "
+                        "HBM (see traffic) and frac can exceed 1" % form_name}
 
     # ---- second kernel of the path: numeric assembly (k_assemble_tmpl / k_assemble_fused), timed alone with CUDA events
     roof_asm = None

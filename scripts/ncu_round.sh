@@ -1,12 +1,14 @@
 #!/bin/bash
-# ncu evidence for one round (run under gpurun): launch list of a short bench run + one --set full capture of the
-# dominant kernel.  Usage: scripts/ncu_round.sh <tag> <kernel-regex>
-TAG=${1:-r01}; KRE=${2:-k_spmv}
+# ncu evidence for one round (run under gpurun): launch list of a short bench run + --set full captures of the dominant
+# kernel (SpMV inside the solver) and of the numeric assembly.  Usage: scripts/ncu_round.sh <tag> [spmv-regex] [asm-regex]
+TAG=${1:-r01}; KRE=${2:-k_spmv_pat}; ARE=${3:-k_assemble_tmpl}
 CMD="python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --maxiter 60 --check-every 20"
 mkdir -p gpurun_out
 $CMD > gpurun_out/ncu_plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 40 -c 3 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
-echo "full capture rc=$?"
+echo "full capture (spmv) rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:$ARE -s 1 -c 2 -f -o gpurun_out/prof_${TAG}_asm $CMD > gpurun_out/ncu_full_${TAG}_asm.log 2>&1
+echo "full capture (assembly) rc=$?"
 ls -la gpurun_out | tail -8
