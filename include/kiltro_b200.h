@@ -265,10 +265,20 @@ size_t kb_blocks_scratch_bytes(int64_t nnz);
  * of d_indices (10 instead of 12 bytes per non-zero) and d_x must point at the x entry of the FIRST ROW of the view. */
 int kb_make_cols16(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, int16_t *d_cols16, int32_t *d_flag,
                    void *stream);                                         /* *d_flag = 1 when an offset does not fit */
+/* d_row_pat / d_pat_tab (optional, from kb_make_row_patterns; take precedence over d_cols16): row-pattern form of
+ * csrc/spmv_pat.cuh -- one byte per row names its tuple of col - row offsets, the <= 256 tuples live in shared memory, no
+ * column index is streamed (8 bytes per non-zero).  Same convention for d_x as with d_cols16; the view's first row must
+ * be a multiple of 16 (bulk-copy alignment of the pattern bytes).
+ * kb_make_row_patterns: d_row_pat (nrows rounded up to 16, + 16 bytes), d_pat_keys (256 x 8 bytes of scratch), d_pat_tab
+ * (256 x 16 int16); *d_flag = 1 when the matrix has more than 256 patterns, a row longer than 16 or an offset beyond 16 bits. */
+int kb_make_row_patterns(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, uint8_t *d_row_pat,
+                         void *d_pat_keys, int16_t *d_pat_tab, int32_t *d_flag, void *stream);
 int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
+                 const uint8_t *d_row_pat, const int16_t *d_pat_tab,
                  const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w,
                  double *d_out2, void *d_scratch, void *stream);          /* y = A x ; out = {<w,y>, <y,y>} */
 int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
+                  const uint8_t *d_row_pat, const int16_t *d_pat_tab,
                   const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w,
                   const double *d_w2, double *d_out4, void *d_scratch, void *stream);   /* {<w,y>,<y,y>,<w2,y>,<w2,w>} */
 /* merged BiCGSTAB update: x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r> */
@@ -321,7 +331,7 @@ int kb_peer_close(void *d_ptr);
 int kb_peer_free(void *d_ptr);
 int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *stream);           /* 0 ok, 1/2: a wait timed out */
 int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
-                 const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
+                 const uint8_t *d_row_pat, const int16_t *d_pat_tab, const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
                  const kb_peer_ctx *ctx, uint64_t event, int wait_vec, uint64_t wait_seq, void *d_scratch, void *stream);
 int kb_peer_bicgstab_s(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho,
                        const double *d_v, double *d_r, double *d_alpha_out, double *d_dn_dst, double *d_up_dst,

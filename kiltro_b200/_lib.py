@@ -88,8 +88,9 @@ SIGNATURES = {
     "kb_mesh_rectangle_strip": (I32, [F64, F64, F64, F64, I64, I64, I64, I64, c_vp, c_vp, c_vp]),
     "kb_blocks_scratch_bytes": (ctypes.c_size_t, [I64]),
     "kb_make_cols16": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_make_row_patterns": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_dots": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_spmv_dots4": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_update_p": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_s2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_bicgstab_update_p2": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -111,7 +112,7 @@ SIGNATURES = {
     "kb_peer_close": (I32, [c_vp]),
     "kb_peer_free": (I32, [c_vp]),
     "kb_peer_error": (I32, [ctypes.POINTER(kb_peer_ctx), ctypes.POINTER(I64), c_vp]),
-    "kb_peer_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_peer_ctx),
+    "kb_peer_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_peer_ctx),
                            ctypes.c_uint64, I32, ctypes.c_uint64, c_vp, c_vp]),
     "kb_peer_bicgstab_s": (I32, [I64, I64, ctypes.POINTER(kb_peer_ctx), ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  ctypes.c_uint64, c_vp, c_vp]),

@@ -377,8 +377,23 @@ template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                     const int32_t *rowblk, double *partials, unsigned int *ticket, const double *x, double *y,
                     const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr,
-                    const double *dotw2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}) {
+                    const double *dotw2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr},
+                    const uint8_t *row_pat = nullptr, const pat_off_t *pat_tab = nullptr) {
     const int64_t nblk = num_blocks(nnz);
+    if (row_pat != nullptr) {                           // row-pattern form: 8 bytes per non-zero cross HBM
+        // like the 16-bit form it addresses x relative to the first row of the view: never fall back silently
+        if (pat_tab == nullptr || g_force_simple_spmv || !tma_eligible(indptr, row_pat, vals)) return KB_EINVAL;
+        static bool configured = false;                 // one flag per template instantiation
+        constexpr size_t bytes = pat_smem_bytes();
+        if (!configured) {
+            KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured = true;
+        }
+        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, row_pat, pat_tab, vals, rowblk, x, y, dotw,
+                                                                        partials, ticket, done, fin, dotw2, pwait);
+        KB_LAUNCH_CHECK();
+        return 0;
+    }
     // 16-bit offsets change the meaning of x (relative to the first row of the view): never fall back silently
     if (indices16 != nullptr && (g_force_simple_spmv || !tma_eligible(indptr, indices16, vals))) return KB_EINVAL;
     if (indices16 != nullptr) {
@@ -413,21 +428,9 @@ template <int DOTS, class Final>
 int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                 const Work &w, const double *x, double *y, const double *dotw, const int *done, Final fin,
                 cudaStream_t s, const double *dotw2 = nullptr) {
-    if (w.usepat) {                                     // row-pattern form: 8 bytes per non-zero cross HBM
-        static bool configured = false;                 // one flag per template instantiation
-        constexpr size_t bytes = pat_smem_bytes();
-        if (!configured) {
-            KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured = true;
-        }
-        const int64_t nblk = num_blocks(nnz);
-        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, w.row_pat, w.pat_tab, vals, w.rowblk, x, y,
-                                                                        dotw, w.partials, w.ticket, done, fin, dotw2);
-        KB_LAUNCH_CHECK();
-        return 0;
-    }
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
-                                        fin, s, w.use16 ? w.cols16 : nullptr, dotw2);
+                                        fin, s, w.use16 ? w.cols16 : nullptr, dotw2,
+                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, w.usepat ? w.row_pat : nullptr, w.pat_tab);
 }
 
 // ------------------------------------------------------------------------------------------------ functors
@@ -821,19 +824,22 @@ extern "C" size_t kb_blocks_scratch_bytes(int64_t nnz) {
 
 // y = A x over `nrows` rows + local partial dots d_out2 = {<w,y>, <y,y>}
 extern "C" int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
-                            const int16_t *d_cols16, const double *d_vals, const int32_t *d_rowblk, const double *d_x,
+                            const int16_t *d_cols16, const uint8_t *d_row_pat, const int16_t *d_pat_tab,
+                            const double *d_vals, const int32_t *d_rowblk, const double *d_x,
                             double *d_y, const double *d_w, double *d_out2, void *d_scratch, void *stream) {
     if (!d_indptr || !d_indices || (!d_vals && nnz > 0) || !d_rowblk || !d_x || !d_y || !d_w || !d_out2 || !d_scratch)
         return KB_EINVAL;
     if (nrows <= 0) return 0;
     const Scratch sc = scratch_of(d_scratch);
     return launch_spmv_raw<1, FinStore>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
-                                        d_y, d_w, nullptr, FinStore{d_out2}, (cudaStream_t)stream, d_cols16);
+                                        d_y, d_w, nullptr, FinStore{d_out2}, (cudaStream_t)stream, d_cols16, nullptr,
+                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, d_row_pat, d_pat_tab);
 }
 // 4-dot form: out4 = {<w,y>, <y,y>, <w2,y>, <w2,w>}  (merged BiCGSTAB update)
 struct FinStore4 { double *out; __device__ void operator()(double a, double b, double c, double d) const { out[0] = a; out[1] = b; out[2] = c; out[3] = d; } };
 extern "C" int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
-                             const int16_t *d_cols16, const double *d_vals, const int32_t *d_rowblk, const double *d_x,
+                             const int16_t *d_cols16, const uint8_t *d_row_pat, const int16_t *d_pat_tab,
+                             const double *d_vals, const int32_t *d_rowblk, const double *d_x,
                              double *d_y, const double *d_w, const double *d_w2, double *d_out4, void *d_scratch,
                              void *stream) {
     if (!d_indptr || !d_indices || (!d_vals && nnz > 0) || !d_rowblk || !d_x || !d_y || !d_w || !d_w2 || !d_out4 ||
@@ -842,7 +848,8 @@ extern "C" int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr
     if (nrows <= 0) return 0;
     const Scratch sc = scratch_of(d_scratch);
     return launch_spmv_raw<2, FinStore4>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
-                                         d_y, d_w, nullptr, FinStore4{d_out4}, (cudaStream_t)stream, d_cols16, d_w2);
+                                         d_y, d_w, nullptr, FinStore4{d_out4}, (cudaStream_t)stream, d_cols16, d_w2,
+                                         kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, d_row_pat, d_pat_tab);
 }
 // x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r>   (s is passed in r)
 extern "C" int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,
@@ -998,6 +1005,30 @@ __global__ void __launch_bounds__(256) k_make_cols16(int64_t n, const int32_t *_
     if (wide) *flag = 1;
 }
 }  // namespace
+// Row-pattern dictionary of a CSR pattern (spmv_pat.cuh) for the SpMV building blocks: d_row_pat (nrows rounded up to 16,
+// + 16 bytes), d_pat_keys (256 x 8 bytes scratch), d_pat_tab (256 x 16 int16), d_flag[0] = 1 when the matrix cannot be
+// expressed (more than 256 patterns, a row longer than 16, an offset beyond 16 bits).
+extern "C" int kb_make_row_patterns(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, uint8_t *d_row_pat,
+                                    void *d_pat_keys, int16_t *d_pat_tab, int32_t *d_flag, void *stream) {
+    if (!d_indptr || !d_indices || !d_row_pat || !d_pat_keys || !d_pat_tab || !d_flag || nrows < 0) return KB_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    int *flag2;
+    KB_CUDA(cudaMallocAsync((void **)&flag2, sizeof(int) * 2, s));
+    KB_CUDA(cudaMemsetAsync(flag2, 0, sizeof(int) * 2, s));
+    KB_CUDA(cudaMemsetAsync(d_pat_keys, 0, sizeof(unsigned long long) * P_SLOTS, s));
+    KB_CUDA(cudaMemsetAsync(d_row_pat, 0, (size_t)((nrows + 15) / 16 * 16 + 16), s));
+    if (nrows > 0) {
+        const int g = kb_grid(nrows, 256, 8);
+        k_pattern_insert<<<g, 256, 0, s>>>(nrows, d_indptr, d_indices, (unsigned long long *)d_pat_keys, d_pat_tab, d_row_pat, flag2);
+        KB_LAUNCH_CHECK();
+        k_pattern_verify<<<g, 256, 0, s>>>(nrows, d_indptr, d_indices, d_pat_tab, d_row_pat, flag2);
+        KB_LAUNCH_CHECK();
+    }
+    KB_CUDA(cudaMemcpyAsync(d_flag, flag2 + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    KB_CUDA(cudaFreeAsync(flag2, s));
+    return 0;
+}
+
 extern "C" int kb_make_cols16(int64_t nrows, const int32_t *d_indptr, const int32_t *d_indices, int16_t *d_cols16,
                               int32_t *d_flag, void *stream) {
     if (!d_indptr || !d_indices || !d_cols16 || !d_flag || nrows < 0) return KB_EINVAL;
@@ -1198,7 +1229,8 @@ extern "C" int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *strea
 // y = A x on the owned rows; partial dots {<w,y>,<y,y>[,<w2,y>,<w2,w>]} are published to every rank as event `event`.
 // wait_vec: -1 no wait, 0 / 1: wait until the neighbours' halo flags of vector 0 (p) / 1 (r) reached wait_seq.
 extern "C" int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
-                            const int16_t *d_cols16, const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y,
+                            const int16_t *d_cols16, const uint8_t *d_row_pat, const int16_t *d_pat_tab,
+                            const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y,
                             const double *d_w, const double *d_w2, const kb_peer_ctx *ctx, uint64_t event, int wait_vec,
                             uint64_t wait_seq, void *d_scratch, void *stream) {
     if (!d_indptr || !d_indices || !d_vals || !d_rowblk || !d_x || !d_y || !d_w || !ctx || !d_scratch || nrows <= 0 ||
@@ -1213,9 +1245,11 @@ extern "C" int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr,
     }
     if (d_w2)
         return launch_spmv_raw<2, FinPostDots>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
-                                               d_y, d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, d_w2, w);
+                                               d_y, d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, d_w2, w,
+                                               d_row_pat, d_pat_tab);
     return launch_spmv_raw<1, FinPostDots>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x, d_y,
-                                           d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, nullptr, w);
+                                           d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, nullptr, w,
+                                           d_row_pat, d_pat_tab);
 }
 extern "C" int kb_peer_bicgstab_s(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho,
                                   const double *d_v, double *d_r, double *d_alpha_out, double *d_dn_dst, double *d_up_dst,

@@ -36,7 +36,8 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
            const pat_off_t *__restrict__ pat_tab, const double *__restrict__ vals, const int32_t *__restrict__ rowblk,
            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
            double *__restrict__ partials, unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
-           const double *__restrict__ w2 = nullptr) {
+           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}) {
+    // pwait: halo flags raised by the neighbouring ranks (peer.cuh); the kernel does not touch x before they are up
     if (done != nullptr && *done != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GRAN = 2;                                // values per 16 bytes (bulk-copy granule)
@@ -56,6 +57,7 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
         for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], T_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        kbpeer::wait_flags(pwait);
     }
     __syncthreads();
 

@@ -26,6 +26,7 @@ from .FiniteElements.Assembly import Assemble
 # Hide the halo exchange behind the interior rows of the SpMV (3 launches instead of 1).  Measured on 2 B200s at 16 M DOF
 # per GPU: no gain (the exchange is short compared with the launch overhead it adds), so it is off by default.
 OVERLAP_HALO = False
+USE_ROW_PATTERNS = True       # row-pattern form of the SpMV (csrc/spmv_pat.cuh) when the local matrix allows it
 
 
 class StripPartition(object):
@@ -158,6 +159,12 @@ class LocalSystem(object):
         self.part = part
         self.lib = _lib.load()
         self.cols16 = None
+        self.row_pat = None             # row-pattern form of the SpMV (csrc/spmv_pat.cuh): one byte per local row
+        self.pat_tab = None
+
+    def pat_ptr(self, row0):
+        """Pattern bytes of a row view starting at local row `row0` (NULL when the form is not in use)."""
+        return None if self.row_pat is None else self.row_pat.data_ptr() + row0
 
     def _view(self, A_vals):
         """Row-range view (owned rows) of the local CSR for the SpMV kernel."""
@@ -166,19 +173,21 @@ class LocalSystem(object):
     def xptr(self, x, row0):
         """x argument of the SpMV kernels for a row view starting at local row `row0`: with 16-bit column offsets the
         kernel addresses x relative to the first row of the view."""
-        return x.data_ptr() + (8 * row0 if self.cols16 is not None else 0)
+        return x.data_ptr() + (8 * row0 if (self.cols16 is not None or self.row_pat is not None) else 0)
 
     def spmv_dots(self, vals, x, y, w, out2):
         p = self.part
         _lib.check(self.lib.kb_spmv_dots(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
-                                         D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(self.rowblk),
+                                         D.ptr(self.indices), D.ptr(self.cols16), self.pat_ptr(p.own_off), D.ptr(self.pat_tab),
+                                         D.ptr(vals), D.ptr(self.rowblk),
                                          self.xptr(x, p.own_off), y.data_ptr() + 8 * p.own_off,
                                          w.data_ptr() + 8 * p.own_off, D.ptr(out2), D.ptr(self.scratch), D.stream_ptr()))
 
     def spmv_dots4(self, vals, x, y, w, w2, out4):
         p = self.part
         _lib.check(self.lib.kb_spmv_dots4(p.n_own, self.nnz_own, self.indptr.data_ptr() + 4 * p.own_off,
-                                          D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(self.rowblk),
+                                          D.ptr(self.indices), D.ptr(self.cols16), self.pat_ptr(p.own_off), D.ptr(self.pat_tab),
+                                          D.ptr(vals), D.ptr(self.rowblk),
                                           self.xptr(x, p.own_off), y.data_ptr() + 8 * p.own_off,
                                           w.data_ptr() + 8 * p.own_off, w2.data_ptr() + 8 * p.own_off, D.ptr(out4),
                                           D.ptr(self.scratch), D.stream_ptr()))
@@ -216,10 +225,12 @@ class LocalSystem(object):
         ip = self.indptr.data_ptr() + 4 * r0
         yp, wp = y.data_ptr() + 8 * r0, w.data_ptr() + 8 * r0
         if w2 is None:
-            _lib.check(self.lib.kb_spmv_dots(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(rb),
+            _lib.check(self.lib.kb_spmv_dots(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), self.pat_ptr(r0),
+                                             D.ptr(self.pat_tab), D.ptr(vals), D.ptr(rb),
                                              self.xptr(x, r0), yp, wp, D.ptr(out), D.ptr(self.scratch), D.stream_ptr()))
         else:
-            _lib.check(self.lib.kb_spmv_dots4(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), D.ptr(vals), D.ptr(rb),
+            _lib.check(self.lib.kb_spmv_dots4(nr, nnz, ip, D.ptr(self.indices), D.ptr(self.cols16), self.pat_ptr(r0),
+                                              D.ptr(self.pat_tab), D.ptr(vals), D.ptr(rb),
                                               self.xptr(x, r0), yp, wp, w2.data_ptr() + 8 * r0, D.ptr(out),
                                               D.ptr(self.scratch), D.stream_ptr()))
 
@@ -304,6 +315,15 @@ def reassemble(sysm):
         c16 = D.empty(K.nnz + 8, torch.int16); flag = D.zeros(1, torch.int32)
         _lib.check(lib.kb_make_cols16(part.n_loc, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(c16), D.ptr(flag), D.stream_ptr()))
         sysm.cols16 = c16 if (int(flag.item()) == 0 and part.nxn % 4 == 0 and K.indptr.data_ptr() % 16 == 0) else None
+        # row patterns (8 bytes per non-zero: no column index is streamed) when the local matrix has <= 256 of them; the
+        # row views start at multiples of nxn, which must keep the pattern bytes 16-byte aligned
+        if sysm.cols16 is not None and part.nxn % 16 == 0 and USE_ROW_PATTERNS:
+            rp = D.empty((part.n_loc + 15) // 16 * 16 + 16, torch.uint8)
+            keys = D.empty(256 * 8, torch.uint8); tab = D.empty(256 * 16, torch.int16); pflag = D.zeros(1, torch.int32)
+            _lib.check(lib.kb_make_row_patterns(part.n_loc, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(rp), D.ptr(keys),
+                                                D.ptr(tab), D.ptr(pflag), D.stream_ptr()))
+            if int(pflag.item()) == 0:
+                sysm.row_pat, sysm.pat_tab = rp, tab
     n = part.n_loc
     # right-hand side of the steady problem on A' = [Kff 0; 0 I]:  F - K[:,fixed] T_D at free rows, T_D at fixed rows
     F = (-Fn).contiguous()
@@ -566,14 +586,16 @@ def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000
     while it < maxiter:
         for _ in range(min(check_every, maxiter - it)):
             region.ev += 1                               # v = A p ; {<rhat,v>}
-            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], A[1], A[2], sysm.xptr(p, off), own(v), own(rhat), None, region.ctx,
+            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], sysm.pat_ptr(off), D.ptr(sysm.pat_tab), A[1], A[2],
+                                        sysm.xptr(p, off), own(v), own(rhat), None, region.ctx,
                                         region.ev, -1 if first else 0, region.hseq[0], D.ptr(sysm.scratch), st()))
             first = False
             region.hseq[1] += 1                          # alpha ; s = r - alpha v ; boundary rows of s -> neighbours
             _lib.check(lib.kb_peer_bicgstab_s(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), own(v), own(r), D.ptr(alpha),
                                               region.dn_dst[1], region.up_dst[1], region.hseq[1], D.ptr(sysm.scratch), st()))
             region.ev += 1                               # t = A s ; {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
-            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], A[1], A[2], sysm.xptr(r, off), own(t), own(r), own(rhat), region.ctx,
+            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], sysm.pat_ptr(off), D.ptr(sysm.pat_tab), A[1], A[2],
+                                        sysm.xptr(r, off), own(t), own(r), own(rhat), region.ctx,
                                         region.ev, 1, region.hseq[1], D.ptr(sysm.scratch), st()))
             region.hseq[0] += 1                          # omega, rho, beta ; x, r, p ; boundary rows of p -> neighbours
             _lib.check(lib.kb_peer_bicgstab_update_p(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), D.ptr(rho[cur ^ 1]),

@@ -497,9 +497,11 @@ def _dist_problem(nx, ny, world, transient, sym=False):
     return K, KD, systems, KD.LocalComm(world), (m, form, mat, bc)
 
 
-@pytest.mark.parametrize("world,sym", [(2, False), (3, False), (4, True)])
-def test_partitioned_steady_matches_single_gpu(world, sym):
-    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(44, 37, world, False, sym)
+@pytest.mark.parametrize("world,sym,nx", [(2, False, 44), (3, False, 44), (4, True, 44), (2, False, 63), (3, True, 95)])
+def test_partitioned_steady_matches_single_gpu(world, sym, nx):
+    """nx = 63 / 95: 64 / 96 nodes per mesh row -> 16-byte aligned row views -> the row-pattern form of the SpMV is used."""
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(nx, 37, world, False, sym)
+    assert all((s.row_pat is not None) == ((nx + 1) % 16 == 0) for s in systems)
     for s, p in zip(systems, [s.part for s in systems]):      # strip coordinates are bit-identical to the global mesh
         assert torch.equal(s.mesh.device_points(), m.device_points()[p.j_first * p.nxn:p.j_first * p.nxn + p.n_loc])
     sols, info = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10)
