@@ -219,9 +219,72 @@ KB_HD void quad4_general(const double (&X)[4][2], const double (&U)[4][2], const
 //   * dV (rho c_v u . grad N_b) = sign(det) (t0[gj] z_b + t1[gi] e_b),  t0 = rcu x dX/deta, t1 = dX/dzeta x rcu -- no
 //     division at all -- and with the weights W_a = N_a + cb0 z_a + cb1 e_a the advection matrix separates the same way.
 // ~215 fp64 instructions per element instead of ~450 (rounding differs from the general routine at the 1e-16 level).
-// Needs det_g of one sign at the four Gauss points (any valid element, either orientation) and a product of the four
-// inside the double range; otherwise returns false with Ke untouched (Fe and Me are always valid) and the caller runs
+// Affine elements (parallelograms: opposite edge vectors bit-equal) take a shorter form of the same algebra (~95 fp64
+// instructions).  Needs det_g of one sign at the four Gauss points (any valid element, either orientation) and a product
+// of the four inside the double range; otherwise returns false with Ke untouched (Fe and Me are always valid) and the caller runs
 // quad4_general for Ke.
+// advection coefficients shared by the general and the affine form: per weight row a,
+// C_ab = sz_b al[a][pb == pa] + se_b be[a][qb == qa]   (zero when there is no advection)
+KB_HD void quad4_adv_coeffs(const double (&t0)[2], const double (&t1)[2], double ub0, double ub1, double hx, double hy,
+                            bool has_adv, const ElemOpts &o, double (&alS)[4], double (&alD)[4], double (&beS)[4],
+                            double (&beD)[4]) {
+    constexpr double HHI = 0.5 * NHI, HLO = 0.5 * NLO;
+    constexpr double HH2 = HHI * HHI, LL2 = HLO * HLO, HL = HHI * HLO;
+    constexpr int PA[4] = {0, 0, 1, 1}, QA[4] = {0, 1, 1, 0};
+    constexpr double SZ[4] = {-1.0, 1.0, 1.0, -1.0}, SE[4] = {-1.0, -1.0, 1.0, 1.0};
+    if (has_adv) {
+        const double A0[2] = {HHI * t0[0] + HLO * t0[1], HLO * t0[0] + HHI * t0[1]};          // A0[q] = sum_gj h_q t0
+        const double A1[2] = {HHI * t1[0] + HLO * t1[1], HLO * t1[0] + HHI * t1[1]};          // A1[p] = sum_gi h_p t1
+        constexpr double H4S = 4.0 * (HH2 + LL2), H4D = 8.0 * HL;       // 4 H[p][p'] : same / different index
+        if (o.petrov) {
+            // weights W_a = N_a + cb0 z_a + cb1 e_a  (parent-space gradients)                    :311-330
+            const double coef = pg_coefficient(sqrt(ub0 * ub0 + ub1 * ub1), sqrt(hx * hx + hy * hy), o.k);
+            const double cb0 = coef * ub0, cb1 = coef * ub1;
+            const double cS0 = cb0 * (t0[0] + t0[1]), cS1 = cb1 * (t1[0] + t1[1]);
+            const double u0 = 0.5 * cb0, v0 = 0.5 * cb1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double A0p = 4.0 * A0[QA[a]] + SZ[a] * cS0, A1p = 4.0 * A1[PA[a]] + SE[a] * cS1;
+                const double ua = (SZ[a] * u0) * A1[PA[a]], va = (SE[a] * v0) * A0[QA[a]];
+                alS[a] = (HH2 + LL2) * A0p + va; alD[a] = (2.0 * HL) * A0p + va;
+                beS[a] = (HH2 + LL2) * A1p + ua; beD[a] = (2.0 * HL) * A1p + ua;
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                alS[a] = H4S * A0[QA[a]]; alD[a] = H4D * A0[QA[a]];
+                beS[a] = H4S * A1[PA[a]]; beD[a] = H4D * A1[PA[a]];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { alS[a] = 0.0; alD[a] = 0.0; beS[a] = 0.0; beD[a] = 0.0; }
+    }
+}
+
+// Ke = (symmetric diffusion part D, upper triangle 00 01 02 03 11 12 13 22 23 33) + advection part
+KB_HD void quad4_writeout(const double (&D)[10], const double (&alS)[4], const double (&alD)[4], const double (&beS)[4],
+                          const double (&beD)[4], const ElemOpts &o, double (&Ke)[16]) {
+    constexpr int PA[4] = {0, 0, 1, 1}, QA[4] = {0, 1, 1, 0};
+    constexpr double SZ[4] = {-1.0, 1.0, 1.0, -1.0}, SE[4] = {-1.0, -1.0, 1.0, 1.0};
+    constexpr int TRI[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+    if (o.mode == KB_MODE_CONSISTENT) {                                                       // MaterialBase.py:58
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                Ke[4 * a + b] = D[TRI[a][b]] + (SZ[b] * (PA[b] == PA[a] ? alS[a] : alD[a]) + SE[b] * (QA[b] == QA[a] ? beS[a] : beD[a]));
+    } else {                                                             // np.dot(advection, W), a scalar     :170
+        double S = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) S += SZ[a] * alS[a] + SE[a] * beS[a];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Ke[4 * a + b] = D[TRI[a][b]] + S;
+    }
+}
+
 KB_HD bool quad4_fast(const double (&X)[4][2], const double (&U)[4][2], const ElemOpts &o, double (&Ke)[16],
                       double (&Fe)[4], double (&Me)[16]) {
     constexpr double HHI = 0.5 * NHI, HLO = 0.5 * NLO;
@@ -236,112 +299,92 @@ KB_HD bool quad4_fast(const double (&X)[4][2], const double (&U)[4][2], const El
     const double e32x = X[2][0] - X[3][0], e32y = X[2][1] - X[3][1];
     const double e03x = X[3][0] - X[0][0], e03y = X[3][1] - X[0][1];
     const double e12x = X[2][0] - X[1][0], e12y = X[2][1] - X[1][1];
-    // dX/dzeta at eta-index gi, dX/deta at zeta-index gj                                    VariationalPrinciple.py:139
-    const double Jzx[2] = {HHI * e01x + HLO * e32x, HLO * e01x + HHI * e32x};
-    const double Jzy[2] = {HHI * e01y + HLO * e32y, HLO * e01y + HHI * e32y};
-    const double Jex[2] = {HHI * e03x + HLO * e12x, HLO * e03x + HHI * e12x};
-    const double Jey[2] = {HHI * e03y + HLO * e12y, HLO * e03y + HHI * e12y};
-    double det4[4];                                   // g = 2 gi + gj
+    double alS[4], alD[4], beS[4], beD[4], D[10], dV[4];
+    bool ok;
+    if (e01x == e32x && e01y == e32y && e03x == e12x && e03y == e12y) {
+        // ---- affine element (parallelogram: everything Mesh.Rectangle generates, MeshGeneration/Mesh.py:33-58).  The
+        // Jacobian is constant, so the Gauss sums collapse: the diffusion part has 6 distinct values from 3 numbers.
+        const double jzx = 0.5 * e01x, jzy = 0.5 * e01y, jex = 0.5 * e03x, jey = 0.5 * e03y;
+        const double det = jzx * jey - jzy * jex, ad = fabs(det);
+        ok = ad > 1.0e-60 && ad < 1.0e60;
+        dV[0] = dV[1] = dV[2] = dV[3] = ad;
+        if (ok) {
+            const double sg = det > 0.0 ? o.rho_cv : -o.rho_cv;                  // sign(det) rho c_v
+            const double rb0 = sg * ub0, rb1 = sg * ub1;
+            const double t0 = rb0 * jey - rb1 * jex, t1 = rb1 * jzx - rb0 * jzy;
+            const double t0v[2] = {t0, t0}, t1v[2] = {t1, t1};
+            quad4_adv_coeffs(t0v, t1v, ub0, ub1, e01x, e01y, has_adv, o, alS, alD, beS, beD);
+            const double s = (o.area * o.k) * fast_rcp(ad);
+            const double A = s * (jey * jey + jex * jex), B = s * (jzy * jzy + jzx * jzx);
+            const double hm = 0.5 * (s * (jey * jzy + jex * jzx));
+            constexpr double C1 = 2.0 * (HH2 + LL2), C2 = 4.0 * HL;             // 1/3 and 1/6 for the exact abscissa
+            const double cab = C1 * (A + B), dab = C2 * (A + B);
+            const double d00 = cab - hm, d11 = cab + hm, d01 = C2 * B - C1 * A, d03 = C2 * A - C1 * B;
+            D[0] = d00; D[1] = d01; D[2] = hm - dab; D[3] = d03; D[4] = d11;
+            D[5] = d03; D[6] = -dab - hm; D[7] = d00; D[8] = d01; D[9] = d11;
+        }
+    } else {
+        // dX/dzeta at eta-index gi, dX/deta at zeta-index gj                                VariationalPrinciple.py:139
+        const double Jzx[2] = {HHI * e01x + HLO * e32x, HLO * e01x + HHI * e32x};
+        const double Jzy[2] = {HHI * e01y + HLO * e32y, HLO * e01y + HHI * e32y};
+        const double Jex[2] = {HHI * e03x + HLO * e12x, HLO * e03x + HHI * e12x};
+        const double Jey[2] = {HHI * e03y + HLO * e12y, HLO * e03y + HHI * e12y};
+        double det4[4];                                   // g = 2 gi + gj
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi)
+        for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-        for (int gj = 0; gj < 2; ++gj) det4[2 * gi + gj] = Jzx[gi] * Jey[gj] - Jzy[gi] * Jex[gj];
-    const bool pos = det4[0] > 0.0 && det4[1] > 0.0 && det4[2] > 0.0 && det4[3] > 0.0;
-    const bool neg = det4[0] < 0.0 && det4[1] < 0.0 && det4[2] < 0.0 && det4[3] < 0.0;
-    const double p01 = det4[0] * det4[1], p23 = det4[2] * det4[3], P4 = p01 * p23;
-    const bool ok = (pos || neg) && (P4 > 1.0e-250 && P4 < 1.0e250);
-    if (ok) {
-        // ---- advection: per weight row a, C_ab = sz_b al[a][pb == pa] + se_b be[a][qb == qa]
-        double alS[4], alD[4], beS[4], beD[4];
-        constexpr int PA[4] = {0, 0, 1, 1}, QA[4] = {0, 1, 1, 0};
-        constexpr double SZ[4] = {-1.0, 1.0, 1.0, -1.0}, SE[4] = {-1.0, -1.0, 1.0, 1.0};
-        if (has_adv) {
+            for (int gj = 0; gj < 2; ++gj) det4[2 * gi + gj] = Jzx[gi] * Jey[gj] - Jzy[gi] * Jex[gj];
+        const bool pos = det4[0] > 0.0 && det4[1] > 0.0 && det4[2] > 0.0 && det4[3] > 0.0;
+        const bool neg = det4[0] < 0.0 && det4[1] < 0.0 && det4[2] < 0.0 && det4[3] < 0.0;
+        const double p01 = det4[0] * det4[1], p23 = det4[2] * det4[3], P4 = p01 * p23;
+        ok = (pos || neg) && (P4 > 1.0e-250 && P4 < 1.0e250);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dV[g] = fabs(det4[g]);
+        if (ok) {
+            // ---- advection
             const double sg = pos ? o.rho_cv : -o.rho_cv;                    // sign(det) rho c_v
             const double rb0 = sg * ub0, rb1 = sg * ub1;
             const double t0[2] = {rb0 * Jey[0] - rb1 * Jex[0], rb0 * Jey[1] - rb1 * Jex[1]};     // per gj
             const double t1[2] = {rb1 * Jzx[0] - rb0 * Jzy[0], rb1 * Jzx[1] - rb0 * Jzy[1]};     // per gi
-            const double A0[2] = {HHI * t0[0] + HLO * t0[1], HLO * t0[0] + HHI * t0[1]};          // A0[q] = sum_gj h_q t0
-            const double A1[2] = {HHI * t1[0] + HLO * t1[1], HLO * t1[0] + HHI * t1[1]};          // A1[p] = sum_gi h_p t1
-            constexpr double H4S = 4.0 * (HH2 + LL2), H4D = 8.0 * HL;       // 4 H[p][p'] : same / different index
-            if (o.petrov) {
-                // weights W_a = N_a + cb0 z_a + cb1 e_a  (parent-space gradients)                    :311-330
-                const double coef = pg_coefficient(sqrt(ub0 * ub0 + ub1 * ub1), sqrt(e01x * e01x + e01y * e01y), o.k);
-                const double cb0 = coef * ub0, cb1 = coef * ub1;
-                const double cS0 = cb0 * (t0[0] + t0[1]), cS1 = cb1 * (t1[0] + t1[1]);
-                const double u0 = 0.5 * cb0, v0 = 0.5 * cb1;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double A0p = 4.0 * A0[QA[a]] + SZ[a] * cS0, A1p = 4.0 * A1[PA[a]] + SE[a] * cS1;
-                    const double ua = (SZ[a] * u0) * A1[PA[a]], va = (SE[a] * v0) * A0[QA[a]];
-                    alS[a] = (HH2 + LL2) * A0p + va; alD[a] = (2.0 * HL) * A0p + va;
-                    beS[a] = (HH2 + LL2) * A1p + ua; beD[a] = (2.0 * HL) * A1p + ua;
-                }
-            } else {
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    alS[a] = H4S * A0[QA[a]]; alD[a] = H4D * A0[QA[a]];
-                    beS[a] = H4S * A1[PA[a]]; beD[a] = H4D * A1[PA[a]];
-                }
+            quad4_adv_coeffs(t0, t1, ub0, ub1, e01x, e01y, has_adv, o, alS, alD, beS, beD);
+            // ---- diffusion
+            // s_g = area k / |det_g| by one batched inversion
+            double s[4];
+            {
+                const double iP = (o.area * o.k) * fast_rcp(P4);                // P4 > 0
+                const double i01 = iP * p23, i23 = iP * p01;
+                s[0] = fabs(i01 * det4[1]); s[1] = fabs(i01 * det4[0]); s[2] = fabs(i23 * det4[3]); s[3] = fabs(i23 * det4[2]);
             }
-        } else {
+            const double n11[2] = {Jey[0] * Jey[0] + Jex[0] * Jex[0], Jey[1] * Jey[1] + Jex[1] * Jex[1]};
+            const double n00[2] = {Jzy[0] * Jzy[0] + Jzx[0] * Jzx[0], Jzy[1] * Jzy[1] + Jzx[1] * Jzx[1]};
+            const double a00[2] = {n11[0] * s[0] + n11[1] * s[1], n11[0] * s[2] + n11[1] * s[3]};      // sum over gj, per gi
+            const double a11[2] = {n00[0] * s[0] + n00[1] * s[2], n00[0] * s[1] + n00[1] * s[3]};      // sum over gi, per gj
+            const double P00 = HH2 * a00[0] + LL2 * a00[1], P11 = LL2 * a00[0] + HH2 * a00[1], P01 = HL * (a00[0] + a00[1]);
+            const double Q00 = HH2 * a11[0] + LL2 * a11[1], Q11 = LL2 * a11[0] + HH2 * a11[1], Q01 = HL * (a11[0] + a11[1]);
+            double m[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { alS[a] = 0.0; alD[a] = 0.0; beS[a] = 0.0; beD[a] = 0.0; }
-        }
-        // ---- diffusion
-        // s_g = area k / |det_g| by one batched inversion
-        double s[4];
-        {
-            const double iP = (o.area * o.k) * fast_rcp(P4);                // P4 > 0
-            const double i01 = iP * p23, i23 = iP * p01;
-            s[0] = fabs(i01 * det4[1]); s[1] = fabs(i01 * det4[0]); s[2] = fabs(i23 * det4[3]); s[3] = fabs(i23 * det4[2]);
-        }
-        const double n11[2] = {Jey[0] * Jey[0] + Jex[0] * Jex[0], Jey[1] * Jey[1] + Jex[1] * Jex[1]};
-        const double n00[2] = {Jzy[0] * Jzy[0] + Jzx[0] * Jzx[0], Jzy[1] * Jzy[1] + Jzx[1] * Jzx[1]};
-        const double a00[2] = {n11[0] * s[0] + n11[1] * s[1], n11[0] * s[2] + n11[1] * s[3]};      // sum over gj, per gi
-        const double a11[2] = {n00[0] * s[0] + n00[1] * s[2], n00[0] * s[1] + n00[1] * s[3]};      // sum over gi, per gj
-        const double P00 = HH2 * a00[0] + LL2 * a00[1], P11 = LL2 * a00[0] + HH2 * a00[1], P01 = HL * (a00[0] + a00[1]);
-        const double Q00 = HH2 * a11[0] + LL2 * a11[1], Q11 = LL2 * a11[0] + HH2 * a11[1], Q01 = HL * (a11[0] + a11[1]);
-        double m[4];
+            for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-        for (int gi = 0; gi < 2; ++gi)
-#pragma unroll
-            for (int gj = 0; gj < 2; ++gj) m[2 * gi + gj] = s[2 * gi + gj] * (Jey[gj] * Jzy[gi] + Jex[gj] * Jzx[gi]);
-        // Y_q[gi] = sum_gj h_q[gj] m[gi][gj];  Xm[p][q] = sum_gi h_p[gi] Y_q[gi]
-        const double Y0[2] = {HHI * m[0] + HLO * m[1], HHI * m[2] + HLO * m[3]};
-        const double Y1[2] = {HLO * m[0] + HHI * m[1], HLO * m[2] + HHI * m[3]};
-        const double X00 = HHI * Y0[0] + HLO * Y0[1], X01 = HHI * Y1[0] + HLO * Y1[1];
-        const double X10 = HLO * Y0[0] + HHI * Y0[1], X11 = HLO * Y1[0] + HHI * Y1[1];
-        double D[10];                 // upper triangle (00 01 02 03 11 12 13 22 23 33)
-        D[0] = (P00 + Q00) - (X00 + X00);
-        D[1] = (Q01 - P00) + (X00 - X01);
-        D[2] = (X01 + X10) - (P01 + Q01);
-        D[3] = (P01 - Q00) + (X00 - X10);
-        D[4] = (P00 + Q11) + (X01 + X01);
-        D[5] = (P01 - Q11) + (X11 - X01);
-        D[6] = -(P01 + Q01) - (X00 + X11);
-        D[7] = (P11 + Q11) - (X11 + X11);
-        D[8] = (Q01 - P11) + (X11 - X10);
-        D[9] = (P11 + Q00) + (X10 + X10);
-        // ---- write out
-        constexpr int TRI[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
-        if (o.mode == KB_MODE_CONSISTENT) {                                                       // MaterialBase.py:58
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    Ke[4 * a + b] = D[TRI[a][b]] + (SZ[b] * (PA[b] == PA[a] ? alS[a] : alD[a]) + SE[b] * (QA[b] == QA[a] ? beS[a] : beD[a]));
-        } else {                                                             // np.dot(advection, W), a scalar     :170
-            double S = 0.0;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) S += SZ[a] * alS[a] + SE[a] * beS[a];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) Ke[4 * a + b] = D[TRI[a][b]] + S;
+                for (int gj = 0; gj < 2; ++gj) m[2 * gi + gj] = s[2 * gi + gj] * (Jey[gj] * Jzy[gi] + Jex[gj] * Jzx[gi]);
+            // Y_q[gi] = sum_gj h_q[gj] m[gi][gj];  Xm[p][q] = sum_gi h_p[gi] Y_q[gi]
+            const double Y0[2] = {HHI * m[0] + HLO * m[1], HHI * m[2] + HLO * m[3]};
+            const double Y1[2] = {HLO * m[0] + HHI * m[1], HLO * m[2] + HHI * m[3]};
+            const double X00 = HHI * Y0[0] + HLO * Y0[1], X01 = HHI * Y1[0] + HLO * Y1[1];
+            const double X10 = HLO * Y0[0] + HHI * Y0[1], X11 = HLO * Y1[0] + HHI * Y1[1];
+            D[0] = (P00 + Q00) - (X00 + X00);
+            D[1] = (Q01 - P00) + (X00 - X01);
+            D[2] = (X01 + X10) - (P01 + Q01);
+            D[3] = (P01 - Q00) + (X00 - X10);
+            D[4] = (P00 + Q11) + (X01 + X01);
+            D[5] = (P01 - Q11) + (X11 - X01);
+            D[6] = -(P01 + Q01) - (X00 + X11);
+            D[7] = (P11 + Q11) - (X11 + X11);
+            D[8] = (Q01 - P11) + (X11 - X10);
+            D[9] = (P11 + Q00) + (X10 + X10);
         }
     }
+    if (ok) quad4_writeout(D, alS, alD, beS, beD, o, Ke);
     // ---- source vector and mass: dV-weighted sums of products of the 1-D tables                       :154,159 / :63-67
-    const double dV[4] = {fabs(det4[0]), fabs(det4[1]), fabs(det4[2]), fabs(det4[3])};
     const double aq = o.area * o.q;
     const double B0[4] = {NHI * NHI, NHI * NLO, NLO * NLO, NLO * NHI};      // Bases[:, g=0]; other points permute it
     constexpr int PERM[4][4] = {{0, 1, 2, 3}, {1, 0, 3, 2}, {3, 2, 1, 0}, {2, 3, 0, 1}};

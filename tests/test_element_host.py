@@ -69,8 +69,12 @@ def _random_quads(seed, ne, kind):
     base = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
     for e in range(ne):
         A = np.eye(2) + 0.3 * rng.standard_normal((2, 2))
-        q = base @ A.T * rng.uniform(0.01, 3.0) + rng.standard_normal(2) + 0.12 * rng.standard_normal((4, 2))
-        if kind == "clockwise":
+        q = base @ A.T * rng.uniform(0.01, 3.0) + rng.standard_normal(2)
+        if not kind.startswith("affine"):
+            q = q + 0.12 * rng.standard_normal((4, 2))
+        elif e % 3 == 0:                               # axis-parallel rectangles (what Mesh.Rectangle generates)
+            q = base * np.array([rng.uniform(0.01, 2.0), rng.uniform(0.01, 2.0)]) + rng.standard_normal(2)
+        if kind in ("clockwise", "affine_cw"):
             q = q[[0, 3, 2, 1]]
         elif kind == "nonconvex":                      # pull node 2 through the diagonal: det changes sign inside
             q = base.copy(); q[2] = [0.3, 0.3] + 0.05 * rng.standard_normal(2)
@@ -79,7 +83,7 @@ def _random_quads(seed, ne, kind):
     return pts, el, vel
 
 
-@pytest.mark.parametrize("kind", ["ccw", "clockwise", "nonconvex"])
+@pytest.mark.parametrize("kind", ["ccw", "clockwise", "nonconvex", "affine", "affine_cw"])
 @pytest.mark.parametrize("mode,petrov", [("reference", False), ("reference", True), ("consistent", False),
                                          ("consistent", True)])
 def test_quad4_host_matches_oracle_random(host, kind, mode, petrov):
