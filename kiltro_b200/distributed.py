@@ -428,7 +428,7 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
                 (t_enq1 - t_enq0) / check_every * 1e6, (t_done - t_enq0) / check_every * 1e6), file=sys.stderr, flush=True)
         comm.allreduce(dr)                                     # ||r||^2 only when convergence is looked at
         rr = float(dr[0][0])                                   # host sync every check_every iterations
-        if not np.isfinite(rr):
+        if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
             break
         if rr <= tol2:
@@ -458,6 +458,7 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
                                      D.ptr(s.scratch), st()))
     comm.allreduce(d)
     rr, bb = float(d[0][0]), float(d[0][1])
+    rr0 = rr
     tol2 = rtol * rtol * bb
     for k in range(P):
         p[k].copy_(r[k]); sc[k]["rho"][0].copy_(d[k][0:1])
@@ -479,7 +480,7 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
             cur ^= 1
             it += 1
         rr = float(dr[0][0])
-        if not np.isfinite(rr):
+        if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
             break
         if rr <= tol2:
@@ -607,7 +608,7 @@ def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000
         rr = float(dr[0])
         if region.error():
             raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
-        if not np.isfinite(rr):
+        if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
             break
         if rr <= tol2:
