@@ -389,7 +389,7 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
             KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             configured = true;
         }
-        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, row_pat, pat_tab, vals, rowblk, x, y, dotw,
+        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), P_THREADS, bytes, s>>>(nblk, indptr, row_pat, pat_tab, vals, rowblk, x, y, dotw,
                                                                         partials, ticket, done, fin, dotw2, pwait);
         KB_LAUNCH_CHECK();
         return 0;

@@ -18,6 +18,26 @@ constexpr int P_STAGES = 4;                      // one stage more than spmv_tma
                                                  // the copy engine needs the same number of bytes in flight to cover DRAM
                                                  // latency (with 3 stages the kernel ran at 70 % instead of 77 % of DRAM peak)
 typedef int16_t pat_off_t;                       // offsets are stored in 16 bits (the builder checks that they fit)
+constexpr int P_CONSUMERS = 256;                 // 8 consumer warps = the rows of one ~2304-nnz row block (one row per thread).
+                                                 // More warps would only idle unless the row blocks grew with them, and 4
+                                                 // stages of larger blocks no longer fit two CTAs per SM.
+constexpr int P_THREADS = P_CONSUMERS + 32;      // + 1 producer warp
+
+__device__ __forceinline__ void pat_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(P_CONSUMERS) : "memory"); }
+// sum of one double per consumer thread (fixed order); result valid in thread 0.  red: 16 doubles.
+__device__ __forceinline__ double pat_consumer_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[w] = v;
+    pat_consumer_sync();
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < (P_CONSUMERS / 32) ? red[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    pat_consumer_sync();
+    return r;
+}
 
 struct __align__(128) StageP {
     double vals[T_VCAP];
@@ -31,7 +51,7 @@ constexpr size_t pat_smem_bytes() {
 }
 
 template <int DOTS, class Final>
-__global__ void __launch_bounds__(T_THREADS, 2)
+__global__ void __launch_bounds__(P_THREADS, 2)
 k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__restrict__ row_pat,
            const pat_off_t *__restrict__ pat_tab, const double *__restrict__ vals, const int32_t *__restrict__ rowblk,
            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
@@ -52,16 +72,16 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
     const int64_t b_end = nblk * (int64_t)(blockIdx.x + 1) / gridDim.x;
     const int nmine = (int)(b_end - b_begin);
 
-    for (int i = threadIdx.x; i < P_SLOTS * P_MAXLEN; i += T_THREADS) s_tab[i] = __ldg(pat_tab + i);
+    for (int i = threadIdx.x; i < P_SLOTS * P_MAXLEN; i += P_THREADS) s_tab[i] = __ldg(pat_tab + i);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], T_CONSUMERS / 32); }
+        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], P_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         kbpeer::wait_flags(pwait);
     }
     __syncthreads();
 
-    if (threadIdx.x >= T_CONSUMERS) {
+    if (threadIdx.x >= P_CONSUMERS) {
         // ------------------------------------------------------------------ producer warp (see spmv_tma.cuh)
         const int lane = threadIdx.x & 31;
         const uint64_t pol_stream = policy_evict_first();
@@ -121,7 +141,7 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
             StageP &st = stages[s];
             const StageMeta m = st.meta;
             const int jcut = m.slow ? 0 : m.pcut - m.pa;
-            for (int r = m.r0 + tid; r < m.r1; r += T_CONSUMERS) {
+            for (int r = m.r0 + tid; r < m.r1; r += P_CONSUMERS) {
                 double wv = 0.0, w2v = 0.0;
                 if (DOTS) wv = __ldcs(w + r);
                 if (DOTS == 2) w2v = __ldg(w2 + r);
@@ -166,9 +186,9 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
         }
         if (DOTS) {
-            d0 = consumer_sum(d0, red);
-            d1 = consumer_sum(d1, red);
-            if (DOTS == 2) { d2 = consumer_sum(d2, red); d3 = consumer_sum(d3, red); }
+            d0 = pat_consumer_sum(d0, red);
+            d1 = pat_consumer_sum(d1, red);
+            if (DOTS == 2) { d2 = pat_consumer_sum(d2, red); d3 = pat_consumer_sum(d3, red); }
             if (tid == 0) {
                 partials[blockIdx.x] = d0;
                 partials[gridDim.x + blockIdx.x] = d1;
@@ -177,18 +197,18 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
                 const unsigned int t = atomicInc(ticket, gridDim.x - 1);
                 *s_last = (t == gridDim.x - 1);
             }
-            consumer_sync();
+            pat_consumer_sync();
             if (*s_last) {
                 __threadfence();
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                for (int k = tid; k < (int)gridDim.x; k += T_CONSUMERS) {
+                for (int k = tid; k < (int)gridDim.x; k += P_CONSUMERS) {
                     a0 += __ldcg(partials + k);
                     a1 += __ldcg(partials + gridDim.x + k);
                     if (DOTS == 2) { a2 += __ldcg(partials + 2 * gridDim.x + k); a3 += __ldcg(partials + 3 * gridDim.x + k); }
                 }
-                a0 = consumer_sum(a0, red);
-                a1 = consumer_sum(a1, red);
-                if (DOTS == 2) { a2 = consumer_sum(a2, red); a3 = consumer_sum(a3, red); }
+                a0 = pat_consumer_sum(a0, red);
+                a1 = pat_consumer_sum(a1, red);
+                if (DOTS == 2) { a2 = pat_consumer_sum(a2, red); a3 = pat_consumer_sum(a3, red); }
                 if (tid == 0) fin(a0, a1, a2, a3);
             }
         }

@@ -130,3 +130,34 @@ def test_transient_heat_conservation_fullsize(big):
         assert abs(h5 - h0) <= 1e-9 * abs(h0), (theta, h0, h5, fs.solver_info)
         assert float(S[:, 1].min()) > 90.0 and float(S[:, 1].max()) < 160.0
         assert float((S[:, 1] - S[:, 0]).abs().max()) > 1e-3          # something did happen
+
+
+def test_next_row_operators_identities_fullsize(big):
+    """SURVEY 8(f) n2 / n3 at 16 M DOF through identities: the Robin matrix is h / (rho c_v) times the mass matrix
+    (K_e = h int N (x) N), its entries sum to h |Omega| and Flux_e to h T_inf |Omega|; the characteristic-Galerkin matrix
+    int (u.grad N)(x)(u.grad N) is symmetric, annihilates constants and, for a uniform velocity u, gives
+    x^T K_u x = |u|^2 |Omega| on the linear field x = (u . X)."""
+    K, mesh, fs, mat = big
+    nn = mesh.nnodes
+    form = K.HeatDiffusion(mesh)
+    M = K.Assemble(fs, form.function_spaces, form, mesh, mat, K.BoundaryCondition())[2]
+    bc = K.BoundaryCondition(); bc.applied_robin_convection = 7.5; bc.ground_robin_convection = 293.0
+    Kr, Fr = K.AssemblyRobinForces(fs, form.function_spaces[0], mesh, mat, bc)
+    assert float((Kr.data - (7.5 / (2.0 * 1.5)) * M.data).abs().max()) <= 1e-13 * float(Kr.data.abs().max())
+    assert abs(float(Kr.data.sum()) - 7.5) < 1e-9 and abs(float(Fr.sum()) - 7.5 * 293.0) < 1e-6
+    u = (3.0, -2.0)
+    vel = torch.zeros((nn, 2), dtype=torch.float64, device="cuda"); vel[:, 0] = u[0]; vel[:, 1] = u[1]
+    formu = K.HeatAdvectionDiffusion(mesh, velocity=vel)
+    Ku, Fu = K.AssembleCharacteristicGalerkin(formu.function_spaces, formu, mesh, mat, bc, fem_solver=fs)
+    ones = torch.ones(nn, dtype=torch.float64, device="cuda")
+    kmax = float(Ku.data.abs().max())
+    assert float(Ku.dot(ones).abs().max()) < 1e-11 * kmax
+    P = mesh.device_points()
+    x = u[0] * P[:, 0] + u[1] * P[:, 1]
+    assert abs(float(torch.dot(x, Ku.dot(x))) - (u[0] ** 2 + u[1] ** 2) ** 2) < 1e-8 * (u[0] ** 2 + u[1] ** 2) ** 2
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    a = torch.randn(nn, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(nn, dtype=torch.float64, device="cuda", generator=g)
+    assert abs(float(torch.dot(a, Ku.dot(b)) - torch.dot(b, Ku.dot(a)))) < 1e-9 * kmax * nn ** 0.5
+    # Flux_u = q area int u.grad N: sums to zero (sum_a grad N_a = 0)
+    assert abs(float(Fu.sum())) < 1e-9 * float(Fu.abs().max()) * nn ** 0.5
