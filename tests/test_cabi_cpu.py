@@ -55,6 +55,16 @@ def test_argument_validation_without_gpu(lib):
     from kiltro_b200 import _lib
     info = _lib.kb_solve_info()
     assert lib.kb_cg_solve(4, 4, None, None, None, None, None, 1e-8, 10, 1, None, 0, info, None) == -1
+    # entry points added with the template assembly, the row-pattern SpMV and the SURVEY 8(f) operators
+    mat = _lib.kb_material()
+    assert lib.kb_assemble_fused_tmpl(None, 4, None, mat, 0, 0, None, 1, None, None, None, None, None, None, None, None,
+                                      None, None, None) == -1
+    i3 = (ctypes.c_int64 * 3)()
+    assert lib.kb_tile_tmpl_build(4, 16, 1, None, None, None, None, None, None, None, None, None, None, i3, None) == -1
+    assert lib.kb_element_operator(2, 7, None, None, 1, None, 1.0, 0.0, None, None, None) == -1      # NULLs / unknown operator
+    assert lib.kb_axpby(4, 1.0, None, 1.0, None, None, None) == -1
+    assert lib.kb_make_row_patterns(4, None, None, None, None, None, None, None) == -1
+    assert lib.kb_spmv_dots(4, 4, None, None, None, None, None, None, None, None, None, None, None, None, None) == -1
 
 
 def test_host_side_size_queries(lib):
@@ -68,6 +78,9 @@ def test_host_side_size_queries(lib):
     assert lib.kb_tile_plan_sizes(4000 * 4000, 3999 * 3999, 4, 4000, 4000, sizes) == 0
     assert sizes[0] == 267 * 267 and sizes[3] == 1                 # 15 x 15 node patches
     assert lib.kb_tile_plan_sizes(1001, 1000, 2, 0, 0, sizes) == 0 and sizes[3] == 0 and sizes[0] == 5
+    t3 = (ctypes.c_int64 * 3)()
+    assert lib.kb_tile_tmpl_sizes(t3) == 0
+    assert t3[0] % 16 == 0 and 20_000 < t3[0] < 32_768 and t3[1] >= 9 and t3[2] >= 15    # one template fits shared memory
 
 
 def test_no_cpu_fallback():
