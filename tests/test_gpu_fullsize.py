@@ -161,3 +161,43 @@ def test_next_row_operators_identities_fullsize(big):
     assert abs(float(torch.dot(a, Ku.dot(b)) - torch.dot(b, Ku.dot(a)))) < 1e-9 * kmax * nn ** 0.5
     # Flux_u = q area int u.grad N: sums to zero (sum_a grad N_a = 0)
     assert abs(float(Fu.sum())) < 1e-9 * float(Fu.abs().max()) * nn ** 0.5
+
+
+def test_permuted_numbering_at_scale():
+    """The generic paths at scale (1 M DOF): the same mesh with RANDOMLY PERMUTED node numbers and shuffled elements has no
+    repeating tiles (generic fused kernel, per-(row, element) records from HBM), a band far beyond 16 bits and far more
+    than 256 row patterns (32-bit SpMV) -- and must give the permuted solution of the structured solve."""
+    import kiltro_b200 as K
+    n = 1000
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (1.0, 1.0), n - 1, n - 1)
+    nn = m.nnodes
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    h = 1.0 / (n - 1)
+    vel = torch.zeros((nn, 2), dtype=torch.float64, device="cuda"); vel[:, 0] = 0.45 * 2.0 / h
+    vel += 0.1 * vel[:, :1].abs().max() * torch.randn((nn, 2), dtype=torch.float64, device="cuda", generator=g)
+    flags = torch.full((nn, 1), float("nan"), dtype=torch.float64, device="cuda")
+    left = torch.arange(n, device="cuda") * n
+    flags[left, 0] = 100.0; flags[left + n - 1, 0] = 500.0
+    mat = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+
+    def solve(mesh, v, f):
+        bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: f)
+        solver = K.LinearSolver(linear_solver_type="bicgstab", tol=1e-11, check_every=50, maxiter=20000)
+        fs = K.FEMSolver(verbose=False)
+        sol = fs.Solve(formulation=K.HeatAdvectionDiffusion(mesh, velocity=v), mesh=mesh, material=mat,
+                       boundary_condition=bc, solver=solver)
+        assert solver.info["status"] == 0, solver.info
+        return sol.sol_device[:, 0, 0], fs
+
+    ref, fs0 = solve(m, vel, flags)
+    assert fs0.assembly_used == "fused_template"
+    perm = torch.randperm(nn, device="cuda", generator=g)          # new id of old node i = perm[i]
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(nn, device="cuda")
+    P2 = m.device_points()[inv].contiguous()                       # coordinates listed in the new numbering
+    el = perm[m.device_elements().long()]
+    el = el[torch.randperm(el.shape[0], device="cuda", generator=g)].contiguous()
+    m2 = K.Mesh(element_type="quad"); m2.set_arrays(P2, el)
+    got, fs2 = solve(m2, vel[inv].contiguous(), flags[inv].contiguous())
+    assert fs2.assembly_used in ("fused", "two_pass") and not fs2.sparsity.tile_plan.templated
+    err = float((got[perm] - ref).abs().max()) / 500.0
+    assert err < 1e-8, err
