@@ -764,3 +764,24 @@ def test_spmv_index_forms_bitwise(case):
     for mode in ("offset16", "index32"):
         assert out[mode][1] == out["pattern"][1], (mode, out[mode][1], out["pattern"][1])
         assert torch.equal(out[mode][0], out["pattern"][0]), mode
+
+
+def test_write_vtk_from_device_solution(tmp_path):
+    """a solution that lives on the device is streamed into the .vtu files (one per load increment)."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).parent))
+    from test_vtk_cpu import read_vtu
+    K = _K()
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (1.0, 0.5), 12, 7)
+    d = np.full((m.nnodes, 1), np.nan); d[m.points[:, 0] == 0.0] = 1.0; d[m.points[:, 0] == 1.0] = 3.0
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: d)
+    sol = K.FEMSolver(verbose=False, number_of_load_increments=2).Solve(
+        formulation=K.HeatDiffusion(m), mesh=m, material=K.FourierConduction(2, k=1.0, area=1.0, density=1.0, c_v=1.0),
+        boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    assert sol._sol_h is None and sol.sol_device is not None          # still on the device when the writer starts
+    files = sol.WriteVTK(str(tmp_path / "field.vtu"))
+    assert len(files) == 2
+    for i, f in enumerate(files):
+        v = read_vtu(f)
+        assert np.array_equal(v["T"], sol.sol[:, 0, i]) and np.array_equal(v["connectivity"], m.elements.ravel())
+        assert np.array_equal(v["points"][:, :2], m.points)
