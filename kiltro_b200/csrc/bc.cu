@@ -65,39 +65,103 @@ struct CntOut {
     __device__ void operator()(int64_t i, int ex, int) const { c[i] = ex; }
 };
 
+// Fill pass of the reduction, coalesced: a CTA takes FB_ROWS consecutive rows.  Phase 1 streams the rows' entries (K,
+// indices, the renumbering of every column) into shared memory with consecutive threads on consecutive entries; phase 2 is
+// one thread per row -- compaction in ascending column order, RHS elimination as a sequential sum over the fixed columns
+// (csr mat-vec order) -- entirely in shared memory; phase 3 streams the compacted block, which is contiguous in K_b, back
+// out.  Blocks whose entries do not fit FB_CAP walk their rows in global memory instead.  (A plain one-thread-per-row
+// kernel reads 72-byte row chunks with 72-byte lane strides: 2.4 ms at 16 M rows for ~0.6 ms worth of traffic.)
+constexpr int FB_ROWS = 256;
+constexpr int FB_CAP = 2560;
 template <bool MASS>
-__global__ void __launch_bounds__(256) k_reduced_fill(int64_t ndof, const int32_t *__restrict__ indptr,
-                                                      const int32_t *__restrict__ indices,
-                                                      const double *__restrict__ K, const double *__restrict__ M,
-                                                      const int32_t *__restrict__ renum,
-                                                      const double *__restrict__ applied, double load_factor,
-                                                      double *__restrict__ F, const int32_t *__restrict__ kb_indptr,
-                                                      int32_t *__restrict__ kb_indices, double *__restrict__ kb_data,
-                                                      double *__restrict__ mb_data, double *__restrict__ Fb) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ndof; i += stride) {
-        const int r = renum[i];
-        if (r < 0) continue;
-        int q = kb_indptr[r];
-        double s = 0.0;
-        for (int p = indptr[i], pe = indptr[i + 1]; p < pe; ++p) {
-            const int col = __ldg(indices + p);
-            const int rc = __ldg(renum + col);
-            const double v = K[p];
-            if (rc >= 0) {
-                kb_indices[q] = rc;
-                kb_data[q] = v;
-                if (MASS) mb_data[q] = M[p];
-                ++q;
-            } else {
-                const double td = __ldg(applied + (-1 - rc));
-                if (!(fabs(td) <= 1.0e-8))                                  // ~np.isclose(T_D, 0)        :182
-                    s = __dadd_rn(s, __dmul_rn(v, td));                     // csr mat-vec, ascending column
-            }
+__global__ void __launch_bounds__(FB_ROWS) k_reduced_fill_flat(int64_t ndof, const int32_t *__restrict__ indptr,
+                                                             const int32_t *__restrict__ indices,
+                                                             const double *__restrict__ K, const double *__restrict__ M,
+                                                             const int32_t *__restrict__ renum,
+                                                             const double *__restrict__ applied, double load_factor,
+                                                             double *__restrict__ F, const int32_t *__restrict__ kb_indptr,
+                                                             int32_t *__restrict__ kb_indices, double *__restrict__ kb_data,
+                                                             double *__restrict__ mb_data, double *__restrict__ Fb) {
+    extern __shared__ __align__(16) unsigned char fb_raw[];
+    double *s_v = reinterpret_cast<double *>(fb_raw);                      // [FB_CAP] staged K values
+    double *s_ov = s_v + FB_CAP;                                           // [FB_CAP] compacted K values
+    double *s_m = s_ov + FB_CAP;                                           // [FB_CAP] staged M values   (MASS)
+    double *s_om = s_m + (MASS ? FB_CAP : 0);                              // [FB_CAP] compacted M values (MASS)
+    int *s_rc = reinterpret_cast<int *>(s_om + (MASS ? FB_CAP : 0));       // [FB_CAP] renum of the column
+    int *s_oc = s_rc + FB_CAP;                                             // [FB_CAP] compacted reduced column
+    __shared__ int s_ip[FB_ROWS + 1];
+    __shared__ int s_qbase, s_qend;
+    const int tid = threadIdx.x;
+    const int64_t nblocks = (ndof + FB_ROWS - 1) / FB_ROWS;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t r0 = blk * FB_ROWS;
+        const int nr = (int)((ndof - r0) < FB_ROWS ? (ndof - r0) : FB_ROWS);
+        for (int i = tid; i <= nr; i += FB_ROWS) s_ip[i] = indptr[r0 + i];
+        if (tid == 0) { s_qbase = -1; s_qend = -1; }
+        __syncthreads();
+        const int p0 = s_ip[0], np = s_ip[nr] - p0;
+        const int r = tid < nr ? renum[r0 + tid] : -1;                     // reduced index of this thread's row (or fixed)
+        const int q = r >= 0 ? kb_indptr[r] : 0;
+        if (r >= 0) {                                                      // first / last free row of the block: output extent
+            atomicMin(reinterpret_cast<unsigned int *>(&s_qbase), (unsigned int)q);      // -1 = 0xffffffff: any q is smaller
+            atomicMax(&s_qend, kb_indptr[r + 1]);
         }
-        const double f = __dadd_rn(F[i], -__dmul_rn(s, load_factor));       // F[in] - (K[in,out] T_D)*LoadFactor  :183-184
-        F[i] = f;
-        Fb[r] = f;                                                          // :190
+        if (np <= FB_CAP) {
+            for (int i = tid; i < np; i += FB_ROWS) {
+                s_v[i] = K[p0 + i];
+                if (MASS) s_m[i] = M[p0 + i];
+                s_rc[i] = __ldg(renum + __ldg(indices + p0 + i));
+            }
+            __syncthreads();
+            if (r >= 0) {
+                int o = q - s_qbase;
+                double s = 0.0;
+                for (int i = s_ip[tid] - p0, ie = s_ip[tid + 1] - p0; i < ie; ++i) {
+                    const int rc = s_rc[i];
+                    const double v = s_v[i];
+                    if (rc >= 0) {
+                        s_oc[o] = rc; s_ov[o] = v;
+                        if (MASS) s_om[o] = s_m[i];
+                        ++o;
+                    } else {
+                        const double td = __ldg(applied + (-1 - rc));
+                        if (!(fabs(td) <= 1.0e-8))                                  // ~np.isclose(T_D, 0)        :182
+                            s = __dadd_rn(s, __dmul_rn(v, td));                     // csr mat-vec, ascending column
+                    }
+                }
+                const double f = __dadd_rn(F[r0 + tid], -__dmul_rn(s, load_factor));   // :183-184
+                F[r0 + tid] = f;
+                Fb[r] = f;                                                          // :190
+            }
+            __syncthreads();
+            if (s_qend > s_qbase) {
+                const int qb = s_qbase, no = s_qend - qb;
+                for (int i = tid; i < no; i += FB_ROWS) {
+                    kb_indices[qb + i] = s_oc[i];
+                    kb_data[qb + i] = s_ov[i];
+                    if (MASS) mb_data[qb + i] = s_om[i];
+                }
+            }
+        } else if (r >= 0) {                                                // oversized block: per-row walk in global memory
+            int o = q;
+            double s = 0.0;
+            for (int p = s_ip[tid], pe = s_ip[tid + 1]; p < pe; ++p) {
+                const int rc = __ldg(renum + __ldg(indices + p));
+                const double v = K[p];
+                if (rc >= 0) {
+                    kb_indices[o] = rc; kb_data[o] = v;
+                    if (MASS) mb_data[o] = M[p];
+                    ++o;
+                } else {
+                    const double td = __ldg(applied + (-1 - rc));
+                    if (!(fabs(td) <= 1.0e-8)) s = __dadd_rn(s, __dmul_rn(v, td));
+                }
+            }
+            const double f = __dadd_rn(F[r0 + tid], -__dmul_rn(s, load_factor));
+            F[r0 + tid] = f;
+            Fb[r] = f;
+        }
+        __syncthreads();
     }
 }
 
@@ -169,10 +233,20 @@ extern "C" int kb_apply_dirichlet_reduce(int64_t ndof, const int32_t *d_indptr, 
     KB_CUDA(cudaMemcpyAsync(&nnzb, ws + kbscan::num_tiles(n_free + 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     KB_CUDA(cudaFreeAsync(ws, s));
     if (ndof > 0) {
-        if (d_M) k_reduced_fill<true><<<g, 256, 0, s>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum, d_applied, load_factor,
-                                                        d_F, d_Kb_indptr, d_Kb_indices, d_Kb_data, d_Mb_data, d_Fb);
-        else k_reduced_fill<false><<<g, 256, 0, s>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum, d_applied, load_factor,
-                                                     d_F, d_Kb_indptr, d_Kb_indices, d_Kb_data, d_Mb_data, d_Fb);
+        static bool configured = false;
+        constexpr size_t bytes_m = (size_t)FB_CAP * (4 * 8 + 2 * 4), bytes_s = (size_t)FB_CAP * (2 * 8 + 2 * 4);
+        if (!configured) {
+            KB_CUDA(cudaFuncSetAttribute(k_reduced_fill_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_m));
+            KB_CUDA(cudaFuncSetAttribute(k_reduced_fill_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_s));
+            configured = true;
+        }
+        const int gf = kb_grid(kb_cdiv(ndof, FB_ROWS) * FB_ROWS, FB_ROWS, 4);
+        if (d_M) k_reduced_fill_flat<true><<<gf, FB_ROWS, bytes_m, s>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum, d_applied,
+                                                                       load_factor, d_F, d_Kb_indptr, d_Kb_indices, d_Kb_data,
+                                                                       d_Mb_data, d_Fb);
+        else k_reduced_fill_flat<false><<<gf, FB_ROWS, bytes_s, s>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum, d_applied,
+                                                                    load_factor, d_F, d_Kb_indptr, d_Kb_indices, d_Kb_data,
+                                                                    d_Mb_data, d_Fb);
         KB_LAUNCH_CHECK();
     }
     KB_CUDA(cudaStreamSynchronize(s));

@@ -120,26 +120,57 @@ __global__ void __launch_bounds__(256) k_diag_scale(int64_t n, const int32_t *__
 }
 
 // vals_hat[p] = vals[p] * scale[col]  (MODE 0)   or   scale[row] * vals[p] * scale[col]  (MODE 1)
+// Coalesced: a CTA takes 256 consecutive rows, the row of every entry is spread through shared memory by one thread per
+// row, then consecutive threads walk consecutive entries (a one-thread-per-row walk reads 72-byte chunks at 72-byte lane
+// strides: 1.7 ms at 16 M rows).  Blocks with more than SM_CAP entries walk their rows directly.
+constexpr int SM_ROWS = 256, SM_CAP = 4096;
 template <int MODE>
-__global__ void __launch_bounds__(256) k_scale_matrix(int64_t n, const int32_t *__restrict__ indptr,
-                                                      const int32_t *__restrict__ indices,
-                                                      const double *__restrict__ vals,
-                                                      const double *__restrict__ scale, double *__restrict__ out,
-                                                      int16_t *__restrict__ cols16 = nullptr,
-                                                      int *__restrict__ bandflag = nullptr) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(SM_ROWS) k_scale_matrix(int64_t n, const int32_t *__restrict__ indptr,
+                                                          const int32_t *__restrict__ indices,
+                                                          const double *__restrict__ vals,
+                                                          const double *__restrict__ scale, double *__restrict__ out,
+                                                          int16_t *__restrict__ cols16 = nullptr,
+                                                          int *__restrict__ bandflag = nullptr) {
+    __shared__ int s_ip[SM_ROWS + 1];
+    __shared__ uint8_t s_row[SM_CAP];                      // row (relative to the block) of every staged entry
+    const int tid = threadIdx.x;
     bool wide = false;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double si = MODE == 1 ? scale[i] : 1.0;
-        for (int p = indptr[i], pe = indptr[i + 1]; p < pe; ++p) {
-            const int col = indices[p];
-            out[p] = si * vals[p] * __ldg(scale + col);
-            if (cols16 != nullptr) {
-                const int d = col - (int)i;
-                if (d < -32768 || d > 32767) wide = true;
-                cols16[p] = (int16_t)d;
+    const int64_t nblocks = (n + SM_ROWS - 1) / SM_ROWS;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t r0 = blk * SM_ROWS;
+        const int nr = (int)((n - r0) < SM_ROWS ? (n - r0) : SM_ROWS);
+        for (int i = tid; i <= nr; i += SM_ROWS) s_ip[i] = indptr[r0 + i];
+        __syncthreads();
+        const int p0 = s_ip[0], np = s_ip[nr] - p0;
+        if (np <= SM_CAP) {
+            if (tid < nr)
+                for (int i = s_ip[tid] - p0, ie = s_ip[tid + 1] - p0; i < ie; ++i) s_row[i] = (uint8_t)tid;
+            __syncthreads();
+            for (int i = tid; i < np; i += SM_ROWS) {
+                const int64_t row = r0 + s_row[i];
+                const int col = indices[p0 + i];
+                const double si = MODE == 1 ? __ldg(scale + row) : 1.0;
+                out[p0 + i] = si * vals[p0 + i] * __ldg(scale + col);
+                if (cols16 != nullptr) {
+                    const int d = col - (int)row;
+                    if (d < -32768 || d > 32767) wide = true;
+                    cols16[p0 + i] = (int16_t)d;
+                }
+            }
+        } else if (tid < nr) {
+            const int64_t i = r0 + tid;
+            const double si = MODE == 1 ? scale[i] : 1.0;
+            for (int p = s_ip[tid], pe = s_ip[tid + 1]; p < pe; ++p) {
+                const int col = indices[p];
+                out[p] = si * vals[p] * __ldg(scale + col);
+                if (cols16 != nullptr) {
+                    const int d = col - (int)i;
+                    if (d < -32768 || d > 32767) wide = true;
+                    cols16[p] = (int16_t)d;
+                }
             }
         }
+        __syncthreads();
     }
     if (wide) *bandflag = 1;          // benign race: every writer stores the same value
 }
@@ -577,7 +608,7 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
         k_diag_scale<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale);
         KB_LAUNCH_CHECK();
         KB_CUDA(cudaMemsetAsync(w.bandflag, 0, sizeof(int) * 4, s));
-        k_scale_matrix<METHOD == 0 ? 1 : 0><<<g, 256, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat,
+        k_scale_matrix<METHOD == 0 ? 1 : 0><<<kb_grid(n, SM_ROWS, 8), SM_ROWS, 0, s>>>(n, indptr, indices, vals, w.scale, w.vals_hat,
                                                              g_force_idx32 ? nullptr : w.cols16, w.bandflag);
         KB_LAUNCH_CHECK();
         if (!g_force_idx32 && !g_no_patterns) {                // row-pattern dictionary (bandflag[1] = not expressible)
