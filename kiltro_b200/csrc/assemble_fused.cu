@@ -21,23 +21,15 @@
 // the tile rim), the plan (4 B per (row, element) pair + 12 B per row) and one write of K.data; `indices` is not read.
 #include "element.cuh"
 #include "tileplan.cuh"
+#include "cpasync.cuh"
 
 using namespace kbel;
 using namespace kbtile;
+using namespace kbasync;
 
 ElemOpts kb_make_opts(const kb_material *m, int mode, int petrov, int want_mass);   // element.cu
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int NDIM> struct ElemIO;
 template <> struct ElemIO<2> {

@@ -13,20 +13,16 @@
 // No atomics, deterministic; K equals the generic kernel's K bit for bit.
 #include "element.cuh"
 #include "tileplan.cuh"
+#include "cpasync.cuh"
 
 using namespace kbel;
 using namespace kbtile;
+using namespace kbasync;
 
 ElemOpts kb_make_opts(const kb_material *m, int mode, int petrov, int want_mass);   // element.cu
 
 namespace {
 
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));

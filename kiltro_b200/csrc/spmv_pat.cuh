@@ -23,21 +23,7 @@ constexpr int P_CONSUMERS = 256;                 // 8 consumer warps = the rows 
                                                  // stages of larger blocks no longer fit two CTAs per SM.
 constexpr int P_THREADS = P_CONSUMERS + 32;      // + 1 producer warp
 
-__device__ __forceinline__ void pat_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(P_CONSUMERS) : "memory"); }
-// sum of one double per consumer thread (fixed order); result valid in thread 0.  red: 16 doubles.
-__device__ __forceinline__ double pat_consumer_sum(double v, double *red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    v = warp_sum(v);
-    if (lane == 0) red[w] = v;
-    pat_consumer_sync();
-    double r = 0.0;
-    if (w == 0) {
-        r = lane < (P_CONSUMERS / 32) ? red[lane] : 0.0;
-        r = warp_sum(r);
-    }
-    pat_consumer_sync();
-    return r;
-}
+static_assert(P_CONSUMERS == T_CONSUMERS, "consumer_sync / consumer_sum of spmv_tma.cuh are reused");
 
 struct __align__(128) StageP {
     double vals[T_VCAP];
@@ -186,9 +172,9 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
         }
         if (DOTS) {
-            d0 = pat_consumer_sum(d0, red);
-            d1 = pat_consumer_sum(d1, red);
-            if (DOTS == 2) { d2 = pat_consumer_sum(d2, red); d3 = pat_consumer_sum(d3, red); }
+            d0 = consumer_sum(d0, red);
+            d1 = consumer_sum(d1, red);
+            if (DOTS == 2) { d2 = consumer_sum(d2, red); d3 = consumer_sum(d3, red); }
             if (tid == 0) {
                 partials[blockIdx.x] = d0;
                 partials[gridDim.x + blockIdx.x] = d1;
@@ -197,7 +183,7 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
                 const unsigned int t = atomicInc(ticket, gridDim.x - 1);
                 *s_last = (t == gridDim.x - 1);
             }
-            pat_consumer_sync();
+            consumer_sync();
             if (*s_last) {
                 __threadfence();
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -206,9 +192,9 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
                     a1 += __ldcg(partials + gridDim.x + k);
                     if (DOTS == 2) { a2 += __ldcg(partials + 2 * gridDim.x + k); a3 += __ldcg(partials + 3 * gridDim.x + k); }
                 }
-                a0 = pat_consumer_sum(a0, red);
-                a1 = pat_consumer_sum(a1, red);
-                if (DOTS == 2) { a2 = pat_consumer_sum(a2, red); a3 = pat_consumer_sum(a3, red); }
+                a0 = consumer_sum(a0, red);
+                a1 = consumer_sum(a1, red);
+                if (DOTS == 2) { a2 = consumer_sum(a2, red); a3 = consumer_sum(a3, red); }
                 if (tid == 0) fin(a0, a1, a2, a3);
             }
         }
