@@ -373,7 +373,32 @@ def _jacobi_scale(systems, comm, mats, mode):
 
 
 # ------------------------------------------------------------------------------------------------------ Krylov loops
-def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
+class _BestIterate(object):
+    """Copy of the iterate with the smallest recurrence residual seen at a convergence check (one vector copy every
+    check_every iterations).  The partitioned loops look at the residual only then, so a breakdown is noticed up to
+    check_every iterations late, on an iterate that may already be wrecked: the loops hand back this copy instead and
+    solve_steady restarts from it (the single-GPU driver freezes the iterate on device before the bad update).  The
+    residual norms are all-reduced, so every rank takes the same decisions."""
+
+    def __init__(self, x, rr, enabled=True):
+        self.x = [xk.clone() for xk in x] if enabled else None
+        self.rr = rr
+
+    def offer(self, x, rr):
+        if self.x is not None and rr < self.rr:
+            for keep, xk in zip(self.x, x):
+                keep.copy_(xk)
+            self.rr = rr
+
+    def restore(self, x):
+        if self.x is None:
+            return float("nan")
+        for keep, xk in zip(self.x, x):
+            xk.copy_(keep)
+        return self.rr
+
+
+def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50, checkpoint=True):
     """Unpreconditioned BiCGSTAB on the (already Jacobi-scaled) partitioned operator, in the merged-update form of the
     single-GPU solver (csrc/krylov.cu): two all-reduces per iteration (after each SpMV; 2 and 4 doubles), the
     residual norm is reduced only when convergence is checked.  b, x: full local vectors per part (x: initial guess in,
@@ -402,6 +427,7 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
     it, rr, status = 0, rr0, 0
     if not (rr0 > tol2):
         return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    keep = _BestIterate(x, rr0, checkpoint)
     import os, time
     dbg = os.environ.get("KB_DIST_DEBUG") == "1" and comm.rank == 0
     while it < maxiter:
@@ -430,7 +456,9 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
         rr = float(dr[0][0])                                   # host sync every check_every iterations
         if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
+            rr = keep.restore(x)                               # the caller restarts from the best checked iterate
             break
+        keep.offer(x, rr)
         if rr <= tol2:
             break
     else:
@@ -440,7 +468,7 @@ def dist_bicgstab(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_ev
     return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
 
 
-def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
+def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50, checkpoint=True):
     """CG on the (already symmetrically Jacobi-scaled) partitioned operator."""
     parts = [s.part for s in systems]
     P = len(systems)
@@ -465,6 +493,7 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
     it, status = 0, 0
     if not (rr > tol2):
         return {"iterations": 0, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
+    keep = _BestIterate(x, rr0, checkpoint)
     while it < maxiter:
         for _ in range(min(check_every, maxiter - it)):
             spmv_overlapped(systems, comm, Ahat, p, q, p, None, d)
@@ -482,7 +511,9 @@ def dist_cg(systems, comm, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50
         rr = float(dr[0][0])
         if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
+            rr = keep.restore(x)
             break
+        keep.offer(x, rr)
         if rr <= tol2:
             break
     else:
@@ -583,6 +614,7 @@ def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000
     comm.halo_exchange([part], [p])
     torch.cuda.synchronize(); comm.barrier()            # every rank's setup is complete before peers start writing
     it, rr, status, first = 0, rr0, 0, True
+    keep = _BestIterate([x], rr0)
     A = (D.ptr(sysm.indices), D.ptr(Ahat), D.ptr(sysm.rowblk), D.ptr(sysm.cols16))
     while it < maxiter:
         for _ in range(min(check_every, maxiter - it)):
@@ -610,7 +642,9 @@ def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000
             raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
         if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
             status = _lib.KB_EBREAKDOWN
+            rr = keep.restore([x])
             break
+        keep.offer([x], rr)
         if rr <= tol2:
             break
     else:
@@ -622,10 +656,28 @@ def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000
 
 
 # ------------------------------------------------------------------------------------------------------ drivers
-def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto", exchange="nccl"):
+def _true_residual(systems, comm, Ahat, b, x):
+    """(||b - A x||^2, ||b||^2) of the partitioned system: one halo exchange, SpMV and reduction."""
+    comm.halo_exchange([s.part for s in systems], x)
+    dres = [D.zeros(2) for _ in systems]
+    for k, s in enumerate(systems):
+        q = D.zeros(s.part.n_loc)
+        s.spmv(Ahat[k], x[k], q)
+        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(q), s.own_ptr(q), D.ptr(dres[k]),
+                                     D.ptr(s.scratch), D.stream_ptr()))
+    comm.allreduce(dres)
+    return float(dres[0][0]), float(dres[0][1])
+
+
+def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto", exchange="nccl",
+                 max_restarts=16, cycle_iterations=None):
     """Partitioned steady solve.  Returns (list of owned-solution tensors (n_own,), info).
     exchange: "nccl" (halo rows and dot products through torch.distributed) or "peer" (BiCGSTAB only, one part per process:
-    the kernels exchange them through NVLink peer memory, no collective inside the iteration)."""
+    the kernels exchange them through NVLink peer memory, no collective inside the iteration).
+    Like the single-GPU driver (csrc/krylov.cu), the iterate is judged by its TRUE residual and the Krylov loop is
+    restarted from it (<= max_restarts times, maxiter iterations in total) when the recurrence broke down / diverged
+    -- from the best checked iterate, see _BestIterate -- or "converged" on an iterate whose true residual does not
+    confirm it.  cycle_iterations caps one cycle (restarted BiCGSTAB/CG; tests use it to exercise the restart path)."""
     mats = [_masked(s, 1.0, 0.0, 1) for s in systems]
     sym = all(s.symmetric for s in systems) if method == "auto" else (method == "cg")
     mode = 1 if sym else 0
@@ -637,30 +689,48 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if mode == 1:
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(s.b), D.ptr(sc), D.ptr(bb), D.stream_ptr()))
         b.append(bb); x.append(D.zeros(s.part.n_loc))
-    if exchange == "peer" and not sym and len(systems) == 1 and isinstance(comm, DistComm) and comm.world > 1:
-        s0 = systems[0]
-        if getattr(s0, "peer_region", None) is None:
-            s0.peer_region = PeerRegion(s0.part, comm.dist)
-        info = dist_bicgstab_peer(s0, comm, s0.peer_region, Ahat[0], b[0], x[0], rtol, maxiter, check_every)
-        info["exchange"] = "peer"
-    else:
-        info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, maxiter, check_every)
-        info["exchange"] = "nccl" if isinstance(comm, DistComm) else "local"
+    peer = exchange == "peer" and not sym and len(systems) == 1 and isinstance(comm, DistComm) and comm.world > 1
+    if peer and getattr(systems[0], "peer_region", None) is None:
+        systems[0].peer_region = PeerRegion(systems[0].part, comm.dist)
+    info = {"iterations": 0, "status": _lib.KB_ENOTCONV, "restarts": 0}
+    tol2_factor = rtol * rtol
+    prev_true = float("inf")
+    rr_true, bb_true = float("nan"), 0.0
+    for cycle in range(max_restarts + 1):
+        left = maxiter - info["iterations"]
+        if left <= 0:
+            break
+        budget = left if cycle_iterations is None else min(left, cycle_iterations)
+        if peer:
+            s0 = systems[0]
+            c = dist_bicgstab_peer(s0, comm, s0.peer_region, Ahat[0], b[0], x[0], rtol, budget, check_every)
+        else:
+            c = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, budget, check_every)
+        info["iterations"] += c["iterations"]
+        info["relative_residual"] = c["relative_residual"]
+        info["status"] = c["status"]
+        info["restarts"] = cycle
+        rr_true, bb_true = _true_residual(systems, comm, Ahat, b, x)
+        if not np.isfinite(rr_true):
+            info["status"] = _lib.KB_EBREAKDOWN           # nothing sane to restart from
+            break
+        if rr_true <= tol2_factor * bb_true:
+            info["status"] = 0
+            break
+        # attainable accuracy: the recurrence converged, the true residual stalls within 1e3 (in norm) of the tolerance
+        if c["status"] == 0 and not (rr_true < 0.25 * prev_true) and rr_true <= 1.0e6 * tol2_factor * bb_true:
+            break
+        if c["status"] == _lib.KB_ENOTCONV and cycle_iterations is None:
+            break                                          # maxiter exhausted
+        prev_true = rr_true
+    info["exchange"] = "peer" if peer else ("nccl" if isinstance(comm, DistComm) else "local")
     info["method"] = "cg" if sym else "bicgstab"
-    # the iterate is judged by its TRUE residual, like the single-GPU driver (csrc/krylov.cu): one more halo exchange,
-    # SpMV and reduction; a recurrence that "converged" on a wrecked iterate is reported as not converged
-    parts = [s.part for s in systems]
-    comm.halo_exchange(parts, x)
-    dres = [D.zeros(2) for _ in systems]
-    for k, s in enumerate(systems):
-        q = D.zeros(s.part.n_loc)
-        s.spmv(Ahat[k], x[k], q)
-        _lib.check(s.lib.kb_residual(s.part.n_own, s.own_ptr(b[k]), s.own_ptr(q), s.own_ptr(q), D.ptr(dres[k]),
-                                     D.ptr(s.scratch), D.stream_ptr()))
-    comm.allreduce(dres)
-    rr_true, bb_true = float(dres[0][0]), float(dres[0][1])
     info["true_relative_residual"] = (rr_true / bb_true) ** 0.5 if bb_true > 0 else 0.0
-    if info["status"] == 0 and not (rr_true <= 1.0e6 * rtol * rtol * bb_true):
+    # same verdict rules as the single-GPU driver: a true residual within 10x of the tolerance counts as converged,
+    # success is never reported on an iterate whose true residual is more than 1e3 (in norm) above it
+    if info["status"] != 0 and rr_true <= 100.0 * tol2_factor * bb_true:
+        info["status"] = 0
+    if info["status"] == 0 and bb_true > 0 and not (rr_true <= 1.0e6 * tol2_factor * bb_true):
         info["status"] = _lib.KB_ENOTCONV if np.isfinite(rr_true) else _lib.KB_EBREAKDOWN
     sols = []
     for s, sc, xh in zip(systems, scales, x):
@@ -692,7 +762,8 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
             torch.add(kt[k], s.Fm, out=rhs[k])
             if mode == 1:
                 _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(rhs[k]), D.ptr(scales[k]), D.ptr(rhs[k]), D.stream_ptr()))
-        info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, rhs, yh, rtol, maxiter, check_every)
+        info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, rhs, yh, rtol, maxiter, check_every,
+                                                       checkpoint=False)   # short inner solves: no restart
         total += info["iterations"]; worst = max(worst, info["relative_residual"])
         for k, s in enumerate(systems):
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(yh[k]), D.ptr(scales[k]), D.ptr(kt[k]), D.stream_ptr()))   # y = D^-1 yhat

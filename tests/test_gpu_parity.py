@@ -512,6 +512,43 @@ def test_partitioned_steady_matches_single_gpu(world, sym, nx):
     assert rel_l2(got, ref.sol.ravel()) < SOL_TOL, (info, solver.info)
 
 
+@pytest.mark.parametrize("sym", [False, True])
+def test_partitioned_steady_restart_cycles(sym):
+    """Restart path of the partitioned driver: cycles capped at 40 iterations (restarted BiCGSTAB / CG from the true
+    residual) must reach the same solution as the single-GPU solve."""
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(44, 37, 3, False, sym)
+    sols, info = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10, cycle_iterations=40, max_restarts=400)
+    assert info["status"] == 0 and info["restarts"] >= 2, info
+    assert info["true_relative_residual"] <= 1e-12, info
+    ref = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc,
+                                           solver=K.LinearSolver(tol=1e-13))
+    assert rel_l2(torch.cat(sols).cpu().numpy(), ref.sol.ravel()) < SOL_TOL, info
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_partitioned_steady_recovers_from_breakdown(sym):
+    """A non-finite dot product in the middle of a cycle (injected once into the reduction) wrecks the iterate; the
+    loop must hand back the best checked iterate and the driver must restart from it and still converge."""
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(44, 37, 2, False, sym)
+
+    class FaultyComm(KD.LocalComm):
+        calls = 0
+
+        def allreduce(self, outs):
+            KD.LocalComm.allreduce(self, outs)
+            FaultyComm.calls += 1
+            if FaultyComm.calls == 36:                      # inside the second batch of 10 iterations
+                for o in outs:
+                    o.fill_(float("nan"))
+
+    sols, info = KD.solve_steady(systems, FaultyComm(2), rtol=1e-13, check_every=10)
+    assert FaultyComm.calls > 36
+    assert info["status"] == 0 and info["restarts"] >= 1, info
+    ref = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc,
+                                           solver=K.LinearSolver(tol=1e-13))
+    assert rel_l2(torch.cat(sols).cpu().numpy(), ref.sol.ravel()) < SOL_TOL, info
+
+
 @pytest.mark.parametrize("theta", [0.0, 0.5])
 def test_partitioned_transient_matches_single_gpu(theta):
     K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(30, 23, 3, True)
