@@ -287,10 +287,33 @@ def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, 
     sysm = LocalSystem(part)
     sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material = mesh, form, bc, fs, material
     sysm.transient, sysm.initial_fn = transient, initial_fn
+    sysm.velocity, sysm.flags = vel, flags
     sysm.symmetric = bool(form.is_symmetric)
     sysm.rowblk = None
     reassemble(sysm)
     return sysm
+
+
+def host_inputs(sysm):
+    """Pinned host copies of the rank's inputs in the reference's array formats (float64 points / velocity / flags, int64
+    connectivity): what a caller holding NumPy-side data would hand over.  Returns (points, elements, velocity, flags)."""
+    pin = lambda t: t.cpu().pin_memory()
+    return (pin(sysm.mesh.device_points()), pin(sysm.mesh.device_elements().to(torch.int64)),
+            pin(sysm.velocity) if sysm.velocity is not None else None, pin(sysm.flags))
+
+
+def refresh_inputs_from_host(sysm, h_points, h_elements, h_velocity, h_flags):
+    """Host -> device copy of every input of the rank's numeric phase into the buffers the cached symbolic phase refers
+    to (connectivity narrowed int64 -> int32 on device, like Mesh.set_arrays); follow with reassemble().  Returns the
+    number of bytes copied."""
+    n = 0
+    sysm.mesh.device_points().copy_(h_points, non_blocking=True); n += h_points.numel() * 8
+    el64 = h_elements.to("cuda", non_blocking=True); n += h_elements.numel() * 8
+    sysm.mesh.device_elements().copy_(el64)
+    if h_velocity is not None:
+        sysm.velocity.copy_(h_velocity, non_blocking=True); n += h_velocity.numel() * 8
+    sysm.flags.copy_(h_flags, non_blocking=True); n += h_flags.numel() * 8
+    return n
 
 
 def reassemble(sysm):
