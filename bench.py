@@ -298,6 +298,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo rows / dot products through NVLink peer memory written by the kernels (default) or NCCL")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (N = 1), so "
+                    "that `ncu --profile-from-start off` lists exactly the launches of the timed region")
     ap.add_argument("--idx32", action="store_true", help="keep 32-bit column indices in the solver's SpMV (default: 16-bit "
                     "offsets when the matrix band fits)")
     args = ap.parse_args()
@@ -360,6 +362,8 @@ def main():
     _lib.check(lib.kb_profile_spmv_begin(8))
     barrier()
     launches0 = lib.kb_launch_count()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     phase = {"assemble_ms": 0.0, "bc_ms": 0.0, "solve_ms": 0.0}
     for _ in range(args.steps):
@@ -368,6 +372,8 @@ def main():
             phase[k] += fs.timings[k]
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = lib.kb_launch_count() - launches0
     ns, tot = _lib.I64(0), _lib.F64(0.0)
     lib.kb_profile_spmv_end(ns, tot)
