@@ -204,6 +204,7 @@ int64_t kb_spmv_num_blocks(int64_t nnz);
 void kb_spmv_force_simple(int on);   /* development switch: 1 = use the one-shot (non-TMA) SpMV kernel */
 void kb_spmv_force_idx32(int on);    /* development switch: 1 = keep 32-bit column indices inside the solvers */
 void kb_spmv_force_no_patterns(int on); /* development switch: 1 = no row-pattern form (csrc/spmv_pat.cuh) in the solvers */
+void kb_set_pdl(int on);             /* development switch: 0 = no programmatic dependent launch in the Krylov loops (default 1) */
 int kb_profile_spmv_begin(int every);
 int kb_profile_spmv_end(int64_t *h_samples, double *h_total_ms);
 int kb_spmv_partition(int64_t nrows, int64_t nnz, const int32_t *d_indptr, int32_t *d_rowblk, void *stream);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "kb_spmv_num_blocks": (I64, [I64]),
     "kb_spmv_force_simple": (None, [I32]),
     "kb_spmv_force_idx32": (None, [I32]),
+    "kb_set_pdl": (None, [I32]),
     "kb_spmv_force_no_patterns": (None, [I32]),
     "kb_profile_spmv_begin": (I32, [I32]),
     "kb_profile_spmv_end": (I32, [ctypes.POINTER(I64), ctypes.POINTER(F64)]),

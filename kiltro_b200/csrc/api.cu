@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 int64_t g_kb_launches = 0;
+int g_kb_pdl = 1;                      // programmatic dependent launch inside the Krylov loops (kb_set_pdl)
 
 int kb_num_sms() {
     static int sms = 0;
@@ -20,6 +21,7 @@ int kb_version(void) { return 100; }
 
 int64_t kb_launch_count(void) { return g_kb_launches; }
 void kb_launch_count_reset(void) { g_kb_launches = 0; }
+void kb_set_pdl(int on) { g_kb_pdl = on ? 1 : 0; }
 
 const char *kb_error_string(int code) {
     switch (code) {

@@ -25,6 +25,29 @@ extern int64_t g_kb_launches;          // api.cu
 
 static inline int64_t kb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with kb_launch_pdl may become resident while the previous
+// kernel of the stream is still draining; everything it does before kb_pdl_wait() (shared-memory set-up, loads of data
+// the previous kernel does not write) overlaps that tail and the launch latency.  kb_pdl_wait() returns when the
+// previous kernel has completed and its writes are visible; without the launch attribute it is a no-op.  A kernel
+// must execute it before its first access to anything a predecessor reads or writes, and before any early return
+// (its own successor is released only when every CTA has passed the wait or exited).
+#ifdef __CUDACC__
+__device__ __forceinline__ void kb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_kb_pdl;                   // api.cu: 1 (default) = the Krylov loops launch their kernels with the attribute
+template <class... KArgs, class... Args>
+static inline cudaError_t kb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (pdl && g_kb_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // grid size for a grid-stride kernel: a multiple of the SM count, capped by the work available
 int kb_num_sms();                      // api.cu (cached)
 static inline int kb_grid(int64_t work_items, int threads, int ctas_per_sm) {

@@ -229,6 +229,7 @@ template <int DOTS, class Body, class Final>
 __global__ void __launch_bounds__(256) k_vec4(int64_t n, Body body, double *__restrict__ partials,
                                               unsigned int *__restrict__ ticket, const int *__restrict__ done,
                                               Final fin) {
+    kb_pdl_wait();                                          // scalars, vectors and `done` come from the previous kernel
     if (done != nullptr && *done != 0) return;
     __shared__ double red[32];
     __shared__ int s_last;
@@ -273,10 +274,11 @@ __global__ void __launch_bounds__(256) k_vec4(int64_t n, Body body, double *__re
 }
 
 template <int DOTS, class Body, class Final>
-int launch_vec4(int64_t n, Body body, Final fin, double *partials, unsigned int *ticket, const int *done, cudaStream_t s) {
+int launch_vec4(int64_t n, Body body, Final fin, double *partials, unsigned int *ticket, const int *done, cudaStream_t s,
+                bool pdl = false) {
     if (n <= 0) return 0;
     const int grid = kb_grid(kb_cdiv(n, 4), 256, 8);
-    k_vec4<DOTS, Body, Final><<<grid, 256, 0, s>>>(n, body, partials, ticket, done, fin);
+    KB_CUDA(kb_launch_pdl(k_vec4<DOTS, Body, Final>, dim3(grid), dim3(256), 0, s, pdl, n, body, partials, ticket, done, fin));
     KB_LAUNCH_CHECK();
     return 0;
 }
@@ -409,7 +411,7 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
                     const int32_t *rowblk, double *partials, unsigned int *ticket, const double *x, double *y,
                     const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr,
                     const double *dotw2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr},
-                    const uint8_t *row_pat = nullptr, const pat_off_t *pat_tab = nullptr) {
+                    const uint8_t *row_pat = nullptr, const pat_off_t *pat_tab = nullptr, bool pdl = false) {
     const int64_t nblk = num_blocks(nnz);
     if (row_pat != nullptr) {                           // row-pattern form: 8 bytes per non-zero cross HBM
         // like the 16-bit form it addresses x relative to the first row of the view: never fall back silently
@@ -420,8 +422,8 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
             KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             configured = true;
         }
-        k_spmv_pat<DOTS, Final><<<tma_grid(nblk), P_THREADS, bytes, s>>>(nblk, indptr, row_pat, pat_tab, vals, rowblk, x, y, dotw,
-                                                                        partials, ticket, done, fin, dotw2, pwait);
+        KB_CUDA(kb_launch_pdl(k_spmv_pat<DOTS, Final>, dim3(tma_grid(nblk)), dim3(P_THREADS), bytes, s, pdl, nblk, indptr,
+                              row_pat, pat_tab, vals, rowblk, x, y, dotw, partials, ticket, done, fin, dotw2, pwait));
         KB_LAUNCH_CHECK();
         return 0;
     }
@@ -458,10 +460,11 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
 template <int DOTS, class Final>
 int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                 const Work &w, const double *x, double *y, const double *dotw, const int *done, Final fin,
-                cudaStream_t s, const double *dotw2 = nullptr) {
+                cudaStream_t s, const double *dotw2 = nullptr, bool pdl = false) {
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
                                         fin, s, w.use16 ? w.cols16 : nullptr, dotw2,
-                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, w.usepat ? w.row_pat : nullptr, w.pat_tab);
+                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, w.usepat ? w.row_pat : nullptr, w.pat_tab,
+                                        pdl);
 }
 
 // ------------------------------------------------------------------------------------------------ functors
@@ -657,17 +660,19 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
             for (int it = 0; it < batch; ++it) {
                 const bool sample = g_prof.on && (it % g_prof.every == 0) && g_prof.used < SpmvProfile::CAP;
                 if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used], s);
+                // every kernel of the loop is a programmatic dependent launch (kb_launch_pdl): its launch and set-up
+                // overlap the tail of the kernel before it
                 if (METHOD == 0) {
-                    if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, p, w.done, FinCgAlpha{w.sc, w.done}, s))) return rc;
+                    if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, p, w.done, FinCgAlpha{w.sc, w.done}, s, nullptr, true))) return rc;
                     if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used++ + 1], s);
-                    if ((rc = launch_vec4<1>(n, HCgUpdate{w.sc + S_ALPHA, p, q, xh, r}, FinCgBeta{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
-                    if ((rc = launch_vec4<0>(n, HCgP{w.sc + S_BETA, r, p}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
+                    if ((rc = launch_vec4<1>(n, HCgUpdate{w.sc + S_ALPHA, p, q, xh, r}, FinCgBeta{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s, true))) return rc;
+                    if ((rc = launch_vec4<0>(n, HCgP{w.sc + S_BETA, r, p}, NoFin{}, w.partials, w.ticket, w.done, s, true))) return rc;
                 } else {
-                    if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, rhat, w.done, FinBiAlpha{w.sc, w.done}, s))) return rc;
+                    if ((rc = launch_spmv<1>(n, nnz, indptr, indices, w.vals_hat, w, p, q, rhat, w.done, FinBiAlpha{w.sc, w.done}, s, nullptr, true))) return rc;
                     if (sample) cudaEventRecord(g_prof.ev[2 * g_prof.used++ + 1], s);
-                    if ((rc = launch_vec4<0>(n, HBiS{w.sc + S_ALPHA, q, r}, NoFin{}, w.partials, w.ticket, w.done, s))) return rc;
-                    if ((rc = launch_spmv<2>(n, nnz, indptr, indices, w.vals_hat, w, r, t, r, w.done, FinBiOmega2{w.sc, w.done, w.iter}, s, rhat))) return rc;
-                    if ((rc = launch_vec4<1>(n, HBiUpdateP{w.sc + S_ALPHA, w.sc + S_OMEGA, w.sc + S_BETA, t, q, xh, r, p}, FinBiRes{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s))) return rc;
+                    if ((rc = launch_vec4<0>(n, HBiS{w.sc + S_ALPHA, q, r}, NoFin{}, w.partials, w.ticket, w.done, s, true))) return rc;
+                    if ((rc = launch_spmv<2>(n, nnz, indptr, indices, w.vals_hat, w, r, t, r, w.done, FinBiOmega2{w.sc, w.done, w.iter}, s, rhat, true))) return rc;
+                    if ((rc = launch_vec4<1>(n, HBiUpdateP{w.sc + S_ALPHA, w.sc + S_OMEGA, w.sc + S_BETA, t, q, xh, r, p}, FinBiRes{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s, true))) return rc;
                 }
             }
             if ((rc = read_state(w, &hs, s))) return rc;

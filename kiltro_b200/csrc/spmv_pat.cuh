@@ -44,7 +44,6 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
            double *__restrict__ partials, unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
            const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}) {
     // pwait: halo flags raised by the neighbouring ranks (peer.cuh); the kernel does not touch x before they are up
-    if (done != nullptr && *done != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GRAN = 2;                                // values per 16 bytes (bulk-copy granule)
     StageP *stages = reinterpret_cast<StageP *>(smem_raw);
@@ -58,13 +57,17 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
     const int64_t b_end = nblk * (int64_t)(blockIdx.x + 1) / gridDim.x;
     const int nmine = (int)(b_end - b_begin);
 
+    // set-up that does not depend on the previous kernel of the stream (the dictionary is written once per solver
+    // set-up): with a programmatic dependent launch it overlaps that kernel's tail
     for (int i = threadIdx.x; i < P_SLOTS * P_MAXLEN; i += P_THREADS) s_tab[i] = __ldg(pat_tab + i);
     if (threadIdx.x == 0) {
         for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], P_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        kbpeer::wait_flags(pwait);
     }
+    kb_pdl_wait();
+    if (done != nullptr && *done != 0) return;             // uniform over the grid
+    if (threadIdx.x == 0) kbpeer::wait_flags(pwait);
     __syncthreads();
 
     if (threadIdx.x >= P_CONSUMERS) {

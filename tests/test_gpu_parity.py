@@ -596,7 +596,7 @@ def test_load_increments_and_heat_source():
 
 
 # ------------------------------------------------------------------------------------------------- example scripts (configs 1-3)
-@pytest.mark.parametrize("script", ["steady_1d.py", "steady_2d.py", "transient_2d.py"])
+@pytest.mark.parametrize("script", ["steady_1d.py", "steady_2d.py", "transient_1d.py", "transient_2d.py"])
 def test_example_scripts_run(script):
     import os, subprocess, sys
     from conftest import ROOT
@@ -608,6 +608,8 @@ def test_example_scripts_run(script):
         assert "105.18" in out.stdout and "249.7" in out.stdout          # steady_2d_addi.pdf
     if script == "transient_2d.py":
         assert "time increment 0.8" in out.stdout and "199.8" in out.stdout
+    if script == "transient_1d.py":                                      # tests/golden/transient.npz ex1d (reference-built)
+        assert "time increment 0.8" in out.stdout and "189.527" in out.stdout and "118.625" in out.stdout
 
 
 # ------------------------------------------------------------------------------------------------- edge cases
