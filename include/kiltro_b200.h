@@ -153,6 +153,17 @@ int kb_assemble_fused_tmpl(const double *d_points, int64_t nnode, const double *
                            const void *d_templates, double *d_K, double *d_M, double *d_Flux, void *d_scratch,
                            void *stream);
 
+/* (d) fused path, grid form (quad-4 meshes numbered like Mesh.Rectangle, MeshGeneration/Mesh.py:33-58: node (i, j) =
+ *     j * nxn + i, element (i, j) = [c, c+1, c+nxn+1, c+nxn] with c = j * nxn + i; row-block strips of such a mesh too).
+ *     kb_grid_verify checks the connectivity against that numbering (*d_flag = 0: it matches).  kb_assemble_grid then
+ *     needs neither the connectivity nor the column indices: a warp sweeps a strip of node columns upwards, element
+ *     matrices stay in registers and neighbouring lanes exchange them by shuffles (csrc/assemble_grid.cu).  Same
+ *     summation order and results as kb_assemble_fused.  d_M / d_velocity may be NULL.  d_scratch: 32 bytes. */
+int kb_grid_verify(const int32_t *d_elements, int64_t nelem, int64_t nxn, int64_t nyn, int32_t *d_flag, void *stream);
+int kb_assemble_grid(const double *d_points, const double *d_velocity, const kb_material *material, int mode, int petrov,
+                     int64_t nxn, int64_t nyn, const int32_t *d_indptr, double *d_K, double *d_M, double *d_Flux,
+                     void *d_scratch, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * K10 element operators of the "next" rows (seam form: element matrices to HBM, then kb_assemble_from_elements)
  *   KB_OP_ROBIN         replaces AssemblyRobinForces (FiniteElements/Assembly.py:121-175): Ke = h sum_g N (x) N dV,

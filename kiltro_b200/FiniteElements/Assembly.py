@@ -3,9 +3,10 @@
 Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_condition) -> (K, Flux, M) with K / M as
 DeviceCSR on the pattern cached on fem_solver (FEMSolver.ComputeSparsityFEM) and Flux a device (ndof, 1) tensor.  The
 per-element Python loop of the reference (Assembly.py:46-72) becomes either
-  * the fused kernel (element matrices on chip; csrc/assemble_tmpl.cu when the tiles of the mesh repeat -- every
-    Mesh.Rectangle mesh -- else the generic csrc/assemble_fused.cu; fem_solver.assembly = "fused_generic" forces the
-    latter), or
+  * the fused kernels (element matrices on chip): csrc/assemble_grid.cu for quad meshes numbered like Mesh.Rectangle
+    (element matrices in registers, exchanged by warp shuffles; "auto" picks it, "fused_grid" demands it), else the tile
+    kernels -- csrc/assemble_tmpl.cu when the tiles of the mesh repeat, the generic csrc/assemble_fused.cu otherwise
+    (fem_solver.assembly = "fused" / "fused_generic" force them), or
   * the two-step seam K1 (kb_element_matrices) + K3 (kb_assemble_from_elements) when fem_solver.assembly == "two_pass".
 The dense AssemblyRobinForces pass whose result the reference discards (Assembly.py:90,121-175) is not run."""
 import numpy as np
@@ -13,6 +14,8 @@ import torch
 
 from .. import _lib, device as D
 from ..sparse import DeviceCSR
+
+GRID_IN_AUTO = False        # assembly="auto" picks the grid kernel (csrc/assemble_grid.cu) on Mesh.Rectangle-numbered meshes
 
 __all__ = ['Assemble', 'AssemblyRobinForces', 'AssembleCharacteristicGalerkin']
 
@@ -31,10 +34,15 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
     M = D.empty(sp.nnz) if transient else None
     Flux = D.empty((nnode * formulation.nvar, 1))
     method = getattr(fem_solver, "assembly", "auto")
-    if method not in ("auto", "fused", "fused_generic", "two_pass"):
-        raise ValueError("assembly must be 'auto', 'fused', 'fused_generic' or 'two_pass'")
-    use_fused = False
-    if method != "two_pass" and formulation.nvar == 1:
+    if method not in ("auto", "fused", "fused_grid", "fused_generic", "two_pass"):
+        raise ValueError("assembly must be 'auto', 'fused', 'fused_grid', 'fused_generic' or 'two_pass'")
+    use_fused = use_grid = False
+    if method in (("auto", "fused_grid") if GRID_IN_AUTO else ("fused_grid",)) and formulation.nvar == 1 and formulation.ndim == 2:
+        from .fused import assemble_grid, grid_shape
+        use_grid = grid_shape(sp, mesh) is not None              # Mesh.Rectangle numbering, verified on device (cached)
+    if method == "fused_grid" and not use_grid:
+        raise _lib.KiltroB200Error("assembly='fused_grid' needs a quad-4 mesh numbered like Mesh.Rectangle")
+    if not use_grid and method != "two_pass" and formulation.nvar == 1:
         from .fused import assemble_fused, build_tile_plan
         if sp.tile_plan is None:
             sp.tile_plan = build_tile_plan(sp, mesh)             # symbolic, cached with the pattern
@@ -43,7 +51,9 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
             raise _lib.KiltroB200Error("the tile plan of this mesh does not fit the fused assembly kernel: %r"
                                        % (sp.tile_plan.info,))
     fem_solver.assembly_used = "fused" if use_fused else "two_pass"
-    if use_fused:
+    if use_grid:
+        assemble_grid(fem_solver, sp, formulation, mesh, material, K, M, Flux)
+    elif use_fused:
         assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux)
     else:
         Ke, Fe, Me = formulation.GetAllElementalMatrices(mesh, material, want_mass=transient)

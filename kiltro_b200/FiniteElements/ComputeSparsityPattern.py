@@ -20,6 +20,8 @@ class SparsityPattern(object):
         self.npe = 0
         self.nvar = 1
         self.tile_plan = None
+        self.grid = None          # None: not checked; False / (nxn, nyn): Mesh.Rectangle numbering (fused.grid_shape)
+        self.grid_scratch = None
 
     def to_numpy(self):
         return (D.to_numpy(self.indices), D.to_numpy(self.indptr), D.to_numpy(self.data_local_indices),

@@ -16,6 +16,32 @@ class TilePlan(object):
         self.tile_class = self.trun_ptr = self.trun_row = self.templates = self.scratch = None
 
 
+def grid_shape(sp, mesh):
+    """(nxn, nyn) when the mesh is numbered like Mesh.Rectangle (checked on device once and cached with the pattern:
+    mesh.structured_shape is only the hint that says which shape to check), else None -- csrc/assemble_grid.cu."""
+    if getattr(sp, "grid", None) is None:
+        sp.grid = False
+        shape = mesh.structured_shape if (mesh.structured_shape is not None and not mesh.host_is_authoritative()) else None
+        el = mesh.device_elements()
+        if shape is not None and sp.nvar == 1 and el.dim() == 2 and int(el.shape[1]) == 4 and min(shape) >= 2:
+            flag = D.empty(1, torch.int32)
+            _lib.check(_lib.load().kb_grid_verify(D.ptr(el), int(el.shape[0]), int(shape[0]), int(shape[1]), D.ptr(flag),
+                                                  D.stream_ptr()))
+            if int(flag.item()) == 0:
+                sp.grid = (int(shape[0]), int(shape[1]))
+                sp.grid_scratch = D.empty(32, torch.uint8)
+    return sp.grid or None
+
+
+def assemble_grid(fem_solver, sp, formulation, mesh, material, K, M, Flux):
+    nxn, nyn = sp.grid
+    fem_solver.assembly_used = "fused_grid"
+    _lib.check(_lib.load().kb_assemble_grid(D.ptr(mesh.device_points()), D.ptr(formulation.device_velocity()),
+                                            material.as_struct(), int(formulation.mode), int(bool(formulation.petrov)),
+                                            nxn, nyn, D.ptr(sp.indptr), D.ptr(K), D.ptr(M), D.ptr(Flux),
+                                            D.ptr(sp.grid_scratch), D.stream_ptr()))
+
+
 def build_tile_plan(sp, mesh):
     """Symbolic phase, part 2 (once per mesh): tiles of rows + their incident elements + per-(row, element) records."""
     lib = _lib.load()

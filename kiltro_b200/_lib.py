@@ -57,6 +57,9 @@ SIGNATURES = {
                                  ctypes.POINTER(I64), c_vp]),
     "kb_assemble_fused_tmpl": (I32, [c_vp, I64, c_vp, ctypes.POINTER(kb_material), I32, I32, c_vp, I64, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kb_grid_verify": (I32, [c_vp, I64, I64, I64, c_vp, c_vp]),
+    "kb_assemble_grid": (I32, [c_vp, c_vp, ctypes.POINTER(kb_material), I32, I32, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               c_vp]),
     "kb_element_operator": (I32, [I32, I32, c_vp, c_vp, I64, c_vp, F64, F64, c_vp, c_vp, c_vp]),
     "kb_axpby": (I32, [I64, F64, c_vp, F64, c_vp, c_vp, c_vp]),
     "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),

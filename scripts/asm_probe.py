@@ -8,7 +8,8 @@ import bench
 nps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 mesh, vel, flags, material = bench.make_problem(K, torch, nps)
 form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
-for method in ("two_pass", "fused_generic", "fused"):
+methods = sys.argv[2].split(",") if len(sys.argv) > 2 else ("two_pass", "fused_generic", "fused", "fused_grid")
+for method in methods:
     for at in ("steady", "transient"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
         bc = K.BoundaryCondition()
@@ -17,10 +18,10 @@ for method in ("two_pass", "fused_generic", "fused"):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(10):
             out = K.Assemble(fs, form.function_spaces, form, mesh, material, bc)
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        ms = e0.elapsed_time(e1) / 10
         nn, ne, nnz = mesh.nnodes, mesh.nelem, out[0].nnz
         byt = 16 * ne + 32 * nn + 8 * nnz + 4 * (nn + 1) + 4 * nnz + (8 * nnz if at == "transient" else 0)
         print("nps=%d %-9s %-9s %.3f ms  %.1f GB/s algorithmic (%.1f%% of 6543)  plan=%s" % (

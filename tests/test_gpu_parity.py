@@ -262,11 +262,13 @@ def test_closed_form_galerkin_advection():
 # ------------------------------------------------------------------------------------------------- fused assembly (K1+K3)
 @pytest.mark.parametrize("nx,ny,transient,cls", [(70, 53, True, "HeatAdvectionDiffusion"), (45, 31, False, "TemperaturePG"),
                                                  (15, 15, True, "Temperature"), (16, 14, False, "HeatAdvectionDiffusionPG"),
-                                                 (3, 2, True, "HeatAdvectionDiffusion")])
+                                                 (3, 2, True, "HeatAdvectionDiffusion"), (1, 1, True, "HeatAdvectionDiffusion"),
+                                                 (40, 150, True, "HeatAdvectionDiffusion"), (95, 130, False, "Temperature")])
 def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
     """Device-generated Rectangle mesh (2-D node-patch tiles), nodes perturbed in place on device: fused == two-pass
     bitwise, and both match the oracle."""
     from oracle import kiltro_oracle as O
+    from kiltro_b200.FiniteElements.Assembly import GRID_IN_AUTO
     K = _K()
     m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (2.0, 1.0), nx, ny)
     g = torch.Generator(device="cuda"); g.manual_seed(7)
@@ -280,8 +282,9 @@ def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
     form = getattr(K, cls)(m, velocity=vel)
     at = "transient" if transient else "steady"
     res = {}
-    used = {"fused": "fused_template", "fused_generic": "fused", "two_pass": "two_pass"}
-    for method in ("fused", "fused_generic", "two_pass"):
+    used = {"fused": "fused_template", "fused_generic": "fused", "two_pass": "two_pass", "fused_grid": "fused_grid",
+            "auto": "fused_grid" if GRID_IN_AUTO else "fused_template"}
+    for method in ("fused", "fused_generic", "two_pass", "fused_grid", "auto"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
         Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
         assert fs.assembly_used == used[method]
@@ -289,11 +292,12 @@ def test_fused_assembly_structured_tiles(nx, ny, transient, cls):
         if method == "fused":
             info = fs.sparsity.tile_plan.info
             assert info["structured"] and fs.sparsity.tile_plan.templated and 1 <= info["templates"] <= 9
-    # template kernel == generic fused kernel, bit for bit (same element routine, same summation order)
-    assert torch.equal(res["fused"][0].data, res["fused_generic"][0].data)
-    assert torch.equal(res["fused"][1], res["fused_generic"][1])
-    if transient:
-        assert torch.equal(res["fused"][2].data, res["fused_generic"][2].data)
+    # template kernel == generic fused kernel == grid kernel, bit for bit (same element routine, same summation order)
+    for other in ("fused_generic", "fused_grid", "auto"):
+        assert torch.equal(res["fused"][0].data, res[other][0].data), other
+        assert torch.equal(res["fused"][1], res[other][1]), other
+        if transient:
+            assert torch.equal(res["fused"][2].data, res[other][2].data), other
     # same device function, same accumulation order; the two kernels may contract FMAs differently in the tanh/PG branch
     assert rel_max(K.to_numpy(res["fused"][0].data), K.to_numpy(res["two_pass"][0].data)) < 1e-14
     assert torch.equal(res["fused"][1], res["two_pass"][1])
@@ -331,13 +335,15 @@ def test_fused_assembly_nonconvex_fixup(cls, transient):
     mode = "consistent" if cls.startswith("Heat") else "reference"
     A = O.assemble(K.to_numpy(P), m.elements, K.to_numpy(vel), matv, mode, cls.endswith("PG"), transient)
     res = {}
-    for method in ("fused", "fused_generic", "two_pass"):
+    for method in ("fused", "fused_generic", "two_pass", "fused_grid"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
         Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
         res[method] = Kc
         assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL, method
         if transient:
             assert rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL, method
+        if method == "fused_grid":           # the grid kernel redoes the whole mesh with the general routine: flag raised
+            assert fs.assembly_used == "fused_grid" and int(fs.sparsity.grid_scratch.view(torch.int32)[4]) == 1
     assert torch.equal(res["fused"].data, res["fused_generic"].data)
     # the tile flags say the fix-up launch really ran
     fs = K.FEMSolver(analysis_type=at, verbose=False, assembly="fused")
