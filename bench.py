@@ -440,7 +440,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "assembly_traffic.json")) as f:
                 tj = json.load(f)
-            if nps == 4000:
+            if nps == 4000 and tj.get("assembly_used") == fs.assembly_used:
                 asm_traffic, asm_src = tj["traffic_bytes_per_launch"], tj["source"]
         except Exception:
             pass
@@ -450,8 +450,10 @@ def main():
                     "peak_source": peak_src, "avg_launch_ms": asm_ms, "launches_timed": n_asm,
                     "algorithmic_bytes_per_launch": asm_bytes,
                     "note": "Assemble() calls back to back (output allocation included), CUDA events; algorithmic bytes = "
-                            "16 nelem + 32 nnode + 12 nnz + 4 (nnode+1), SURVEY 8(d); the kernel is bound by the "
-                            "shared-memory pipe and exposed latency at 16 warps/SM, not by HBM (DESIGN 4.2)"}
+                            "16 nelem + 32 nnode + 12 nnz + 4 (nnode+1), SURVEY 8(d); " + (
+                                "grid kernel: element matrices in registers, exchanged by warp shuffles; connectivity and "
+                                "column indices are not read (DESIGN 4.2)" if fs.assembly_used == "fused_grid" else
+                                "tile kernels: bound by the shared-memory pipe and exposed latency at 16 warps/SM (DESIGN 4.2)")}
 
     # ---- e2e: same step from pinned host buffers in the reference's array formats
     e2e = None

@@ -15,7 +15,7 @@ import torch
 from .. import _lib, device as D
 from ..sparse import DeviceCSR
 
-GRID_IN_AUTO = False        # assembly="auto" picks the grid kernel (csrc/assemble_grid.cu) on Mesh.Rectangle-numbered meshes
+GRID_IN_AUTO = True         # assembly="auto" picks the grid kernel (csrc/assemble_grid.cu) on Mesh.Rectangle-numbered meshes
 
 __all__ = ['Assemble', 'AssemblyRobinForces', 'AssembleCharacteristicGalerkin']
 

@@ -23,7 +23,14 @@ def grid_shape(sp, mesh):
         sp.grid = False
         shape = mesh.structured_shape if (mesh.structured_shape is not None and not mesh.host_is_authoritative()) else None
         el = mesh.device_elements()
-        if shape is not None and sp.nvar == 1 and el.dim() == 2 and int(el.shape[1]) == 4 and min(shape) >= 2:
+        quads = sp.nvar == 1 and el.dim() == 2 and int(el.shape[1]) == 4 and int(el.shape[0]) > 0
+        if shape is None and quads:
+            # user-provided arrays: the first element of a Mesh.Rectangle numbering is [0, 1, nxn + 1, nxn]
+            first = [int(v) for v in el[0].tolist()]
+            nxn, nn = first[3], int(mesh.nnodes)
+            if first[0] == 0 and first[1] == 1 and nxn >= 2 and first[2] == nxn + 1 and nn % nxn == 0 and nn // nxn >= 2:
+                shape = (nxn, nn // nxn)
+        if shape is not None and quads and min(shape) >= 2:
             flag = D.empty(1, torch.int32)
             _lib.check(_lib.load().kb_grid_verify(D.ptr(el), int(el.shape[0]), int(shape[0]), int(shape[1]), D.ptr(flag),
                                                   D.stream_ptr()))
@@ -36,7 +43,8 @@ def grid_shape(sp, mesh):
 def assemble_grid(fem_solver, sp, formulation, mesh, material, K, M, Flux):
     nxn, nyn = sp.grid
     fem_solver.assembly_used = "fused_grid"
-    _lib.check(_lib.load().kb_assemble_grid(D.ptr(mesh.device_points()), D.ptr(formulation.device_velocity()),
+    pts, vel = mesh.device_points(), formulation.device_velocity()    # (kept alive: uploads of host arrays are temporaries)
+    _lib.check(_lib.load().kb_assemble_grid(D.ptr(pts), D.ptr(vel),
                                             material.as_struct(), int(formulation.mode), int(bool(formulation.petrov)),
                                             nxn, nyn, D.ptr(sp.indptr), D.ptr(K), D.ptr(M), D.ptr(Flux),
                                             D.ptr(sp.grid_scratch), D.stream_ptr()))

@@ -18,6 +18,7 @@
 // HBM traffic: 32 B per node (+ 1/31 + 1/STRIP_ROWS overlap), 4 B per row of indptr, 8 B per non-zero out.
 // No atomics, deterministic.  Lane 31 only feeds lane 30 (3 % redundant element work), the first step of a strip
 // recomputes the element row below it (1 / STRIP_ROWS).
+#include <cstdlib>
 #include "element.cuh"
 
 using namespace kbel;
@@ -29,8 +30,22 @@ namespace {
 constexpr int G_THREADS = 256;                 // 8 warps per CTA, 2 CTAs per SM
 constexpr int G_WARPS = G_THREADS / 32;
 constexpr int G_COLS = 31;                     // node columns owned by a warp
-constexpr int G_STRIP = 64;                    // node rows per task
+constexpr int G_STRIP = 64;                    // node rows per task (default)
 constexpr int G_BUF = G_COLS * 9 + 1;          // doubles parked per warp and step
+constexpr int G_PFD = 4;                       // L2 prefetch distance in steps (node rows; default)
+
+// a load whose issue point matters (one step ahead of its use): volatile, so the compiler does not sink it to the use
+__device__ __forceinline__ double2 ldg_pin(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_pin(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ double shfl_next(double v) { return __shfl_down_sync(KB_FULL, v, 1); }
 template <int W>
@@ -54,11 +69,14 @@ __global__ void __launch_bounds__(256) k_grid_verify(const int4 *__restrict__ el
 
 // WHICH = 0: K (+ Flux); WHICH = 1: M.  GENERAL: see assemble_tmpl.cu (second launch, general element routine for every
 // element, runs only when the first launch met an element the sum-factorised routine declines).
-template <bool HAS_U, int WHICH, bool GENERAL>
+// PF (development switch, KB_GRID_VARIANT): 0 = loads where they are used; 1 = row pointers loaded (one coalesced load per
+// step) before the element is computed + L2 prefetch of the node rows G_PFD steps ahead; 2 = 1 + the upper nodes of the next
+// element are loaded into registers one step ahead.
+template <bool HAS_U, int WHICH, bool GENERAL, int PF>
 __global__ void __launch_bounds__(G_THREADS, 2)
 k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ velocity, ElemOpts o, int nxn, int nyn,
                 const int32_t *__restrict__ indptr, double *__restrict__ out, double *__restrict__ Flux,
-                int ntask_x, int ntasks, unsigned int *__restrict__ counter, int *__restrict__ nbad) {
+                int ntask_x, int ntasks, unsigned int *__restrict__ counter, int *__restrict__ nbad, int strip, int pfd) {
     __shared__ double s_buf[G_WARPS][G_BUF];
     if (GENERAL && *reinterpret_cast<volatile int *>(nbad) == 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,7 +92,7 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
         if (task >= (unsigned int)ntasks) break;
         const int ty = (int)(task / (unsigned int)ntask_x), tx = (int)(task - (unsigned int)ty * ntask_x);
         const int n0 = tx * G_COLS;                          // first owned node column
-        const int j0 = ty * G_STRIP, j1 = min(j0 + G_STRIP, nyn);
+        const int j0 = ty * strip, j1 = min(j0 + strip, nyn);
         const int c = n0 - 1 + lane;                         // this lane's element column
         const int n = c + 1;                                 // ... and node column
         const bool col_ok = c >= 0 && c < nex;               // the element column exists
@@ -97,6 +115,13 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
         }
         // rows 2 (upper right node) and 3 (upper left node) of the element matrix of the step before, and its fe
         double p2[4] = {0.0, 0.0, 0.0, 0.0}, p3[4] = {0.0, 0.0, 0.0, 0.0}, pf2 = 0.0, pf3 = 0.0;
+        const int nown = min(G_COLS, nxn - n0);                          // owned node columns of this strip
+        double2 nq0, nq1, nu0, nu1;                                      // PF == 2: upper nodes of the next element
+        if (PF == 2) {
+            const int64_t b = (int64_t)min(jstart + 1, nyn - 1) * nxn + cl;
+            nq0 = __ldg(points + b); nq1 = __ldg(points + b + 1);
+            if (HAS_U) { nu0 = __ldg(velocity + b); nu1 = __ldg(velocity + b + 1); }
+        }
 
         // element rows je = jstart .. j1 - 1 (je = j0 - 1 only primes p2 / p3); node row je is emitted after element je
         for (int je = jstart; je < j1; ++je) {
@@ -105,7 +130,21 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
             U[0][0] = U[3][0]; U[0][1] = U[3][1]; U[1][0] = U[2][0]; U[1][1] = U[2][1];
             double ke[16], fe[4], me[16];
             const bool el_ok = col_ok && je < ney;
-            {
+            int ip = 0;                                                  // PF >= 1: indptr[row0 + lane], loaded early
+            if (PF >= 1) {
+                ip = ldg_pin(indptr + (int64_t)max(je, j0) * nxn + n0 + min(lane, nown));
+                const int64_t bp = (int64_t)min(je + 1 + pfd, nyn - 1) * nxn + cl;
+                prefetch_l2(points + bp);
+                if (HAS_U) prefetch_l2(velocity + bp);
+                if (lane < 16) prefetch_l2(indptr + (int64_t)min(je + pfd, nyn - 1) * nxn + n0 + 2 * lane);
+            }
+            if (PF == 2) {
+                X[3][0] = nq0.x; X[3][1] = nq0.y; X[2][0] = nq1.x; X[2][1] = nq1.y;
+                if (HAS_U) { U[3][0] = nu0.x; U[3][1] = nu0.y; U[2][0] = nu1.x; U[2][1] = nu1.y; }
+                const int64_t b = (int64_t)min(je + 2, nyn - 1) * nxn + cl;
+                nq0 = ldg_pin(points + b); nq1 = ldg_pin(points + b + 1);
+                if (HAS_U) { nu0 = ldg_pin(velocity + b); nu1 = ldg_pin(velocity + b + 1); }
+            } else {
                 const int64_t b = (int64_t)min(je + 1, nyn - 1) * nxn + cl;
                 const double2 q0 = __ldg(points + b), q1 = __ldg(points + b + 1);
                 X[3][0] = q0.x; X[3][1] = q0.y; X[2][0] = q1.x; X[2][1] = q1.y;
@@ -143,11 +182,17 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
                 const double e8 = d0[2];
                 const int64_t row = (int64_t)je * nxn + n;
                 const int64_t row0 = (int64_t)je * nxn + n0;
-                const int nown = min(G_COLS, nxn - n0);                  // owned node columns of this strip
-                const int base = __ldg(indptr + row0);
-                const int total = __ldg(indptr + row0 + nown) - base;
+                int base, total, pos;
+                if (PF >= 1) {
+                    base = __shfl_sync(KB_FULL, ip, 0);
+                    total = __shfl_sync(KB_FULL, ip, nown) - base;
+                    pos = ip - base;
+                } else {
+                    base = __ldg(indptr + row0);
+                    total = __ldg(indptr + row0 + nown) - base;
+                    pos = own ? __ldg(indptr + row) - base : 0;
+                }
                 if (own) {
-                    int pos = __ldg(indptr + row) - base;
                     const bool xl = n > 0, xr = n < nxn - 1, yd = je > 0, yu = je < nyn - 1;
                     if (yd) {
                         if (xl) buf[pos++] = e0;
@@ -183,20 +228,42 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
     if (!GENERAL && bad) *nbad = 1;
 }
 
-template <bool HAS_U, int WHICH>
-int launch_grid(cudaStream_t s, const double *points, const double *velocity, const ElemOpts &o, int nxn, int nyn,
-                const int32_t *indptr, double *out, double *Flux, unsigned int *counters, int *nbad) {
-    const int ntx = (nxn + G_COLS - 1) / G_COLS, nty = (nyn + G_STRIP - 1) / G_STRIP;
+int g_grid_variant = -1;      // development switch (environment KB_GRID_VARIANT): see PF above
+
+template <bool HAS_U, int WHICH, int PF>
+int launch_grid_pf(cudaStream_t s, const double *points, const double *velocity, const ElemOpts &o, int nxn, int nyn,
+                   const int32_t *indptr, double *out, double *Flux, unsigned int *counters, int *nbad) {
+    static int strip = 0, pfd = 0;                           // development switches KB_GRID_STRIP / KB_GRID_PFD
+    if (strip == 0) {
+        const char *e = getenv("KB_GRID_STRIP"), *f = getenv("KB_GRID_PFD");
+        strip = e && atoi(e) > 0 ? atoi(e) : G_STRIP;
+        pfd = f && atoi(f) > 0 ? atoi(f) : G_PFD;
+    }
+    const int ntx = (nxn + G_COLS - 1) / G_COLS, nty = (nyn + strip - 1) / strip;
     const int ntasks = ntx * nty;
     const int64_t cap = (int64_t)kb_num_sms() * 2;
     const int grid = (int)((ntasks + G_WARPS - 1) / G_WARPS < cap ? (ntasks + G_WARPS - 1) / G_WARPS : cap);
-    k_assemble_grid<HAS_U, WHICH, false><<<grid, G_THREADS, 0, s>>>((const double2 *)points, (const double2 *)velocity, o, nxn,
-                                                                    nyn, indptr, out, Flux, ntx, ntasks, counters, nbad);
+    k_assemble_grid<HAS_U, WHICH, false, PF><<<grid, G_THREADS, 0, s>>>((const double2 *)points, (const double2 *)velocity, o,
+                                                                        nxn, nyn, indptr, out, Flux, ntx, ntasks, counters, nbad,
+                                                                        strip, pfd);
     KB_LAUNCH_CHECK();
-    k_assemble_grid<HAS_U, WHICH, true><<<grid, G_THREADS, 0, s>>>((const double2 *)points, (const double2 *)velocity, o, nxn,
-                                                                   nyn, indptr, out, Flux, ntx, ntasks, counters + 1, nbad);
+    k_assemble_grid<HAS_U, WHICH, true, 0><<<grid, G_THREADS, 0, s>>>((const double2 *)points, (const double2 *)velocity, o, nxn,
+                                                                      nyn, indptr, out, Flux, ntx, ntasks, counters + 1, nbad,
+                                                                      strip, pfd);
     KB_LAUNCH_CHECK();
     return 0;
+}
+
+template <bool HAS_U, int WHICH>
+int launch_grid(cudaStream_t s, const double *points, const double *velocity, const ElemOpts &o, int nxn, int nyn,
+                const int32_t *indptr, double *out, double *Flux, unsigned int *counters, int *nbad) {
+    if (g_grid_variant < 0) {
+        const char *e = getenv("KB_GRID_VARIANT");
+        g_grid_variant = e ? atoi(e) : 1;
+    }
+    if (g_grid_variant == 0) return launch_grid_pf<HAS_U, WHICH, 0>(s, points, velocity, o, nxn, nyn, indptr, out, Flux, counters, nbad);
+    if (g_grid_variant == 2) return launch_grid_pf<HAS_U, WHICH, 2>(s, points, velocity, o, nxn, nyn, indptr, out, Flux, counters, nbad);
+    return launch_grid_pf<HAS_U, WHICH, 1>(s, points, velocity, o, nxn, nyn, indptr, out, Flux, counters, nbad);
 }
 
 }  // namespace

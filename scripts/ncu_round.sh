@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for one round (run under gpurun): launch list of a short bench run + --set full captures of the dominant
 # kernel (SpMV inside the solver) and of the numeric assembly.  Usage: scripts/ncu_round.sh <tag> [spmv-regex] [asm-regex]
-TAG=${1:-r01}; KRE=${2:-k_spmv_pat}; ARE=${3:-k_assemble_tmpl}
+TAG=${1:-r01}; KRE=${2:-k_spmv_pat}; ARE=${3:-k_assemble_grid}
 CMD="python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --maxiter 60 --check-every 20"
 mkdir -p gpurun_out
 $CMD > gpurun_out/ncu_plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain_$TAG.log; exit 1; }

@@ -333,7 +333,9 @@ def test_fused_assembly_nonconvex_fixup(cls, transient):
     at = "transient" if transient else "steady"
     form = getattr(K, cls)(m, velocity=vel)
     mode = "consistent" if cls.startswith("Heat") else "reference"
-    A = O.assemble(K.to_numpy(P), m.elements, K.to_numpy(vel), matv, mode, cls.endswith("PG"), transient)
+    # (connectivity taken from the device copy: reading m.elements would make the host arrays authoritative)
+    A = O.assemble(K.to_numpy(P), K.to_numpy(m.device_elements()).astype(np.int64), K.to_numpy(vel), matv, mode,
+                   cls.endswith("PG"), transient)
     res = {}
     for method in ("fused", "fused_generic", "two_pass", "fused_grid"):
         fs = K.FEMSolver(analysis_type=at, verbose=False, assembly=method)
@@ -368,6 +370,36 @@ def test_fused_assembly_row_chunk_tiles_golden(name):
     fs2 = K.FEMSolver(analysis_type="transient", verbose=False, assembly="two_pass")
     K2 = K.Assemble(fs2, form.function_spaces, form, m, mat, K.BoundaryCondition())[0]
     assert rel_max(K.to_numpy(K2.data), K.to_numpy(Kc.data)) < 1e-14
+
+
+def test_grid_assembly_on_host_provided_arrays():
+    """User-provided (host) arrays: the Mesh.Rectangle numbering is recognised from the connectivity itself and checked
+    on device; a mesh with any other numbering is refused by assembly='fused_grid' (and served by the tile kernels)."""
+    from oracle import kiltro_oracle as O
+    K = _K()
+    pts, el = O.mesh_rectangle((0.0, 0.0), (1.5, 1.0), 37, 29)
+    rng = np.random.default_rng(5)
+    vel = rng.standard_normal(pts.shape) * 2.0 + 1.0
+    matv = (1.1, 0.8, 1.3, 0.9, 1.7)
+    m = make_mesh(pts, el)
+    form = K.HeatAdvectionDiffusion(m, velocity=vel)
+    fs = K.FEMSolver(analysis_type="transient", verbose=False, assembly="fused_grid")
+    Kc, Flux, Mm = K.Assemble(fs, form.function_spaces, form, m, material_for(matv, 2), K.BoundaryCondition())
+    assert fs.assembly_used == "fused_grid" and fs.sparsity.grid == (38, 30)
+    A = O.assemble(pts, el, vel, matv, "consistent", False, True)
+    assert np.array_equal(K.to_numpy(Kc.indices), A["indices"])
+    assert rel_max(K.to_numpy(Kc.data), A["K"]) < VAL_TOL and rel_max(K.to_numpy(Mm.data), A["M"]) < VAL_TOL
+    assert rel_max(K.to_numpy(Flux).ravel(), A["Flux"]) < VAL_TOL
+    el2 = el.copy(); el2[[3, 11]] = el2[[11, 3]]                       # two elements swapped: not the grid numbering
+    m2 = make_mesh(pts, el2)
+    form2 = K.HeatAdvectionDiffusion(m2, velocity=vel)
+    from kiltro_b200._lib import KiltroB200Error
+    with pytest.raises(KiltroB200Error):
+        K.Assemble(K.FEMSolver(verbose=False, assembly="fused_grid"), form2.function_spaces, form2, m2, material_for(matv, 2),
+                   K.BoundaryCondition())
+    fs3 = K.FEMSolver(verbose=False, assembly="auto")
+    K3 = K.Assemble(fs3, form2.function_spaces, form2, m2, material_for(matv, 2), K.BoundaryCondition())[0]
+    assert fs3.assembly_used != "fused_grid" and rel_max(K.to_numpy(K3.data), A["K"]) < VAL_TOL
 
 
 def test_fused_assembly_line_mesh_large():
