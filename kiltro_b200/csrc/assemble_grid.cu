@@ -15,9 +15,9 @@
 //   * per step a lane loads the two upper nodes of its element (coordinates and velocity, 16 bytes each, consecutive
 //     lanes -> consecutive addresses); the connectivity and the column indices are not read at all.
 //
-// HBM traffic: 32 B per node (+ 1/31 + 1/STRIP_ROWS overlap), 4 B per row of indptr, 8 B per non-zero out.
+// HBM traffic: 32 B per node (+ 1/31 + 1/G_STRIP overlap), 4 B per row of indptr, 8 B per non-zero out.
 // No atomics, deterministic.  Lane 31 only feeds lane 30 (3 % redundant element work), the first step of a strip
-// recomputes the element row below it (1 / STRIP_ROWS).
+// recomputes the element row below it (1 / G_STRIP).
 #include <cstdlib>
 #include "element.cuh"
 
@@ -30,9 +30,9 @@ namespace {
 constexpr int G_THREADS = 256;                 // 8 warps per CTA, 2 CTAs per SM
 constexpr int G_WARPS = G_THREADS / 32;
 constexpr int G_COLS = 31;                     // node columns owned by a warp
-constexpr int G_STRIP = 64;                    // node rows per task (default)
+constexpr int G_STRIP = 32;                    // node rows per task (default; 64: 0.477 ms, 32: 0.451 ms, 128: 0.508 ms @S16)
 constexpr int G_BUF = G_COLS * 9 + 1;          // doubles parked per warp and step
-constexpr int G_PFD = 4;                       // L2 prefetch distance in steps (node rows; default)
+constexpr int G_PFD = 3;                       // L2 prefetch distance in steps (node rows; default; 8 is slower than 4, 2 faster)
 
 // a load whose issue point matters (one step ahead of its use): volatile, so the compiler does not sink it to the use
 __device__ __forceinline__ double2 ldg_pin(const double2 *p) {

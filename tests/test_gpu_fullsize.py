@@ -45,7 +45,7 @@ def test_assembly_identities_fullsize(big):
     K, mesh, fs, mat = big
     form = K.HeatDiffusion(mesh)
     Kc, Flux, M = K.Assemble(fs, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
-    assert fs.assembly_used == "fused_template" and fs.sparsity.tile_plan.info["structured"]
+    assert fs.assembly_used == "fused_grid" and fs.sparsity.grid == (NPS, NPS)
     nn = mesh.nnodes
     ones = torch.ones(nn, dtype=torch.float64, device="cuda")
     kmax = float(Kc.data.abs().max())
@@ -66,6 +66,12 @@ def test_assembly_identities_fullsize(big):
     fs2 = K.FEMSolver(analysis_type="transient", verbose=False, assembly="two_pass")
     K3, F3, M3 = K.Assemble(fs2, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
     assert torch.equal(K3.data, Kc.data) and torch.equal(M3.data, M.data) and torch.equal(F3, Flux)
+    del K3, M3, F3, fs2
+    # ... and so does the template form of the tile kernels (the default before the grid kernel)
+    fs3 = K.FEMSolver(analysis_type="transient", verbose=False, assembly="fused")
+    K4, F4, M4 = K.Assemble(fs3, form.function_spaces, form, mesh, mat, K.BoundaryCondition())
+    assert fs3.assembly_used == "fused_template" and fs3.sparsity.tile_plan.info["structured"]
+    assert torch.equal(K4.data, Kc.data) and torch.equal(M4.data, M.data) and torch.equal(F4, Flux)
 
 
 def test_steady_closed_form_fullsize(big):
@@ -190,7 +196,7 @@ def test_permuted_numbering_at_scale():
         return sol.sol_device[:, 0, 0], fs
 
     ref, fs0 = solve(m, vel, flags)
-    assert fs0.assembly_used == "fused_template"
+    assert fs0.assembly_used == "fused_grid"
     perm = torch.randperm(nn, device="cuda", generator=g)          # new id of old node i = perm[i]
     inv = torch.empty_like(perm); inv[perm] = torch.arange(nn, device="cuda")
     P2 = m.device_points()[inv].contiguous()                       # coordinates listed in the new numbering
