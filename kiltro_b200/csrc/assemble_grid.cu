@@ -32,7 +32,7 @@ constexpr int G_WARPS = G_THREADS / 32;
 constexpr int G_COLS = 31;                     // node columns owned by a warp
 constexpr int G_STRIP = 32;                    // node rows per task (default; 64: 0.477 ms, 32: 0.451 ms, 128: 0.508 ms @S16)
 constexpr int G_BUF = G_COLS * 9 + 1;          // doubles parked per warp and step
-constexpr int G_PFD = 3;                       // L2 prefetch distance in steps (node rows; default; 8 is slower than 4, 2 faster)
+constexpr int G_PFD = 2;                       // L2 prefetch distance in steps (node rows; default; 8 is slower than 4, 2 faster)
 
 // a load whose issue point matters (one step ahead of its use): volatile, so the compiler does not sink it to the use
 __device__ __forceinline__ double2 ldg_pin(const double2 *p) {
