@@ -31,7 +31,7 @@ constexpr int G_THREADS = 256;                 // 8 warps per CTA, 2 CTAs per SM
 constexpr int G_WARPS = G_THREADS / 32;
 constexpr int G_COLS = 31;                     // node columns owned by a warp
 constexpr int G_STRIP = 32;                    // node rows per task (default; 64: 0.477 ms, 32: 0.451 ms, 128: 0.508 ms @S16)
-constexpr int G_BUF = G_COLS * 9 + 1;          // doubles parked per warp and step
+constexpr int G_BUF = 9 * 32;                  // doubles parked per warp and step (31 rows x <= 9 entries)
 constexpr int G_PFD = 2;                       // L2 prefetch distance in steps (node rows; default; 8 is slower than 4, 2 faster)
 
 // a load whose issue point matters (one step ahead of its use): volatile, so the compiler does not sink it to the use
@@ -194,30 +194,42 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
                 }
                 if (own) {
                     const bool xl = n > 0, xr = n < nxn - 1, yd = je > 0, yu = je < nyn - 1;
-                    if (yd) {
-                        if (xl) buf[pos++] = e0;
-                        buf[pos++] = e1;
-                        if (xr) buf[pos++] = e2;
-                    }
-                    if (xl) buf[pos++] = e3;
-                    buf[pos++] = e4;
-                    if (xr) buf[pos++] = e5;
-                    if (yu) {
-                        if (xl) buf[pos++] = e6;
-                        buf[pos++] = e7;
-                        if (xr) buf[pos++] = e8;
+                    double *bq = buf + pos;
+                    if (xl && xr && yd && yu) {                          // interior row: nine entries, fixed offsets
+                        bq[0] = e0; bq[1] = e1; bq[2] = e2; bq[3] = e3; bq[4] = e4;
+                        bq[5] = e5; bq[6] = e6; bq[7] = e7; bq[8] = e8;
+                    } else {
+                        if (yd) {
+                            if (xl) *bq++ = e0;
+                            *bq++ = e1;
+                            if (xr) *bq++ = e2;
+                        }
+                        if (xl) *bq++ = e3;
+                        *bq++ = e4;
+                        if (xr) *bq++ = e5;
+                        if (yu) {
+                            if (xl) *bq++ = e6;
+                            *bq++ = e7;
+                            if (xr) *bq++ = e8;
+                        }
                     }
                 }
                 if (WHICH == 0) {                                        // source vector          Assembly.py:69-72
-                    const double fb = shfl_next(pf3), fd = shfl_next(fe[0]);
-                    if (own) {
-                        double f = 0.0;
-                        if (has_q) { f = pf2 + fb; f += fe[1]; f += fd; }
-                        Flux[row] = f;
+                    double f = 0.0;
+                    if (has_q) {                                         // (uniform over the grid)
+                        const double fb = shfl_next(pf3), fd = shfl_next(fe[0]);
+                        f = pf2 + fb; f += fe[1]; f += fd;
                     }
+                    if (own) Flux[row] = f;
                 }
                 __syncwarp();
-                for (int t = lane; t < total; t += 32) __stcs(out + base + t, buf[t]);
+                {
+                    double *op = out + base + lane;
+                    const double *bp = buf + lane;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        if (lane + 32 * k < total) __stcs(op + 32 * k, bp[32 * k]);
+                }
                 __syncwarp();
             }
 #pragma unroll
