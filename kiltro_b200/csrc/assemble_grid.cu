@@ -132,20 +132,20 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
             const bool el_ok = col_ok && je < ney;
             int ip = 0;                                                  // PF >= 1: indptr[row0 + lane], loaded early
             if (PF >= 1) {
-                ip = ldg_pin(indptr + (int64_t)max(je, j0) * nxn + n0 + min(lane, nown));
-                const int64_t bp = (int64_t)min(je + 1 + pfd, nyn - 1) * nxn + cl;
+                ip = ldg_pin(indptr + (max(je, j0) * nxn + n0 + min(lane, nown)));
+                const int bp = min(je + 1 + pfd, nyn - 1) * nxn + cl;      // (node indices fit 32 bits)
                 prefetch_l2(points + bp);
                 if (HAS_U) prefetch_l2(velocity + bp);
-                if (lane < 16) prefetch_l2(indptr + (int64_t)min(je + pfd, nyn - 1) * nxn + n0 + 2 * lane);
+                if (lane < 16) prefetch_l2(indptr + (min(je + pfd, nyn - 1) * nxn + n0 + 2 * lane));
             }
             if (PF == 2) {
                 X[3][0] = nq0.x; X[3][1] = nq0.y; X[2][0] = nq1.x; X[2][1] = nq1.y;
                 if (HAS_U) { U[3][0] = nu0.x; U[3][1] = nu0.y; U[2][0] = nu1.x; U[2][1] = nu1.y; }
-                const int64_t b = (int64_t)min(je + 2, nyn - 1) * nxn + cl;
+                const int b = min(je + 2, nyn - 1) * nxn + cl;
                 nq0 = ldg_pin(points + b); nq1 = ldg_pin(points + b + 1);
                 if (HAS_U) { nu0 = ldg_pin(velocity + b); nu1 = ldg_pin(velocity + b + 1); }
             } else {
-                const int64_t b = (int64_t)min(je + 1, nyn - 1) * nxn + cl;
+                const int b = min(je + 1, nyn - 1) * nxn + cl;
                 const double2 q0 = __ldg(points + b), q1 = __ldg(points + b + 1);
                 X[3][0] = q0.x; X[3][1] = q0.y; X[2][0] = q1.x; X[2][1] = q1.y;
                 if (HAS_U) {
@@ -180,8 +180,8 @@ k_assemble_grid(const double2 *__restrict__ points, const double2 *__restrict__ 
                 const double e6 = mat[7];
                 const double e7 = mat[6] + d0[3];
                 const double e8 = d0[2];
-                const int64_t row = (int64_t)je * nxn + n;
-                const int64_t row0 = (int64_t)je * nxn + n0;
+                const int row = je * nxn + n;
+                const int row0 = je * nxn + n0;
                 int base, total, pos;
                 if (PF >= 1) {
                     base = __shfl_sync(KB_FULL, ip, 0);
@@ -302,7 +302,7 @@ extern "C" int kb_assemble_grid(const double *d_points, const double *d_velocity
                                 double *d_Flux, void *d_scratch, void *stream) {
     if (!d_points || !material || !d_indptr || !d_K || !d_Flux || !d_scratch) return KB_EINVAL;
     if (nxn < 2 || nyn < 2) return KB_EINVAL;
-    if (nxn * nyn > (int64_t)INT32_MAX) return KB_ETOOBIG;
+    if (nxn * nyn > (int64_t)INT32_MAX - 64) return KB_ETOOBIG;         // node indices (+ the prefetch overshoot) fit 32 bits
     if (mode != KB_MODE_REFERENCE && mode != KB_MODE_CONSISTENT) return KB_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const ElemOpts o = kb_make_opts(material, mode, petrov, d_M != nullptr);
