@@ -21,6 +21,7 @@ for row in csv.DictReader(lines):
     k = re.sub(r"\(.*", "", row["Kernel Name"])[:100]
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(v[1] for v in agg.values())
+out.append("# command: see scripts/ncu_round.sh (bench.py --profiler-range under ncu --profile-from-start off: the launches of ONE timed step)")
 out.append("# ncu --metrics gpu__time_duration.sum --clock-control none  (tag %s); per-launch times are cold-cache and serialised: compare SHARES" % tag)
 out.append("# launches  total_ms  avg_us  share  kernel")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
