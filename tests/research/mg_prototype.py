@@ -4,7 +4,7 @@ assembly to build the S16-style test matrix): Jacobi-BiCGSTAB, as prescribed by 
 preconditioned by one geometric-multigrid V-cycle (bilinear transfer on the Mesh.Rectangle hierarchy, Galerkin coarse
 operators R A P, damped-Jacobi smoothing = the SpMV the B200 path already has).  Counts operator applications.
 
-    python scripts/research/mg_prototype.py [elements_per_side = 256]
+    python tests/research/mg_prototype.py [elements_per_side = 256]
 """
 import os
 import sys
