@@ -196,10 +196,11 @@ class LinearSolver(object):
     """Replaces kiltro/FEMSolver.py:335-364 (scipy spsolve) with device Krylov solvers (csrc/krylov.cu).
 
     linear_solver_type: "auto" (CG when the matrix is known symmetric, BiCGSTAB otherwise), "cg", "bicgstab".
-    The reference's ("direct", "lapack") arguments are accepted and mapped to "auto" with the default tolerance."""
+    The reference's ("direct", "lapack") arguments are accepted and mapped to "auto" with the default tolerance.
+    preconditioner (experimental, opt-in): a kiltro_b200.multigrid.GridMultigrid -> BiCGSTAB preconditioned by a V-cycle."""
 
     def __init__(self, linear_solver="iterative", linear_solver_type="auto", tol=1.0e-12, maxiter=None,
-                 check_every=50, raise_on_failure=False):
+                 check_every=50, raise_on_failure=False, preconditioner=None):
         self.is_sparse = True
         self.solver_type = linear_solver
         self.solver_subtype = linear_solver_type if linear_solver_type in ("cg", "bicgstab") else "auto"
@@ -210,6 +211,8 @@ class LinearSolver(object):
         self.raise_on_failure = raise_on_failure
         self.info = None
         self.x0 = None
+        # None: Jacobi (the prescribed method, csrc/krylov.cu).  EXPERIMENTAL opt-in: a kiltro_b200.multigrid.GridMultigrid
+        self.preconditioner = preconditioner
 
     def Solve(self, A, b):
         if not issparse(A):
@@ -222,6 +225,15 @@ class LinearSolver(object):
             return b.clone()
         if b.shape[0] != n:
             raise ValueError("dimension mismatch between A and b")
+        if self.preconditioner is not None:
+            x, self.info = self.preconditioner.solve(A, b, rtol=self.tol, maxiter=int(self.maxiter or 200))
+            if self.info["status"] != 0:
+                msg = "%s stopped after %d iterations with relative residual %.3e (status %d)" % (
+                    self.info["method"], self.info["iterations"], self.info["relative_residual"], self.info["status"])
+                if self.raise_on_failure:
+                    raise _lib.KiltroB200Error(msg)
+                warn(msg)
+            return x
         method = self.solver_subtype
         if method == "auto":
             method = "cg" if A.symmetric else "bicgstab"
