@@ -57,7 +57,7 @@ class _Level(object):
 
 class GridMultigrid(object):
 
-    def __init__(self, mesh, formulation, material, boundary_condition, nu=2, omega=0.8, coarsest=400, max_levels=12):
+    def __init__(self, mesh, formulation, material, boundary_condition, nu=2, omega=0.67, coarsest=400, max_levels=12):
         from .FiniteElements.fused import grid_shape
         if formulation.ndim != 2 or formulation.nvar != 1:
             raise ValueError("GridMultigrid needs a 2-D scalar problem")
@@ -198,6 +198,7 @@ class GridMultigrid(object):
         v, s, t, ph, sh = D.empty(n), D.empty(n), D.empty(n), D.empty(n), D.empty(n)
         rho, bb = dot2(rhat, r)
         status, it, rr = _lib.KB_ENOTCONV, 0, bb
+        history = []
         tol2 = rtol * rtol * bb
         if bb == 0.0:
             status = 0
@@ -225,6 +226,7 @@ class GridMultigrid(object):
             self._axpby(1.0, s, -omega, t, r)
             it += 1
             rho_new, rr = dot2(rhat, r)
+            history.append(math.sqrt(rr / bb) if rr >= 0.0 and bb > 0.0 else float("nan"))
             if not math.isfinite(rr):
                 status = _lib.KB_EBREAKDOWN
                 break
@@ -247,5 +249,5 @@ class GridMultigrid(object):
         info = {"method": "bicgstab+multigrid", "iterations": it, "status": int(status), "vcycles": self.cycles,
                 "levels": len(self.levels), "residual": math.sqrt(max(rt, 0.0)), "rhs_norm": math.sqrt(bb),
                 "relative_residual": math.sqrt(max(rt, 0.0) / bb) if bb > 0 else 0.0,
-                "kernel_launches": int(lib.kb_launch_count() - launches0)}
+                "kernel_launches": int(lib.kb_launch_count() - launches0), "history": history}
         return x, info

@@ -41,3 +41,11 @@ print("multigrid       : solve %.1f ms, %d iterations, %d levels, set-up %.2f s,
       % (fs.timings["solve_ms"], mgs.info["iterations"], mgs.info["levels"], t_setup, mgs.info["kernel_launches"], err,
          mgs.info["relative_residual"], mgs.info["status"],
          mesh.nnodes / (1e-3 * (fs.timings["solve_ms"] + fs.timings["assemble_ms"] + fs.timings["bc_ms"]))), flush=True)
+
+if "sweep" in sys.argv:                                   # residual histories for a few smoother settings
+    for nu, omega in ((2, 0.8), (3, 0.8), (2, 0.67)):
+        mg.nu, mg.omega = nu, omega
+        run(mgs)
+        h = mgs.info["history"]
+        print("nu=%d omega=%.2f: %d iterations, solve %.1f ms, history %s" % (
+            nu, omega, mgs.info["iterations"], fs.timings["solve_ms"], " ".join("%.1e" % v for v in h[:6] + h[-4:])), flush=True)
