@@ -79,3 +79,22 @@ def test_gloo_world2_halo_exchange_and_allreduce():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, 8, 10, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_best_iterate_checkpoint():
+    """The partitioned loops' checkpoint of the best checked iterate (distributed._BestIterate): keeps the iterate with the
+    smallest residual offered, hands it back on restore, and is inert when disabled (short inner solves)."""
+    import torch
+    from kiltro_b200.distributed import _BestIterate
+    x = [torch.zeros(4, dtype=torch.float64), torch.ones(3, dtype=torch.float64)]
+    keep = _BestIterate(x, 10.0)
+    x[0] += 1.0; x[1] += 1.0
+    keep.offer(x, 4.0)                                   # better: stored
+    x[0] += 5.0; x[1] += 5.0
+    keep.offer(x, 7.0)                                   # worse: ignored
+    x[0].fill_(float("nan")); x[1].fill_(float("inf"))   # the iterate gets wrecked
+    assert keep.restore(x) == 4.0
+    assert torch.equal(x[0], torch.full((4,), 1.0, dtype=torch.float64)) and torch.equal(x[1], torch.full((3,), 2.0, dtype=torch.float64))
+    off = _BestIterate(x, 1.0, enabled=False)
+    off.offer(x, 0.5)
+    assert off.x is None and off.restore(x) != off.restore(x)          # NaN: nothing to restore from
