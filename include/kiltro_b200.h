@@ -27,6 +27,7 @@ extern "C" {
 #define KB_EWORKSPACE (-3)   /* caller-provided workspace too small */
 #define KB_EBREAKDOWN (-4)   /* Krylov breakdown (rho, omega or p.Ap vanished / non-finite) */
 #define KB_ENOTCONV   (-5)   /* maxiter reached without meeting the tolerance */
+#define KB_ESTAGNATED (-6)   /* the iteration stalled with ||b - A x|| more than 10x above rtol ||b|| (fp64 floor or lost recurrence) */
 
 /* advection term of the element matrix */
 #define KB_MODE_REFERENCE  0 /* scalar broadcast, what Temperature/TemperaturePG compute: VariationalPrinciple.py:152,156,164-173 */
@@ -42,10 +43,15 @@ typedef struct kb_material { double k, rho, c_v, area, q; } kb_material;
 /* result record of the Krylov solvers */
 typedef struct kb_solve_info {
     int32_t iterations;      /* iterations performed */
-    int32_t status;          /* 0 converged, KB_ENOTCONV, KB_EBREAKDOWN */
-    double  residual;        /* final ||b - A x||_2 (recurrence residual of the preconditioned system, see krylov.cu) */
-    double  rhs_norm;        /* ||b||_2 of the system actually iterated on */
+    int32_t status;          /* 0: TRUE residual ||b - A x||_2 <= rtol ||b||_2 of the caller's (unscaled) system, or <= 10 rtol
+                                ||b||_2 with attainable_accuracy = 1; else KB_ENOTCONV, KB_EBREAKDOWN, KB_ESTAGNATED */
+    double  residual;        /* final TRUE ||b - A x||_2, recomputed from the returned x in the caller's system */
+    double  rhs_norm;        /* ||b||_2 of the caller's system */
     int64_t kernel_launches; /* kernels launched by the call */
+    int32_t attainable_accuracy; /* 1: restarts from the true residual stopped improving it (fp64 rounding floor) */
+    int32_t restarts;        /* restart cycles taken (0 = the first cycle converged and was confirmed) */
+    int32_t failed_step;     /* kb_transient_run: 1-based time step whose inner solve failed and stopped the loop (0 = none) */
+    int32_t steps_done;      /* kb_transient_run: time steps completed */
 } kb_solve_info;
 
 const char *kb_error_string(int code);

@@ -87,6 +87,7 @@ class FEMSolver(object):
         post_process.SetMesh(mesh)
         post_process.SetSolution(TotalSol)
         post_process.solver_info = self.solver_info
+        post_process.converged = getattr(self, "converged", True)
         return post_process
 
     # ------------------------------------------------------------------------------------------ FEMSolver.py:73-153
@@ -122,6 +123,7 @@ class FEMSolver(object):
         nnodes, nvar = mesh.nnodes, formulation.nvar
         if TotalSol is None:
             TotalSol = D.zeros((nnodes, nvar, LoadIncrement))
+        self.converged = True
         NodalFluxes = -LoadFactor * NeumannFluxes                                            # :171
         AppliedDirichletInc = LoadFactor * boundary_condition.applied_dirichlet_device       # :172
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -152,6 +154,13 @@ class FEMSolver(object):
             self.timings = {"assemble_ms": ev[0].elapsed_time(ev[1]), "bc_ms": ev[1].elapsed_time(ev[2]),
                             "solve_ms": ev[2].elapsed_time(ev[3])}
             self.solver_info = getattr(solver, "info", None)
+            # the reference's direct solve cannot fail silently; an iterative one can: the verdict travels with the result
+            # (PostProcess.converged / .solver_info) and is announced even when the solver object swallowed it
+            st = self.solver_info.get("status", 0) if isinstance(self.solver_info, dict) else 0
+            if st != 0:
+                self.converged = False
+                warn("FEMSolver: the linear solve of load increment %d did not converge (status %d, relative residual %.3e)"
+                     % (Increment, st, self.solver_info.get("relative_residual", float("nan"))))
             _say("Finished load increment " + str(Increment) + " for linear problem. Solver time is",
                  self.timings["solve_ms"] * 1e-3)
         if LoadIncrement > 1:                                                                # :225-226
@@ -245,15 +254,20 @@ class LinearSolver(object):
         fn = lib.kb_cg_solve if method == "cg" else lib.kb_bicgstab_solve
         _lib.check(fn(n, A.nnz, D.ptr(A.indptr), D.ptr(A.indices), D.ptr(A.data), D.ptr(b), D.ptr(x), self.tol,
                       maxiter, self.check_every, D.ptr(ws), nbytes, info, D.stream_ptr()))
+        # residual / rhs_norm: TRUE ||b - A x||_2 and ||b||_2 of the system handed over (unscaled), recomputed from x
         self.info = {"method": method, "iterations": int(info.iterations), "status": int(info.status),
                      "residual": float(info.residual), "rhs_norm": float(info.rhs_norm),
                      "relative_residual": float(info.residual) / float(info.rhs_norm) if info.rhs_norm > 0 else 0.0,
-                     "kernel_launches": int(info.kernel_launches)}
+                     "tol": self.tol, "attainable_accuracy": bool(info.attainable_accuracy),
+                     "restarts": int(info.restarts), "kernel_launches": int(info.kernel_launches)}
         if info.status != 0:
-            msg = "%s stopped after %d iterations with relative residual %.3e (status %d: %s)" % (
-                method, info.iterations, self.info["relative_residual"], info.status,
+            msg = "%s stopped after %d iterations with relative residual %.3e > tol %.1e (status %d: %s)" % (
+                method, info.iterations, self.info["relative_residual"], self.tol, info.status,
                 lib.kb_error_string(int(info.status)).decode())
             if self.raise_on_failure:
                 raise _lib.KiltroB200Error(msg)
             warn(msg)
+        elif info.attainable_accuracy:
+            warn("%s reached the attainable accuracy of fp64: relative residual %.3e (requested %.1e, accepted within 10x)"
+                 % (method, self.info["relative_residual"], self.tol))
         return x

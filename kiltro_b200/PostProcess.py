@@ -21,6 +21,7 @@ class PostProcess(object):
         self._sol_h = None
         self.sol_device = None
         self.solver_info = None
+        self.converged = True          # False when an iterative solve behind this result did not meet its tolerance
 
     def SetMesh(self, mesh):
         self.mesh = mesh

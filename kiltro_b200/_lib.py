@@ -23,7 +23,8 @@ class kb_peer_ctx(ctypes.Structure):
 
 class kb_solve_info(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("residual", F64), ("rhs_norm", F64),
-                ("kernel_launches", I64)]
+                ("kernel_launches", I64), ("attainable_accuracy", ctypes.c_int32), ("restarts", ctypes.c_int32),
+                ("failed_step", ctypes.c_int32), ("steps_done", ctypes.c_int32)]
 
 
 KB_MODE_REFERENCE = 0
@@ -32,6 +33,7 @@ KB_OP_ROBIN = 1
 KB_OP_CHARGALERKIN = 2
 KB_ENOTCONV = -5
 KB_EBREAKDOWN = -4
+KB_ESTAGNATED = -6
 
 # name -> (restype, argtypes); mirrors include/kiltro_b200.h one to one
 SIGNATURES = {

@@ -31,6 +31,7 @@ const char *kb_error_string(int code) {
         case KB_EWORKSPACE: return "kiltro_b200: workspace too small";
         case KB_EBREAKDOWN: return "kiltro_b200: Krylov breakdown";
         case KB_ENOTCONV: return "kiltro_b200: Krylov solver did not converge";
+        case KB_ESTAGNATED: return "kiltro_b200: Krylov solver stagnated above the requested tolerance";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -53,7 +53,8 @@ void prof_collect(bool keep) {
 }
 
 // device scalar slots
-enum { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RES2, S_TOL2, S_AUX0, S_AUX1, S_R0N2, S_WHY, S_COUNT = 16 };   // S_R0N2: <r,r> at the (re)start = |rhat|^2
+enum { S_RHO = 0, S_ALPHA, S_OMEGA, S_BETA, S_RES2, S_TOL2, S_AUX0, S_AUX1, S_R0N2, S_WHY, S_URES2, S_UB2, S_COUNT = 16 };   // S_R0N2: <r,r> at the (re)start = |rhat|^2
+// S_URES2 / S_UB2 (CG only): ||b - A x||^2 and ||b||^2 of the UNSCALED system (the CG recurrence runs on D^-1/2 A D^-1/2)
 
 struct Work {
     double *vals_hat, *scale, *v0, *v1, *v2, *v3, *v4, *v5, *partials, *sc;
@@ -495,6 +496,29 @@ struct FinInit {            // rho = <r,r> ; tol2 = max(rtol^2 <b,b>, tiny) ; do
         if (!(rr > tol2)) { done[0] = isfinite(rr) ? 1 : 2; }
     }
 };
+// CG iterates on the symmetrically scaled system; the verdict (and kb_solve_info) use the residual of the system the
+// caller handed over: r_unscaled = r / scale, b_unscaled = bh / scale  (scale = 1/sqrt(diag)).
+struct BodyUnscaledNorms {  // d0 = ||r / scale||^2 ; d1 = ||bh / scale||^2
+    const double *r, *bh, *scale;
+    __device__ void operator()(int64_t i, double &d0, double &d1) const {
+        const double s = scale[i], ru = r[i] / s, bu = bh[i] / s;
+        d0 += ru * ru; d1 += bu * bu;
+    }
+};
+struct FinInitUnscaled {    // runs right after FinInit: the unscaled residual decides; the recurrence's (scaled) target follows it
+    double *sc; int *done; double rtol2, slack;
+    __device__ void operator()(double ru2, double bu2, double = 0.0, double = 0.0) const {
+        sc[S_URES2] = ru2; sc[S_UB2] = bu2;
+        const double tolu2 = rtol2 * bu2;
+        if (!isfinite(ru2)) { done[0] = 2; return; }
+        if (!(ru2 > tolu2)) { done[0] = 1; return; }
+        if (done[0] == 1) done[0] = 0;                         // converged in the scaled norm only: keep iterating
+        // scaled residual the recurrence has to reach for the unscaled one to meet rtol (ratio of the two norms taken
+        // from the current residual; `slack` < 1 after a cycle that ended short of it)
+        const double t = slack * sc[S_RES2] * (tolu2 / ru2);
+        if (t < sc[S_TOL2]) sc[S_TOL2] = t;
+    }
+};
 struct BodyUnscale {        // x = xh * scale
     const double *xh, *scale; double *x;
     __device__ void operator()(int64_t i, double &, double &) const { x[i] = xh[i] * scale[i]; }
@@ -636,22 +660,33 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
 
     HostState hs;
     double *t = METHOD == 1 ? x : nullptr;   // BiCGSTAB's extra vector borrows the caller's x (rewritten from xh at the end)
-    int total_iters = 0, status = KB_ENOTCONV;
+    int total_iters = 0, status = KB_ENOTCONV, restarts = 0;
     const double rtol2 = rtol * rtol;
     double prev_true = INFINITY;
-    bool recurrence_converged = false;
+    bool recurrence_converged = false, attainable = false;
+    // residual / rhs norms (squared) the verdict is taken on: the caller's system.  BiCGSTAB iterates on A D^-1, whose
+    // residual IS b - A x; CG iterates on D^-1/2 A D^-1/2 and measures the unscaled residual separately.
+    auto res2_of = [&](const HostState &h) { return METHOD == 0 ? h.sc[S_URES2] : h.sc[S_RES2]; };
+    auto b2_of = [&](const HostState &h) { return METHOD == 0 ? h.sc[S_UB2] : h.sc[S_AUX0]; };
     for (int restart = 0; restart < 16 && total_iters < maxiter; ++restart) {
+        restarts = restart;
         // (re)start from the TRUE residual: r = bh - Ahat xh ; p = r ; rhat = r ; rho = <r,r>
         if ((rc = launch_spmv<0>(n, nnz, indptr, indices, w.vals_hat, w, xh, q, nullptr, nullptr, NoFinal{}, s))) return rc;
         if ((rc = launch_vec<1>(n, BodyResidual{bh, q, r, p, METHOD == 1 ? rhat : nullptr},
                                 FinInit{w.sc, w.done, rtol2}, w, nullptr, s))) return rc;
+        if (METHOD == 0)
+            if ((rc = launch_vec<1>(n, BodyUnscaledNorms{r, bh, w.scale},
+                                    FinInitUnscaled{w.sc, w.done, rtol2, restart == 0 ? 1.0 : 0.25}, w, nullptr, s))) return rc;
         if ((rc = read_state(w, &hs, s))) return rc;
-        const double true_rr = hs.sc[S_RES2];
+        const double true_rr = res2_of(hs), tol2 = rtol2 * b2_of(hs);
         if (hs.done[0] == 1) { status = 0; break; }                       // true residual meets the tolerance
         if (hs.done[0] == 2) { status = KB_EBREAKDOWN; break; }           // non-finite residual
-        // attainable accuracy reached: the recurrence converged but fp64 rounding floors ||b - A x|| -- accepted only
-        // near the tolerance (within 1e3 in norm); a recurrence that "converged" on a wrecked iterate is not
-        if (recurrence_converged && !(true_rr < 0.25 * prev_true) && true_rr <= 1.0e6 * hs.sc[S_TOL2]) { status = 0; break; }
+        // attainable accuracy: a whole restart cycle (converged recurrence or breakdown at the rounding floor) did not
+        // bring the TRUE residual down 2x in norm while it already sits within 10x of the tolerance -- fp64 rounding
+        // floors ||b - A x||; reported through info->attainable_accuracy, never silently
+        if (restart > 0 && !(true_rr < 0.25 * prev_true) && true_rr <= 100.0 * tol2) { attainable = true; break; }
+        // a recurrence that converged while the true residual stalls far above the tolerance: stop, report failure
+        if (recurrence_converged && !(true_rr < 0.25 * prev_true) && true_rr <= 1.0e6 * tol2) { attainable = true; break; }
         prev_true = true_rr;
         recurrence_converged = false;
         bool stop = false;
@@ -690,20 +725,31 @@ int krylov_solve(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *i
         k_clear_done<<<1, 1, 0, s>>>(w.done);
         KB_LAUNCH_CHECK();
     }
-    // true residual of the scaled system with the final iterate (for BiCGSTAB this is b - A x itself)
+    // true residual with the final iterate (for BiCGSTAB the scaled system's residual is b - A x itself; CG adds the
+    // unscaled norms)
     if ((rc = launch_spmv<0>(n, nnz, indptr, indices, w.vals_hat, w, xh, q, nullptr, nullptr, NoFinal{}, s))) return rc;
     if ((rc = launch_vec<1>(n, BodyResidual{bh, q, r, p, nullptr}, FinInit{w.sc, w.iter + 2, rtol2}, w, nullptr, s))) return rc;
+    if (METHOD == 0)
+        if ((rc = launch_vec<1>(n, BodyUnscaledNorms{r, bh, w.scale}, FinInitUnscaled{w.sc, w.iter + 2, rtol2, 1.0}, w, nullptr, s))) return rc;
     if ((rc = launch_vec<0>(n, BodyUnscale{xh, w.scale, x}, NoFin{}, w, nullptr, s))) return rc;
     if ((rc = read_state(w, &hs, s))) return rc;
+    const double res2 = res2_of(hs), b2 = b2_of(hs);
     info->iterations = total_iters;
-    info->residual = sqrt(hs.sc[S_RES2]);
-    info->rhs_norm = sqrt(hs.sc[S_AUX0]);
-    if (hs.sc[S_AUX0] == 0.0 && hs.sc[S_RES2] == 0.0) status = 0;                          // b = 0 -> x = 0
-    // the iterate is judged by its TRUE residual: within a factor 10 of the requested tolerance counts as converged
-    // (restarts that end in a breakdown at the fp64 floor, or a recurrence residual that drifted, do not change that)
-    if (status != 0 && hs.sc[S_RES2] <= 100.0 * rtol2 * hs.sc[S_AUX0]) status = 0;
-    if (status == 0 && !(hs.sc[S_RES2] <= 1.0e6 * rtol2 * hs.sc[S_AUX0]) && hs.sc[S_AUX0] > 0.0)
-        status = isfinite(hs.sc[S_RES2]) ? KB_ENOTCONV : KB_EBREAKDOWN;   // never report success on a wrecked iterate
+    info->residual = sqrt(res2);
+    info->rhs_norm = sqrt(b2);
+    info->restarts = restarts;
+    // Verdict, on the TRUE residual of the caller's system only:
+    //   0              ||b - A x|| <= rtol ||b||, or <= 10 rtol ||b|| with attainable_accuracy = 1 (fp64 floor, see above)
+    //   KB_ESTAGNATED  the iteration stalled above that
+    //   KB_EBREAKDOWN  non-finite residual / breakdown that the restarts did not cure
+    //   KB_ENOTCONV    maxiter (or the restart budget) exhausted
+    if (b2 == 0.0 && res2 == 0.0) status = 0;                                              // b = 0 -> x = 0
+    else if (!isfinite(res2)) status = KB_EBREAKDOWN;
+    else if (res2 <= rtol2 * b2) status = 0;
+    else if (attainable) {
+        info->attainable_accuracy = 1;
+        status = (res2 <= 100.0 * rtol2 * b2) ? 0 : KB_ESTAGNATED;
+    } else if (status == 0) status = KB_ENOTCONV;
     info->status = status;
     info->kernel_launches = g_kb_launches - launches0;
     return 0;
@@ -774,7 +820,7 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
     int snap = 0, rc;
     int64_t total_iters = 0;
     double worst = 0.0;
-    int status = 0;
+    int status = 0, failed_step = 0, steps_done = 0;
     // snapshot of the initial state (step index 0)
     while (snap < nsnap && h_snap_steps[snap] == 0) {
         KB_CUDA(cudaMemcpyAsync(d_snapshots + (size_t)snap * ndof, d_T, sizeof(double) * (size_t)ndof,
@@ -796,8 +842,16 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
                                  step > 1);
         if (rc) return rc;
         total_iters += info.iterations;
-        if (info.status != 0) status = info.status;
         if (info.rhs_norm > 0 && info.residual / info.rhs_norm > worst) worst = info.residual / info.rhs_norm;
+        if (info.status != 0 || !isfinite(info.residual)) {
+            // a failed inner solve stops the time loop: T keeps the last good state (step - 1), later snapshots are
+            // not written, and the caller learns which step failed
+            status = info.status != 0 ? info.status : KB_EBREAKDOWN;
+            failed_step = step;
+            if (!isfinite(info.residual)) worst = NAN;
+            break;
+        }
+        steps_done = step;
         // T^{n+1}
         if ((rc = launch_vec<0>(ndof, BodyStep{d_renum, d_applied, y, d_T, dt}, NoFin{}, wv, nullptr, s))) return rc;
         while (snap < nsnap && h_snap_steps[snap] == step) {
@@ -812,6 +866,8 @@ extern "C" int kb_transient_run(int64_t ndof, int64_t nnz, const int32_t *d_indp
     h_info->status = status;
     h_info->residual = worst;           // worst relative residual of the per-step solves
     h_info->rhs_norm = 1.0;
+    h_info->failed_step = failed_step;
+    h_info->steps_done = steps_done;
     h_info->kernel_launches = g_kb_launches - launches0;
     return 0;
 }

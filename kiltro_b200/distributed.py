@@ -715,7 +715,7 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
     peer = exchange == "peer" and not sym and len(systems) == 1 and isinstance(comm, DistComm) and comm.world > 1
     if peer and getattr(systems[0], "peer_region", None) is None:
         systems[0].peer_region = PeerRegion(systems[0].part, comm.dist)
-    info = {"iterations": 0, "status": _lib.KB_ENOTCONV, "restarts": 0}
+    info = {"iterations": 0, "status": _lib.KB_ENOTCONV, "restarts": 0, "attainable_accuracy": False}
     tol2_factor = rtol * rtol
     prev_true = float("inf")
     rr_true, bb_true = float("nan"), 0.0
@@ -730,7 +730,6 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         else:
             c = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, budget, check_every)
         info["iterations"] += c["iterations"]
-        info["relative_residual"] = c["relative_residual"]
         info["status"] = c["status"]
         info["restarts"] = cycle
         rr_true, bb_true = _true_residual(systems, comm, Ahat, b, x)
@@ -740,21 +739,30 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if rr_true <= tol2_factor * bb_true:
             info["status"] = 0
             break
-        # attainable accuracy: the recurrence converged, the true residual stalls within 1e3 (in norm) of the tolerance
-        if c["status"] == 0 and not (rr_true < 0.25 * prev_true) and rr_true <= 1.0e6 * tol2_factor * bb_true:
+        # attainable accuracy (same rule as csrc/krylov.cu): a whole cycle did not halve the TRUE residual norm while it
+        # sits within 10x of the tolerance, or the recurrence converged while the true residual stalls
+        stalled = not (rr_true < 0.25 * prev_true)
+        if (cycle > 0 and stalled and rr_true <= 100.0 * tol2_factor * bb_true) or \
+                (c["status"] == 0 and stalled and rr_true <= 1.0e6 * tol2_factor * bb_true):
+            info["attainable_accuracy"] = True
             break
         if c["status"] == _lib.KB_ENOTCONV and cycle_iterations is None:
             break                                          # maxiter exhausted
         prev_true = rr_true
     info["exchange"] = "peer" if peer else ("nccl" if isinstance(comm, DistComm) else "local")
     info["method"] = "cg" if sym else "bicgstab"
-    info["true_relative_residual"] = (rr_true / bb_true) ** 0.5 if bb_true > 0 else 0.0
-    # same verdict rules as the single-GPU driver: a true residual within 10x of the tolerance counts as converged,
-    # success is never reported on an iterate whose true residual is more than 1e3 (in norm) above it
-    if info["status"] != 0 and rr_true <= 100.0 * tol2_factor * bb_true:
+    # the verdict is taken on the TRUE residual only (for CG: of the symmetrically scaled system the loop iterates on)
+    info["relative_residual"] = info["true_relative_residual"] = (rr_true / bb_true) ** 0.5 if bb_true > 0 else 0.0
+    if bb_true == 0.0 and rr_true == 0.0:
         info["status"] = 0
-    if info["status"] == 0 and bb_true > 0 and not (rr_true <= 1.0e6 * tol2_factor * bb_true):
-        info["status"] = _lib.KB_ENOTCONV if np.isfinite(rr_true) else _lib.KB_EBREAKDOWN
+    elif not np.isfinite(rr_true):
+        info["status"] = _lib.KB_EBREAKDOWN
+    elif rr_true <= tol2_factor * bb_true:
+        info["status"] = 0
+    elif info["attainable_accuracy"]:
+        info["status"] = 0 if rr_true <= 100.0 * tol2_factor * bb_true else _lib.KB_ESTAGNATED
+    elif info["status"] == 0:
+        info["status"] = _lib.KB_ENOTCONV
     sols = []
     for s, sc, xh in zip(systems, scales, x):
         out = D.empty(s.part.n_loc)
@@ -778,6 +786,7 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
     rhs = [D.zeros(s.part.n_loc) for s in systems]
     total = 0
     worst = 0.0
+    status, failed_step, steps_done = 0, 0, 0
     for step in range(nsteps):
         comm.halo_exchange(parts, T)
         for k, s in enumerate(systems):
@@ -787,10 +796,23 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
                 _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(rhs[k]), D.ptr(scales[k]), D.ptr(rhs[k]), D.stream_ptr()))
         info = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, rhs, yh, rtol, maxiter, check_every,
                                                        checkpoint=False)   # short inner solves: no restart
-        total += info["iterations"]; worst = max(worst, info["relative_residual"])
+        total += info["iterations"]
+        rel = info["relative_residual"]
+        if info["status"] != 0 or not np.isfinite(rel):
+            # a failed inner solve stops the time loop: T keeps the last good state and the caller learns which step failed
+            status = info["status"] if info["status"] != 0 else _lib.KB_EBREAKDOWN
+            failed_step = step + 1
+            worst = rel if not np.isfinite(rel) else max(worst, rel)
+            break
+        worst = max(worst, rel)
+        steps_done = step + 1
         for k, s in enumerate(systems):
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(yh[k]), D.ptr(scales[k]), D.ptr(kt[k]), D.stream_ptr()))   # y = D^-1 yhat
             _lib.check(s.lib.kb_transient_update(s.part.n_loc, D.ptr(s.bc.renum), D.ptr(s.bc.applied_dirichlet_device),
                                                  D.ptr(kt[k]), float(dt), D.ptr(T[k]), D.stream_ptr()))
+    if status != 0:
+        from warnings import warn
+        warn("partitioned transient loop stopped at step %d of %d: inner solve failed (status %d)" % (failed_step, nsteps, status))
     return [Tk[s.part.own()].clone() for Tk, s in zip(T, systems)], {"iterations": total, "worst_relative_residual": worst,
-                                                                     "method": "cg" if sym else "bicgstab"}
+                                                                     "method": "cg" if sym else "bicgstab", "status": status,
+                                                                     "failed_step": failed_step, "steps_done": steps_done}

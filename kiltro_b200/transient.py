@@ -86,7 +86,19 @@ def run_transient(fem_solver, function_spaces, formulation, solver, mesh, materi
                                     info, D.stream_ptr()))
     fem_solver.solver_info = {"method": "cg" if symmetric else "bicgstab", "iterations": int(info.iterations),
                               "status": int(info.status), "worst_relative_residual": float(info.residual),
-                              "kernel_launches": int(info.kernel_launches), "dt": dt, "theta": theta, "steps": nincr - 1}
+                              "kernel_launches": int(info.kernel_launches), "dt": dt, "theta": theta, "steps": nincr - 1,
+                              "steps_done": int(info.steps_done), "failed_step": int(info.failed_step)}
+    fem_solver.converged = info.status == 0
+    if info.status != 0:
+        # the loop stops at the first failed inner solve (T keeps the last good state, later snapshots are not written)
+        msg = "transient loop stopped at step %d of %d: inner %s solve failed (status %d: %s)" % (
+            info.failed_step, nincr - 1, "cg" if symmetric else "bicgstab", info.status,
+            lib.kb_error_string(int(info.status)).decode())
+        if getattr(solver, "raise_on_failure", False):
+            raise _lib.KiltroB200Error(msg)
+        from warnings import warn
+        warn(msg)
+        out[[k for k, i in enumerate(order) if int(snaps[i]) > int(info.steps_done)]] = float("nan")
     # undo the sort, return (nnodes*nvar, nsnap) like TotalSol[:,0,[...]]
     res = torch.empty_like(out)
     for k, i in enumerate(order):

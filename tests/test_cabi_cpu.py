@@ -113,7 +113,7 @@ def test_product_never_imports_oracle():
                     assert "import oracle" not in src and "from oracle" not in src, f
     # bench.py touches it only inside its CPU legs (cpu_baseline / --impl reference)
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert src.count("from oracle") == 1 and "def cpu_oracle_run" in "".join(src.split("from oracle")[0].splitlines()[-4:])
+    assert src.count("from oracle") == 1 and "def cpu_oracle_run" in "".join(src.split("from oracle")[0].splitlines()[-6:])
 
 
 def test_function_space_tables_match_reference():
