@@ -411,7 +411,7 @@ template <int DOTS, class Final>
 int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const double *vals,
                     const int32_t *rowblk, double *partials, unsigned int *ticket, const double *x, double *y,
                     const double *dotw, const int *done, Final fin, cudaStream_t s, const int16_t *indices16 = nullptr,
-                    const double *dotw2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr},
+                    const double *dotw2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0},
                     const uint8_t *row_pat = nullptr, const pat_off_t *pat_tab = nullptr, bool pdl = false) {
     const int64_t nblk = num_blocks(nnz);
     if (row_pat != nullptr) {                           // row-pattern form: 8 bytes per non-zero cross HBM
@@ -464,7 +464,7 @@ int launch_spmv(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *in
                 cudaStream_t s, const double *dotw2 = nullptr, bool pdl = false) {
     return launch_spmv_raw<DOTS, Final>(n, nnz, indptr, indices, vals, w.rowblk, w.partials, w.ticket, x, y, dotw, done,
                                         fin, s, w.use16 ? w.cols16 : nullptr, dotw2,
-                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, w.usepat ? w.row_pat : nullptr, w.pat_tab,
+                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}, w.usepat ? w.row_pat : nullptr, w.pat_tab,
                                         pdl);
 }
 
@@ -925,7 +925,7 @@ extern "C" int kb_spmv_dots(int64_t nrows, int64_t nnz, const int32_t *d_indptr,
     const Scratch sc = scratch_of(d_scratch);
     return launch_spmv_raw<1, FinStore>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
                                         d_y, d_w, nullptr, FinStore{d_out2}, (cudaStream_t)stream, d_cols16, nullptr,
-                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, d_row_pat, d_pat_tab);
+                                        kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}, d_row_pat, d_pat_tab);
 }
 // 4-dot form: out4 = {<w,y>, <y,y>, <w2,y>, <w2,w>}  (merged BiCGSTAB update)
 struct FinStore4 { double *out; __device__ void operator()(double a, double b, double c, double d) const { out[0] = a; out[1] = b; out[2] = c; out[3] = d; } };
@@ -941,7 +941,7 @@ extern "C" int kb_spmv_dots4(int64_t nrows, int64_t nnz, const int32_t *d_indptr
     const Scratch sc = scratch_of(d_scratch);
     return launch_spmv_raw<2, FinStore4>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
                                          d_y, d_w, nullptr, FinStore4{d_out4}, (cudaStream_t)stream, d_cols16, d_w2,
-                                         kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}, d_row_pat, d_pat_tab);
+                                         kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}, d_row_pat, d_pat_tab);
 }
 // x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; out2[0] = <r,r>   (s is passed in r)
 extern "C" int kb_bicgstab_update_p(int64_t n, const double *d_alpha, const double *d_omega, const double *d_beta,

@@ -28,10 +28,12 @@ struct Ctx {
     unsigned long long *ctrl[MAXP];       // control block of every rank as mapped into this process (ctrl[rank] = own)
 };
 
-struct Wait {                             // flags (in the own control block) a kernel waits for before it starts
-    const unsigned long long *f0, *f1;
+struct Wait {                             // flags (in the own control block) an SpMV waits for before it gathers x
+    const unsigned long long *f0, *f1;    // f0: raised by the rank below (halo row under the first owned mesh row), f1: above
     unsigned long long val;
     unsigned long long *err;
+    int edge;                             // rows per mesh row: only the CTAs whose rows touch the first / last `edge` rows of
+                                          // the view read halo entries and have to wait (0 = every CTA waits)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -59,6 +61,17 @@ __device__ __forceinline__ void wait_flags(const Wait &w) {
     if (!spin_until_ge(w.f0, w.val) || !spin_until_ge(w.f1, w.val)) {
         if (w.err) *w.err = 1ull;
     }
+}
+// The CTA owning rows [r_first, r_last) of an nrows-row view waits only for the halo rows it will read: rows of the first
+// mesh row reference the halo row below (f0), rows of the last mesh row the one above (f1); every other CTA starts at once.
+__device__ __forceinline__ void wait_flags_rows(const Wait &w, int r_first, int r_last, int nrows) {
+    if (w.f0 == nullptr && w.f1 == nullptr) return;
+    if (w.edge <= 0) { wait_flags(w); return; }
+    if (r_last <= r_first) return;
+    bool ok = true;
+    if (r_first < w.edge) ok = spin_until_ge(w.f0, w.val) && ok;
+    if (r_last > nrows - w.edge) ok = spin_until_ge(w.f1, w.val) && ok;
+    if (!ok && w.err) *w.err = 1ull;
 }
 
 // post this rank's partial sums of event `ev` to every rank (one thread)

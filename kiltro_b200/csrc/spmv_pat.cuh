@@ -42,7 +42,7 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
            const pat_off_t *__restrict__ pat_tab, const double *__restrict__ vals, const int32_t *__restrict__ rowblk,
            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
            double *__restrict__ partials, unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
-           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}) {
+           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}) {
     // pwait: halo flags raised by the neighbouring ranks (peer.cuh); the kernel does not touch x before they are up
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GRAN = 2;                                // values per 16 bytes (bulk-copy granule)
@@ -67,7 +67,8 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
     }
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;             // uniform over the grid
-    if (threadIdx.x == 0) kbpeer::wait_flags(pwait);
+    if (threadIdx.x == 0 && (pwait.f0 != nullptr || pwait.f1 != nullptr))
+        kbpeer::wait_flags_rows(pwait, __ldg(rowblk + b_begin), __ldg(rowblk + b_end), __ldg(rowblk + nblk));
     __syncthreads();
 
     if (threadIdx.x >= P_CONSUMERS) {

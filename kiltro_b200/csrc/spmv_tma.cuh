@@ -119,7 +119,7 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
            const double *__restrict__ vals, const int32_t *__restrict__ rowblk, const double *__restrict__ x,
            double *__restrict__ y, const double *__restrict__ w, double *__restrict__ partials,
            unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
-           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr}) {
+           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}) {
     // DOTS: 0 none; 1 -> {<w,y>, <y,y>}; 2 -> additionally {<w2,y>, <w2,w>} (the merged BiCGSTAB update, krylov.cu)
     // pwait: halo flags raised by the neighbouring ranks (peer.cuh); the kernel does not touch x before they are up
     if (done != nullptr && *done != 0) return;
@@ -142,7 +142,8 @@ k_spmv_tma(int64_t nblk, const int32_t *__restrict__ indptr, const IDX *__restri
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], T_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        kbpeer::wait_flags(pwait);
+        if (pwait.f0 != nullptr || pwait.f1 != nullptr)
+            kbpeer::wait_flags_rows(pwait, __ldg(rowblk + b_begin), __ldg(rowblk + b_end), __ldg(rowblk + nblk));
     }
     __syncthreads();
 
