@@ -340,105 +340,262 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ N > 1: partitioned
+def strip_problem(K, torch, nps, world, rank, uniform=False):
+    """Rank `rank`'s strip of the weak-scaling case: global mesh nps x (nps * world) nodes on [0,1] x [0,world] (S16 per
+    GPU), through the ordinary API with a StripPartition.  uniform=True: noise-free velocity (closed-form check)."""
+    nxn, nyn = nps, nps * world
+    part = K.StripPartition(nxn, nyn, world, rank)
+    mesh = K.Mesh(element_type="quad")
+    mesh.Rectangle(lower_left_point=(0.0, 0.0), upper_right_point=(1.0, float(world)), nx=nxn - 1, ny=nyn - 1, partition=part)
+    if uniform:
+        vel = torch.zeros((part.n_loc, 2), dtype=torch.float64, device="cuda")
+        vel[:, 0] = PECLET * 2.0 * (nxn - 1)
+    else:
+        vel = synthetic_velocity(mesh.global_node_ids(), nxn)            # hash of the GLOBAL node id: same field for every N
+    flags = torch.full((part.n_loc, 1), float("nan"), dtype=torch.float64, device="cuda")
+    idx = torch.arange(part.nrows_loc, device="cuda") * nxn
+    flags[idx, 0] = 100.0
+    flags[idx + nxn - 1, 0] = 500.0
+    material = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+    return part, mesh, vel, flags, material
+
+
+def closed_form_check(K, torch, dist, world, rank, exchange, nps=1024, rows_per_rank=256):
+    """Correctness evidence for the exchange kernels on THIS box and THIS rank count: a short uniform-velocity solve
+    (nps x rows_per_rank*world nodes, cell Peclet 0.45) through the same partitioned API, against the exact discrete
+    solution T_i = T_0 + dT (r^i - 1)/(r^n - 1), r = (1+Pe)/(1-Pe), which does not depend on y."""
+    import math
+    nxn, nyn = nps, rows_per_rank * world
+    part = K.StripPartition(nxn, nyn, world, rank)
+    mesh = K.Mesh(element_type="quad")
+    mesh.Rectangle((0.0, 0.0), (1.0, float(nyn - 1) / (nxn - 1)), nxn - 1, nyn - 1, partition=part)     # square cells
+    vel = torch.zeros((part.n_loc, 2), dtype=torch.float64, device="cuda"); vel[:, 0] = PECLET * 2.0 * (nxn - 1)
+    flags = torch.full((part.n_loc, 1), float("nan"), dtype=torch.float64, device="cuda")
+    idx = torch.arange(part.nrows_loc, device="cuda") * nxn
+    flags[idx, 0] = 100.0; flags[idx + nxn - 1, 0] = 500.0
+    material = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    fs = K.FEMSolver(analysis_type="steady", partition="rows", exchange=exchange, verbose=False)
+    solver = K.LinearSolver(linear_solver_type="bicgstab", tol=1e-12, check_every=50, maxiter=50000)
+    out = fs.Solve(formulation=K.HeatAdvectionDiffusion(mesh, velocity=vel), mesh=mesh, material=material,
+                   boundary_condition=bc, solver=solver)
+    n = nxn - 1
+    lr = math.log((1 + PECLET) / (1 - PECLET))
+    i = torch.arange(nxn, dtype=torch.float64, device="cuda")
+    exact = 100.0 + 400.0 * torch.exp((i - n) * lr) * (-torch.expm1(-i * lr)) / (-math.expm1(-n * lr))
+    T = out.sol_device[:, 0, 0].reshape(-1, nxn)
+    err = (T - exact[None, :]).abs().max().reshape(1) / 500.0
+    if world > 1:
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    if getattr(fs, "_psys", None) is not None:
+        from kiltro_b200 import distributed as KD
+        KD.close_peer_regions([fs._psys])
+    return {"closed_form_max_error": float(err.item()), "closed_form_ok": bool(float(err.item()) < 1e-8),
+            "closed_form_case": "%dx%d nodes, uniform velocity, rtol 1e-12, %d iterations, status %d" % (
+                nxn, nyn, fs.solver_info["iterations"], fs.solver_info["status"])}
+
+
 def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier):
-    """Weak scaling of the same metric: the global mesh is nps x (nps*N) nodes (S16 per GPU), split into N row blocks;
-    every SpMV exchanges one halo mesh row per neighbour and every dot product is all-reduced over NCCL."""
+    """Weak scaling of the same metric: the global mesh is nps x (nps*N) nodes (S16 per GPU), split into N row blocks, one
+    per rank, through the drop-in API -- FEMSolver(partition="rows").Solve(...) on the rank's strip.  Every SpMV needs one
+    halo mesh row per neighbour and every dot product a sum over the ranks; with exchange="peer" (default) the kernels
+    move both through NVLink peer memory themselves."""
     from kiltro_b200 import distributed as KD
     nps = args.nodes_per_side
     nxn, nyn = nps, nps * world
-    rect = ((0.0, 0.0), (1.0, float(world)), nxn - 1, nyn - 1)
-    h = 1.0 / (nxn - 1)
-    U = 0.45 * 2.0 / h
-    part = KD.StripPartition(nxn, nyn, world, rank)
-
-    def velocity_fn(pts):
-        # the hash field of the GLOBAL node id: identical on both sides of a partition cut and for every N
-        gid = part.j_first * nxn + torch.arange(part.n_loc, dtype=torch.int64, device=pts.device)
-        return synthetic_velocity(gid, nxn)
-
-    def dirichlet_fn(pts):
-        f = torch.full((pts.shape[0], 1), float("nan"), dtype=torch.float64, device=pts.device)
-        idx = torch.arange(part.nrows_loc, device=pts.device) * nxn
-        f[idx, 0] = 100.0
-        f[idx + nxn - 1, 0] = 500.0
-        return f
-
-    material = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
-    comm = KD.DistComm()
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    sysm = KD.build_local_system(part, rect, material, K.HeatAdvectionDiffusion, velocity_fn, dirichlet_fn)
-    torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
+    part, mesh, vel, flags, material = strip_problem(K, torch, nps, world, rank)
+    form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    fs = K.FEMSolver(analysis_type="steady", partition="rows", exchange=args.exchange, verbose=False)
+    solver = K.LinearSolver(linear_solver="iterative", linear_solver_type="bicgstab", tol=args.rtol,
+                            check_every=args.check_every, maxiter=args.maxiter or 100000)
 
     def step():
-        KD.reassemble(sysm)
-        return KD.solve_steady([sysm], comm, rtol=args.rtol, maxiter=args.maxiter or 100000,
-                               check_every=min(args.check_every, 25), method="bicgstab", exchange=args.exchange)
+        return fs.Solve(formulation=form, mesh=mesh, material=material, boundary_condition=bc, solver=solver)
 
-    for _ in range(args.warmup):
-        sols, info = step()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = step()                                              # first call: symbolic phase + peer mappings (reported as setup)
+    torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
+    for _ in range(max(0, args.warmup - 1)):
+        out = step()
     sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = lib.kb_launch_count()
     e0.record()
+    phase = {"assemble_ms": 0.0, "bc_ms": 0.0, "solve_ms": 0.0}
     for _ in range(args.steps):
-        sols, info = step()
+        out = step()
+        for k in phase:
+            phase[k] += fs.timings[k]
     e1.record()
     barrier()
     launches = lib.kb_launch_count() - launches0
     clocks = sampler.stop()
+    info = dict(fs.solver_info)
     tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     ndof = nxn * nyn
     value = ndof * args.steps / (ms * 1e-3)
-    # e2e: every step uploads the rank's inputs from pinned host memory (reference array formats: float64 points /
-    # velocity / flags, int64 connectivity) and reads the owned part of the solution back to pinned host memory
-    h_in = KD.host_inputs(sysm)
-    h_sol = torch.empty(part.n_own, dtype=torch.float64).pin_memory()
-    h2d = 0
+    solve_ms = torch.tensor([phase["solve_ms"] / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(solve_ms, op=dist.ReduceOp.MAX)
 
-    def e2e_step():
-        nbytes = KD.refresh_inputs_from_host(sysm, *h_in)
-        sols, info = step()
-        h_sol.copy_(sols[0], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return nbytes, info
+    # ---- verify (outside the timed region): (a) the true residual of the timed solution recomputed through a DIFFERENT
+    # exchange path (NCCL halo exchange + plain SpMV on the unscaled operator + all-reduce); (b) a short closed-form solve
+    verify = None
+    if args.verify:
+        rel = KD.residual_check(fs._psys, KD.DistComm(), out.sol_device[:, 0, 0].contiguous())
+        verify = {"true_relative_residual": rel, "rtol": args.rtol, "residual_ok": bool(rel <= 10.0 * args.rtol),
+                  "note": "||b - A x|| / ||b|| of the timed solution on A' = [Kff 0; 0 I] (unscaled), recomputed with an NCCL "
+                          "halo exchange + plain SpMV + all-reduce, i.e. independently of the peer-memory kernels that "
+                          "produced x; closed_form_*: a short uniform-velocity solve through the same API and exchange "
+                          "against the exact discrete solution"}
+        verify.update(closed_form_check(K, torch, dist, world, rank, args.exchange))
+    if info["status"] != 0:
+        raise SystemExit("bench.py: the timed partitioned solve did not converge (status %d)" % info["status"])
 
-    h2d, info_e = e2e_step()                                 # warm-up
-    barrier(); t0 = time.perf_counter()
-    for _ in range(max(1, args.e2e_steps)):
-        h2d, info_e = e2e_step()
-    barrier(); wall = time.perf_counter() - t0
-    nb = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(nb, op=dist.ReduceOp.SUM)
-    t2 = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_steps = max(1, args.e2e_steps)
+    # ---- e2e: every step uploads the rank's inputs from pinned host memory in the reference's array formats (float64
+    # points / velocity / flags, int64 connectivity), goes through the same API call and reads the owned solution back
+    e2e = None
+    if args.e2e_steps > 0:
+        pin = lambda t: t.cpu().pin_memory()
+        h_pts, h_el = pin(mesh.device_points()), pin(mesh.device_elements().to(torch.int64))
+        h_vel, h_flags = pin(vel), pin(flags)
+        h_sol = torch.empty((part.n_own, 1, 1), dtype=torch.float64).pin_memory()
+        h2d = (h_pts.numel() + h_el.numel() + h_vel.numel() + h_flags.numel()) * 8
+
+        def e2e_step():
+            m = K.Mesh(element_type="quad")
+            m.set_arrays(h_pts, h_el, partition=part)                # host -> device inside
+            f = K.HeatAdvectionDiffusion(m, velocity=h_vel)
+            b = K.BoundaryCondition(); b.SetDirichletCriteria(lambda: h_flags)
+            o = fs.Solve(formulation=f, mesh=m, material=material, boundary_condition=b, solver=solver)
+            h_sol.copy_(o.sol_device, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return o
+
+        e2e_step()                                               # warm-up
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier(); wall = time.perf_counter() - t0
+        nb = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        t2 = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": ndof * args.e2e_steps / float(t2.item()), "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
+               "d2h_bytes_per_step": int(ndof * 8), "steps": args.e2e_steps,
+               "ms_per_step": float(t2.item()) / args.e2e_steps * 1e3, "iterations": fs.solver_info["iterations"],
+               "note": "every rank uploads its strip (points, int64 connectivity, velocity, flags) from pinned host memory, "
+                       "calls FEMSolver(partition='rows').Solve and reads its owned solution back, inside the timed "
+                       "region; bytes are summed over the ranks"}
     if rank == 0:
+        cfg = gpu_config(nps, world, args.rtol, True)
+        peer = info.get("exchange") == "peer"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "S16 per GPU: synthetic 2D structured quad mesh %dx%d nodes (%d DOF total), steady "
-                                       "convection-diffusion (consistent Galerkin, cell Pe 0.45 + 10%% noise), "
-                                       "Jacobi-BiCGSTAB rtol %.0e, pattern cached" % (nxn, nyn, ndof, args.rtol),
-                           "ndof_per_gpu": nxn * nps,
-                           "parallelism": "row-block partition x%d; per SpMV one halo mesh row per neighbour, per dot product a "
-                                          "P-way sum: %s" % (world, "written/summed by the kernels through NVLink peer memory "
-                                          "(NCCL only for the convergence check every 25 iterations)"
-                                          if info.get("exchange") == "peer" else "NCCL send/recv + all-reduce"),
-                           "l2_policy": "inputs far larger than the 126 MB L2", "rtol": args.rtol},
+                "dtype": "f64", "data": "synthetic", "config": cfg,
+                "parallelism": "row-block partition x%d through FEMSolver(partition='rows'); per SpMV one halo mesh row per "
+                               "neighbour, per dot product a P-way sum: %s" % (
+                                   world, "written / summed by the kernels through NVLink peer memory (no collective call and no "
+                                   "host round trip inside an iteration)" if peer else "NCCL send/recv + all-reduce"),
                 "solver": {"method": info["method"], "iterations": info["iterations"],
-                           "relative_residual": info["relative_residual"], "status": info["status"]},
-                "t_setup_ms": t_setup * 1e3, "roofline": None, "cpu_baseline": None,
-                "e2e": {"value": ndof * e2e_steps / float(t2.item()), "unit": UNIT,
-                        "h2d_bytes_per_step": int(nb.item()), "d2h_bytes_per_step": int(nxn * nyn * 8), "steps": e2e_steps,
-                        "iterations": info_e["iterations"],
-                        "note": "every rank uploads its strip (points, int64 connectivity, velocity, flags) from pinned "
-                                "host memory and reads its owned solution back, inside the timed region; bytes are "
-                                "summed over the ranks"},
+                           "relative_residual": info["relative_residual"], "status": info["status"],
+                           "attainable_accuracy": info.get("attainable_accuracy"), "restarts": info.get("restarts"),
+                           "exchange": info.get("exchange"),
+                           "ms_per_iteration": float(solve_ms.item()) / max(1, info["iterations"])},
+                "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+                "verify": verify, "t_setup_ms": t_setup * 1e3, "roofline": None, "cpu_baseline": None, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks}
         emit(line)
+    KD.close_peer_regions([fs._psys])
+
+
+# ------------------------------------------------------------------------------------------------ config 5: transient
+def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, barrier):
+    """BASELINE configs[4] / SURVEY 8(d) config 5: 4000 x (4000 N) nodes (128 M DOF at N = 8), theta-method time loop
+    (theta = 0: the reference's intended forward Euler with a consistent-mass solve per step, FEMSolver.py:253-297),
+    row-block partitioned, through FEMSolver(analysis_type='transient', partition='rows').  A bench "step" = `--time-steps`
+    time steps of the loop; value = DOF * time steps / s."""
+    from kiltro_b200 import distributed as KD
+    nps = args.nodes_per_side
+    nxn, nyn = nps, nps * world
+    part = K.StripPartition(nxn, nyn, world, rank)
+    mesh = K.Mesh(element_type="quad")
+    mesh.Rectangle((0.0, 0.0), (1.0, float(world)), nxn - 1, nyn - 1, partition=part)
+    h = 1.0 / (nxn - 1)
+    vel = torch.zeros((part.n_loc, 2), dtype=torch.float64, device="cuda"); vel[:, 0] = PECLET * 2.0 / h
+    flags = torch.full((part.n_loc, 1), float("nan"), dtype=torch.float64, device="cuda")
+    idx = torch.arange(part.nrows_loc, device="cuda") * nxn
+    flags[idx + nxn - 1, 0] = 0.0
+    T0 = torch.full((part.n_loc, 1), 200.0, dtype=torch.float64, device="cuda")
+    material = K.FourierConduction(2, k=1.0, area=1.0, density=1.0, heat_capacity_v=1.0, q=0.0)
+    form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags); bc.SetInitialConditions(lambda: T0)
+    dt = 0.1 * h * h / 2.0                                    # FEMSolver.py:138-144 on the uniform mesh (rho c_v = k = 1)
+    nt = args.time_steps
+    fs = K.FEMSolver(analysis_type="transient", partition="rows", exchange=args.exchange, number_of_increments=nt + 1,
+                     theta=args.theta, time_step=dt, verbose=False)
+    solver = K.LinearSolver(tol=args.rtol, maxiter=2000)
+
+    def step():
+        return fs.Solve(formulation=form, mesh=mesh, material=material, boundary_condition=bc, solver=solver)
+
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = step()
+    torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
+    for _ in range(max(0, args.warmup - 1)):
+        out = step()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.kb_launch_count()
+    e0.record()
+    loop_ms = 0.0
+    for _ in range(args.steps):
+        out = step()
+        loop_ms += fs.timings["solve_ms"]
+    e1.record()
+    barrier()
+    launches = lib.kb_launch_count() - launches0
+    clocks = sampler.stop()
+    info = dict(fs.solver_info)
+    t = torch.tensor([e0.elapsed_time(e1), loop_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, loop_ms = float(t[0].item()), float(t[1].item())
+    if info["status"] != 0:
+        raise SystemExit("bench.py: the transient loop failed (status %d at step %d)" % (info["status"], info["failed_step"]))
+    T = out.sol_device[:, 0, 0]
+    rng = torch.stack([T.min(), -T.max()])
+    if world > 1:
+        dist.all_reduce(rng, op=dist.ReduceOp.MIN)
+    ndof = nxn * nyn
+    if rank == 0:
+        line = {"metric": "transient DOF*steps/s, 2D conv-diff theta-method (config 5)", "value": ndof * nt * args.steps / (ms * 1e-3),
+                "unit": "DOF*steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config 5: synthetic 2D structured quad mesh %dx%d nodes (%d DOF), transient "
+                                       "convection-diffusion, theta = %g, %d time steps per bench step (assembly of K and M + "
+                                       "boundary conditions + the whole time loop), inner Jacobi-%s rtol %.0e" % (
+                                           nxn, nyn, ndof, args.theta, nt, info["method"].upper(), args.rtol),
+                           "ndof": ndof, "ndof_per_gpu": nxn * nps, "theta": args.theta, "time_steps": nt, "dt": dt,
+                           "l2_policy": "operators (2 x 1.15 GB + vectors per GPU) far larger than the 126 MB L2"},
+                "time_loop": {"ms_per_time_step": loop_ms / args.steps / nt, "krylov_iterations_per_time_step":
+                              info["iterations"] / nt, "method": info["method"], "exchange": info.get("exchange"),
+                              "worst_relative_residual": info["worst_relative_residual"], "status": info["status"],
+                              "dof_steps_per_s_loop_only": ndof * nt / (loop_ms / args.steps * 1e-3)},
+                "verify": {"T_min": float(rng[0].item()), "T_max": float(-rng[1].item()),
+                           "note": "bounded by the initial / boundary data up to the explicit scheme's small overshoot; parity "
+                                   "of the partitioned loop against the single-GPU loop: tests/test_gpu_parity.py::"
+                                   "test_peer_partitioned_transient_matches_single_gpu"},
+                "t_setup_ms": t_setup * 1e3, "roofline": None, "cpu_baseline": None, "e2e": None,
+                "gpu_launches": int(launches), "clocks": clocks}
+        emit(line)
+    if getattr(fs, "_psys", None) is not None:
+        KD.close_peer_regions([fs._psys])
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -448,6 +605,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="steady", choices=["steady", "transient"],
+                    help="steady: the headline metric (BASELINE configs[3]); transient: config 5 (theta-method time loop)")
+    ap.add_argument("--theta", type=float, default=0.0, help="--workload transient: theta of the time scheme")
+    ap.add_argument("--time-steps", type=int, default=50, help="--workload transient: time steps per bench step")
     ap.add_argument("--nodes-per-side", type=int, default=4000)
     ap.add_argument("--rtol", type=float, default=1.0e-10)
     ap.add_argument("--check-every", type=int, default=100)
@@ -497,6 +658,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "transient":
+        run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if world > 1:
         run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier)
         dist.destroy_process_group()

@@ -27,6 +27,7 @@ extern "C" {
 #define KB_EWORKSPACE (-3)   /* caller-provided workspace too small */
 #define KB_EBREAKDOWN (-4)   /* Krylov breakdown (rho, omega or p.Ap vanished / non-finite) */
 #define KB_ENOTCONV   (-5)   /* maxiter reached without meeting the tolerance */
+#define KB_EPEER      (-7)   /* a peer-memory wait timed out (a rank fell out of the partitioned iteration) */
 #define KB_ESTAGNATED (-6)   /* the iteration stalled with ||b - A x|| more than 10x above rtol ||b|| (fp64 floor or lost recurrence) */
 
 /* advection term of the element matrix */
@@ -348,16 +349,53 @@ int kb_peer_open(const unsigned char *h_handle64, void **d_ptr);
 int kb_peer_close(void *d_ptr);
 int kb_peer_free(void *d_ptr);
 int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *stream);           /* 0 ok, 1/2: a wait timed out */
-int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, const int16_t *d_cols16,
-                 const uint8_t *d_row_pat, const int16_t *d_pat_tab, const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y, const double *d_w, const double *d_w2,
-                 const kb_peer_ctx *ctx, uint64_t event, int wait_vec, uint64_t wait_seq, void *d_scratch, void *stream);
-int kb_peer_bicgstab_s(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho,
-                       const double *d_v, double *d_r, double *d_alpha_out, double *d_dn_dst, double *d_up_dst,
-                       uint64_t halo_seq, void *d_scratch, void *stream);
-int kb_peer_bicgstab_update_p(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho_in,
-                              double *d_rho_out, const double *d_alpha, const double *d_t, const double *d_v, double *d_x,
-                              double *d_r, double *d_p, double *d_dn_dst, double *d_up_dst, uint64_t halo_seq,
-                              double *d_out2, void *d_scratch, void *stream);
+int kb_peer_clear_error(const kb_peer_ctx *ctx, void *stream);
+
+/* One rank's share of a partitioned system: the mapped control blocks, the rank's exchanged vectors inside its region
+ * (full local vectors: [halo row below | owned rows | halo row above]; 0 = p, 1 = r -- the SpMV inputs of the Krylov loops --
+ * 2 = T of the time loop), the neighbours' halo slots of each, and the running event / halo sequence numbers (the calls
+ * advance them; every rank makes the same calls, so they stay equal across ranks). */
+typedef struct kb_peer_part {
+    kb_peer_ctx ctx;
+    int64_t n_loc, n_own, own_off, nxn;   /* local / owned DOFs, first owned entry, DOFs per mesh row (= halo row length) */
+    void *d_vec[3];
+    void *d_dn_dst[3];                    /* halo-ABOVE slot of rank-1 for each vector (NULL on rank 0) */
+    void *d_up_dst[3];                    /* halo-BELOW slot of rank+1 (NULL on the last rank) */
+    uint64_t ev;
+    uint64_t hseq[3];
+} kb_peer_part;
+/* Owned-row view of the rank's local CSR (columns in local numbering).  d_cols16 / d_row_pat_own + d_pat_tab optional
+ * (kb_make_cols16 / kb_make_row_patterns); d_indptr_own = indptr + own_off, d_row_pat_own = row_pat + own_off. */
+typedef struct kb_peer_op {
+    int64_t nnz_own;
+    const int32_t *d_indptr_own, *d_indices;
+    const int16_t *d_cols16;
+    const uint8_t *d_row_pat_own;
+    const int16_t *d_pat_tab;
+    const double  *d_vals;                /* the operator the loop iterates on (already Jacobi-scaled) */
+    const int32_t *d_rowblk;              /* kb_spmv_partition of the owned-row view */
+} kb_peer_op;
+/* Partitioned Jacobi-Krylov solves of the scaled system  Ahat xhat = bhat  (extends LinearSolver.Solve, FEMSolver.py:350-364,
+ * to a mesh split into strips): every halo row and every dot product travels through peer memory inside the kernels; the
+ * host reads its own device's state every check_every iterations; restarts from the true residual and verdict as
+ * kb_cg_solve / kb_bicgstab_solve.  d_b_own / d_x_own: owned parts (x: initial guess in, solution out).  d_scale_own (CG,
+ * optional): D^-1/2, so that the verdict is taken on the unscaled residual.  Returns KB_EPEER when a wait timed out. */
+size_t kb_peer_krylov_workspace_bytes(int64_t n_own, int64_t nnz_own);
+int kb_peer_cg_solve(kb_peer_part *part, const kb_peer_op *op, const double *d_b_own, double *d_x_own,
+                     const double *d_scale_own, double rtol, int maxiter, int check_every, void *d_workspace,
+                     size_t workspace_bytes, kb_solve_info *h_info, void *stream);
+int kb_peer_bicgstab_solve(kb_peer_part *part, const kb_peer_op *op, const double *d_b_own, double *d_x_own, double rtol,
+                           int maxiter, int check_every, void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info,
+                           void *stream);
+/* Partitioned theta-method loop (extends FEMSolver.TransientSolver, FEMSolver.py:253-297): nsteps steps of
+ *   (M + theta dt Kff) y = Kff T^n + Fm ;  T^{n+1} = T^n - dt y / prescribed values,
+ * T in part->d_vec[2] (owned part; halo rows are exchanged by the kernels).  op->d_vals: the Jacobi-scaled inner operator,
+ * d_scale_own its scaling vector (D^-1/2 when a_symmetric, else D^-1), d_Kff_vals: Kff (unscaled) on the same pattern. */
+size_t kb_peer_transient_workspace_bytes(int64_t n_own, int64_t nnz_own);
+int kb_peer_transient_run(kb_peer_part *part, const kb_peer_op *op, const double *d_Kff_vals, int a_symmetric,
+                          const double *d_scale_own, const double *d_Fm_own, const int32_t *d_renum_own,
+                          const double *d_applied, double dt, int nsteps, double rtol, int maxiter, void *d_workspace,
+                          size_t workspace_bytes, kb_solve_info *h_info, void *stream);
 
 #ifdef __cplusplus
 }

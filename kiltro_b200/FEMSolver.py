@@ -33,7 +33,8 @@ class FEMSolver(object):
                  memory_store_frequency=1, recompute_sparsity_pattern=False,
                  squeeze_sparsity_pattern=False, number_of_increments=None, theta=0.0, time_step=None,
                  time_step_factor=0.1, include_heat_source=False, include_robin=False,
-                 characteristic_galerkin=False, assembly="auto", verbose=True):
+                 characteristic_galerkin=False, assembly="auto", verbose=True, partition=None, comm=None,
+                 exchange="peer"):
         # FEMSolver.py:14-28 (+ the examples' number_of_increments=, examples/transient_2d.py:73-74)
         self.analysis_type = analysis_type
         self.analysis_nature = analysis_nature
@@ -55,6 +56,18 @@ class FEMSolver(object):
         self.characteristic_galerkin = characteristic_galerkin
         self.assembly = assembly                                  # "auto" | "fused" | "fused_generic" | "two_pass"
         self.verbose = verbose
+        # SURVEY 8(e), new capability: partition="rows" -> the mesh handed to Solve() is ONE RANK'S strip of a row-block
+        # partitioned mesh (Mesh.Rectangle(..., partition=StripPartition(...))); formulation / boundary_condition hold the
+        # rank's local nodal data; Solve() returns the rank's OWNED part of the solution.  comm: a
+        # kiltro_b200.distributed communicator (default: torch.distributed's world); exchange: "peer" (halo rows and dot
+        # products through NVLink peer memory inside the kernels) or "nccl" (host-driven loops over the communicator).
+        if partition not in (None, "rows"):
+            raise ValueError("partition must be None or 'rows'")
+        self.partition = partition
+        self.comm = comm
+        self.exchange = exchange
+        self._psys = None
+        self._psys_key = None
         self.sparsity = None
         self.timings = {}
         self.solver_info = None
@@ -97,6 +110,8 @@ class FEMSolver(object):
         function_spaces, solver = self.__checkdata__(material, boundary_condition, formulation, mesh,
                                                      function_spaces, solver)
         self.PrintPreAnalysisInfo(mesh, formulation)
+        if self.partition is not None:
+            return self._solve_partitioned(function_spaces, formulation, mesh, material, boundary_condition, solver)
         self.ComputeSparsityFEM(mesh, formulation)
 
         _say('Assembling the system and acquiring neccessary information for the analysis...')
@@ -166,6 +181,77 @@ class FEMSolver(object):
         if LoadIncrement > 1:                                                                # :225-226
             TotalSol = torch.cumsum(TotalSol, dim=2)
         return TotalSol
+
+    # ------------------------------------------------------------------------------------------ new capability
+    def _solve_partitioned(self, function_spaces, formulation, mesh, material, boundary_condition, solver):
+        """Row-block partitioned Solve(): same stages as the single-GPU path, per rank -- numeric assembly of the strip
+        (owned rows complete, no communication), Dirichlet / Neumann, right-hand side -- then the partitioned
+        Jacobi-CG / BiCGSTAB (kiltro_b200.distributed.solve_steady) or theta-method loop (run_transient).  Returns a
+        PostProcess whose .sol_device is (n_own, nvar, 1): the nodes this rank owns (.partition tells which)."""
+        from . import distributed as KD
+        part = getattr(mesh, "partition", None)
+        if part is None:
+            raise ValueError("FEMSolver(partition='rows') needs a mesh made with Mesh.Rectangle(..., partition=StripPartition(...))")
+        if self.analysis_nature == "nonlinear":
+            raise ValueError("nonlinear analysis is not available (the reference's branch is unreachable too)")
+        comm = self.comm
+        if comm is None:
+            comm = KD.DistComm() if part.world > 1 else KD.LocalComm(1)
+            self.comm = comm
+        if comm.world != part.world:
+            raise ValueError("the communicator has %d ranks, the partition %d" % (comm.world, part.world))
+        transient = self.analysis_type != "steady"
+        key = (part.nxn, part.nyn, part.world, part.rank, mesh.nnodes, mesh.nelem, transient)
+        if self._psys is None or self._psys_key != key:
+            self._psys = KD.local_system_from(mesh, formulation, boundary_condition, self, material, transient)
+            self._psys_key = key
+        else:                                                    # pattern / index forms / peer mappings stay cached
+            KD.attach_objects(self._psys, mesh, formulation, boundary_condition, self, material, transient)
+        sysm = self._psys
+        _say('Assembling the system and acquiring neccessary information for the analysis...')
+        KD.reassemble(sysm)
+        ev = sysm.events + [torch.cuda.Event(enable_timing=True)]
+        method = getattr(solver, "solver_subtype", "auto")
+        tol = getattr(solver, "tol", 1e-12)
+        self.converged = True
+        if not transient:
+            n_glob = part.nxn * part.nyn
+            maxiter = getattr(solver, "maxiter", None) or max(1000, 20 * int(np.sqrt(n_glob)) + 200)
+            sols, info = KD.solve_steady([sysm], comm, rtol=tol, maxiter=int(maxiter),
+                                         check_every=getattr(solver, "check_every", 50), method=method,
+                                         exchange=self.exchange)
+            ev[3].record()
+            TotalSol = sols[0].reshape(part.n_own, formulation.nvar, 1)
+        else:
+            nincr = self.number_of_increments
+            if nincr is None or int(nincr) < 2:
+                raise ValueError("transient analysis needs FEMSolver(number_of_increments=N) with N >= 2")
+            if self.time_step is None:
+                raise ValueError("partitioned transient analysis needs FEMSolver(time_step=dt) (the reference's rule, "
+                                 "FEMSolver.py:138-144, is a global minimum over the elements)")
+            self.time_increment = float(self.time_step)
+            sols, info = KD.run_transient([sysm], comm, self.time_increment, int(nincr) - 1, theta=self.theta, rtol=tol,
+                                          maxiter=getattr(solver, "maxiter", None) or 2000, exchange=self.exchange)
+            ev[3].record()
+            TotalSol = sols[0].reshape(part.n_own, formulation.nvar, 1)       # the last increment only
+        torch.cuda.synchronize()
+        self.timings = {"assemble_ms": ev[0].elapsed_time(ev[1]), "bc_ms": ev[1].elapsed_time(ev[2]),
+                        "solve_ms": ev[2].elapsed_time(ev[3])}
+        info = dict(info)
+        info.setdefault("tol", tol)
+        self.solver_info = info
+        if hasattr(solver, "info"):
+            solver.info = info
+        if info.get("status", 0) != 0:
+            self.converged = False
+            msg = "partitioned %s solve did not converge (status %d, relative residual %.3e)" % (
+                info.get("method", "?"), info["status"], info.get("relative_residual", info.get("worst_relative_residual", float("nan"))))
+            if getattr(solver, "raise_on_failure", False):
+                raise _lib.KiltroB200Error(msg)
+            warn(msg)
+        post = self.__makeoutput__(mesh, TotalSol, formulation)
+        post.partition = part
+        return post
 
     # ------------------------------------------------------------------------------------------ FEMSolver.py:253-297
     def TransientSolver(self, function_spaces, formulation, solver, mesh, material, boundary_condition,

@@ -21,6 +21,7 @@ class Mesh(object):
         self.ndim = None
         self.element_type = element_type
         self.structured_shape = None      # (nx_nodes, ny_nodes) for generator-made meshes (tiling hint only)
+        self.partition = None             # StripPartition when this is one rank's strip (+ halo rows) of a larger mesh
 
     # ---------------------------------------------------------------- host views (lazy)
     @property
@@ -77,9 +78,26 @@ class Mesh(object):
             self.element_type = "line"
         self.structured_shape = (n + 1, 1)
 
-    def Rectangle(self, lower_left_point=(0, 0), upper_right_point=(1, 1), nx=5, ny=5):      # Mesh.py:33-58
+    def Rectangle(self, lower_left_point=(0, 0), upper_right_point=(1, 1), nx=5, ny=5, partition=None):      # Mesh.py:33-58
+        """partition (extension): a kiltro_b200.StripPartition of the (nx+1) x (ny+1) node grid -- the mesh then
+        holds only this rank's mesh rows plus one halo row per interior side, in local numbering (coordinates bit-identical
+        to the global mesh); use with FEMSolver(partition="rows")."""
         nx, ny = int(nx), int(ny)
         lib = _lib.load()
+        if partition is not None:
+            part = partition
+            if nx + 1 != part.nxn or ny + 1 != part.nyn:
+                raise ValueError("partition does not match the rectangle")
+            pts = D.empty((part.n_loc, 2)); el = D.empty(((part.nrows_loc - 1) * nx, 4), torch.int32)
+            _lib.check(lib.kb_mesh_rectangle_strip(float(lower_left_point[0]), float(lower_left_point[1]),
+                                                   float(upper_right_point[0]), float(upper_right_point[1]), nx, ny,
+                                                   part.j_first, part.nrows_loc, D.ptr(pts), D.ptr(el), D.stream_ptr()))
+            self._set_device(pts, el, 2)
+            if self.element_type is None:
+                self.element_type = "quad"
+            self.structured_shape = (part.nxn, part.nrows_loc)
+            self.partition = part
+            return
         pts = D.empty(((nx + 1) * (ny + 1), 2)); el = D.empty((nx * ny, 4), torch.int32)
         _lib.check(lib.kb_mesh_rectangle(float(lower_left_point[0]), float(lower_left_point[1]),
                                          float(upper_right_point[0]), float(upper_right_point[1]), nx, ny,
@@ -89,15 +107,22 @@ class Mesh(object):
             self.element_type = "quad"
         self.structured_shape = (nx + 1, ny + 1)
 
-    def set_arrays(self, points, elements):
+    def global_node_ids(self):
+        """int64 device tensor: global node id of every local node (arange for an unpartitioned mesh)."""
+        off = 0 if self.partition is None else self.partition.j_first * self.partition.nxn
+        return off + torch.arange(self.nnodes, dtype=torch.int64, device="cuda")
+
+    def set_arrays(self, points, elements, partition=None):
         """Adopt caller-provided arrays (NumPy, torch host/pinned or torch CUDA) by uploading them once: the device
-        copies become the source of truth (use the `points` / `elements` setters for host arrays you intend to edit)."""
+        copies become the source of truth (use the `points` / `elements` setters for host arrays you intend to edit).
+        partition: the arrays are one rank's strip (+ halo rows, local numbering) of a partitioned mesh."""
         pts = D.to_device(points, torch.float64)
         el = D.to_device(elements, torch.int32)
         self._set_device(pts, el, int(pts.shape[1]))
         if self.element_type is None:
             self.element_type = "quad" if el.shape[1] == 4 else "line"
         self.structured_shape = None
+        self.partition = partition
 
     def _set_device(self, pts, el, ndim):
         self._points_d, self._elements_d = pts, el
@@ -132,4 +157,5 @@ class Mesh(object):
         m._elements_h = None if self._elements_h is None else self._elements_h.copy()
         m._points_d, m._elements_d = self._points_d, self._elements_d      # immutable on device: share
         m.nnodes, m.nelem, m.ndim, m.structured_shape = self.nnodes, self.nelem, self.ndim, self.structured_shape
+        m.partition = self.partition
         return m

@@ -16,8 +16,9 @@ from .VariationalPrinciple import (VariationalPrinciple, Temperature, Temperatur
 from .PostProcess import PostProcess
 from .sparse import DeviceCSR
 from .device import to_numpy
+from .partition import StripPartition
 
 __all__ = ["Mesh", "BoundaryCondition", "FunctionSpace", "Assemble", "ComputeSparsityPattern",
            "ComputeSparsityPatternDevice", "SparsityPattern", "AssemblyRobinForces", "AssembleCharacteristicGalerkin", "FEMSolver", "LinearSolver", "Material",
            "FourierConduction", "VariationalPrinciple", "Temperature", "TemperaturePG", "HeatDiffusion",
-           "HeatAdvectionDiffusion", "HeatAdvectionDiffusionPG", "PostProcess", "DeviceCSR", "to_numpy"]
+           "HeatAdvectionDiffusion", "HeatAdvectionDiffusionPG", "PostProcess", "DeviceCSR", "to_numpy", "StripPartition"]

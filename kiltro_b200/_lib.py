@@ -21,6 +21,17 @@ class kb_peer_ctx(ctypes.Structure):
     _fields_ = [("nranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("ctrl", ctypes.c_void_p * 8)]
 
 
+class kb_peer_part(ctypes.Structure):
+    _fields_ = [("ctx", kb_peer_ctx), ("n_loc", I64), ("n_own", I64), ("own_off", I64), ("nxn", I64),
+                ("d_vec", ctypes.c_void_p * 3), ("d_dn_dst", ctypes.c_void_p * 3), ("d_up_dst", ctypes.c_void_p * 3),
+                ("ev", ctypes.c_uint64), ("hseq", ctypes.c_uint64 * 3)]
+
+
+class kb_peer_op(ctypes.Structure):
+    _fields_ = [("nnz_own", I64), ("d_indptr_own", c_vp), ("d_indices", c_vp), ("d_cols16", c_vp), ("d_row_pat_own", c_vp),
+                ("d_pat_tab", c_vp), ("d_vals", c_vp), ("d_rowblk", c_vp)]
+
+
 class kb_solve_info(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("residual", F64), ("rhs_norm", F64),
                 ("kernel_launches", I64), ("attainable_accuracy", ctypes.c_int32), ("restarts", ctypes.c_int32),
@@ -34,6 +45,7 @@ KB_OP_CHARGALERKIN = 2
 KB_ENOTCONV = -5
 KB_EBREAKDOWN = -4
 KB_ESTAGNATED = -6
+KB_EPEER = -7
 
 # name -> (restype, argtypes); mirrors include/kiltro_b200.h one to one
 SIGNATURES = {
@@ -118,12 +130,15 @@ SIGNATURES = {
     "kb_peer_close": (I32, [c_vp]),
     "kb_peer_free": (I32, [c_vp]),
     "kb_peer_error": (I32, [ctypes.POINTER(kb_peer_ctx), ctypes.POINTER(I64), c_vp]),
-    "kb_peer_spmv": (I32, [I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_peer_ctx),
-                           ctypes.c_uint64, I32, ctypes.c_uint64, c_vp, c_vp]),
-    "kb_peer_bicgstab_s": (I32, [I64, I64, ctypes.POINTER(kb_peer_ctx), ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                 ctypes.c_uint64, c_vp, c_vp]),
-    "kb_peer_bicgstab_update_p": (I32, [I64, I64, ctypes.POINTER(kb_peer_ctx), ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "kb_peer_clear_error": (I32, [ctypes.POINTER(kb_peer_ctx), c_vp]),
+    "kb_peer_krylov_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
+    "kb_peer_cg_solve": (I32, [ctypes.POINTER(kb_peer_part), ctypes.POINTER(kb_peer_op), c_vp, c_vp, c_vp, F64, I32, I32, c_vp,
+                               ctypes.c_size_t, ctypes.POINTER(kb_solve_info), c_vp]),
+    "kb_peer_bicgstab_solve": (I32, [ctypes.POINTER(kb_peer_part), ctypes.POINTER(kb_peer_op), c_vp, c_vp, F64, I32, I32, c_vp,
+                                     ctypes.c_size_t, ctypes.POINTER(kb_solve_info), c_vp]),
+    "kb_peer_transient_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
+    "kb_peer_transient_run": (I32, [ctypes.POINTER(kb_peer_part), ctypes.POINTER(kb_peer_op), c_vp, I32, c_vp, c_vp, c_vp, c_vp,
+                                    F64, I32, F64, I32, c_vp, ctypes.c_size_t, ctypes.POINTER(kb_solve_info), c_vp]),
 }
 
 _LIB = None

@@ -31,6 +31,7 @@ const char *kb_error_string(int code) {
         case KB_EWORKSPACE: return "kiltro_b200: workspace too small";
         case KB_EBREAKDOWN: return "kiltro_b200: Krylov breakdown";
         case KB_ENOTCONV: return "kiltro_b200: Krylov solver did not converge";
+        case KB_EPEER: return "kiltro_b200: a peer-memory wait timed out (a rank fell out of the partitioned iteration)";
         case KB_ESTAGNATED: return "kiltro_b200: Krylov solver stagnated above the requested tolerance";
         default: break;
     }

@@ -1151,223 +1151,7 @@ extern "C" int kb_scale_matrix(int64_t nrows, const int32_t *d_indptr, const int
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ K9 peer-memory path
-// The partitioned BiCGSTAB iteration with every exchange done by the kernels themselves over NVLink peer memory
-// (peer.cuh): no NCCL call inside the iteration.
-namespace {
-using kbpeer::Ctx;
-
-struct FinPostDots {        // SpMV epilogue: publish this rank's partial sums to every rank
-    Ctx c; unsigned long long ev;
-    __device__ void operator()(double a0, double a1, double a2 = 0.0, double a3 = 0.0) const {
-        kbpeer::post_dots(c, ev, a0, a1, a2, a3);
-    }
-};
-
-struct HaloOut {            // where the first / last owned mesh row of the produced vector goes, and the flags to raise
-    double *dn_dst, *up_dst;              // halo_above slot of rank-1 / halo_below slot of rank+1 (null at the domain ends)
-    unsigned long long *dn_flag, *up_flag;
-    unsigned long long seq;
-    int64_t nxn, n;
-    __device__ __forceinline__ bool store(int64_t i, double v) const {
-        bool remote = false;
-        if (dn_dst != nullptr && i < nxn) { dn_dst[i] = v; remote = true; }
-        if (up_dst != nullptr && i >= n - nxn) { up_dst[i - (n - nxn)] = v; remote = true; }
-        return remote;
-    }
-    __device__ __forceinline__ void raise() const {
-        if (dn_flag != nullptr) kbpeer::st_release_sys(dn_flag, seq);
-        if (up_flag != nullptr) kbpeer::st_release_sys(up_flag, seq);
-    }
-};
-
-struct PBiS {               // alpha = rho / sum_ranks <rhat,v> ; s = r - alpha v ; boundary rows of s go to the neighbours
-    Ctx c; unsigned long long ev; const double *rho, *v; double *r, *alpha_out; HaloOut h;
-    struct S { double a; }; struct L { double r, v; };
-    __device__ S prepare() const {
-        double d[4];
-        kbpeer::collect_dots(c, ev, d);
-        const double a = rho[0] / d[0];
-        if (blockIdx.x == 0) alpha_out[0] = a;
-        return S{a};
-    }
-    __device__ void load(int64_t i, L &l) const { l.r = r[i]; l.v = __ldcs(v + i); }
-    __device__ bool apply(int64_t i, const L &l, const S &s, double &, double &) const {
-        const double sn = l.r - s.a * l.v;
-        r[i] = sn;
-        return h.store(i, sn);
-    }
-    __device__ void finish(double, double) const { h.raise(); }
-};
-struct PBiUpdateP {         // omega, rho_new, beta from the summed 4 dots ; merged x / r / p update ; boundary rows of p out
-    Ctx c; unsigned long long ev; const double *rho_in, *alpha, *t, *v; double *x, *r, *p, *rho_out, *out2; HaloOut h;
-    struct S { double a, om, b; }; struct L { double x, p, s, t, v; };
-    __device__ S prepare() const {
-        double d[4];
-        kbpeer::collect_dots(c, ev, d);
-        const double om = d[1] > 0.0 ? d[0] / d[1] : 0.0;
-        const double rho_new = d[3] - om * d[2];
-        const double a = alpha[0];
-        const double b = (rho_new / rho_in[0]) * (a / om);
-        if (blockIdx.x == 0) rho_out[0] = rho_new;
-        return S{a, om, b};
-    }
-    __device__ void load(int64_t i, L &l) const { l.x = x[i]; l.p = p[i]; l.s = r[i]; l.t = __ldcs(t + i); l.v = __ldcs(v + i); }
-    __device__ bool apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
-        x[i] = l.x + (s.a * l.p + s.om * l.s);
-        const double ri = l.s - s.om * l.t;
-        r[i] = ri;
-        const double pn = ri + s.b * (l.p - s.om * l.v);
-        p[i] = pn;
-        d0 += ri * ri;
-        return h.store(i, pn);
-    }
-    __device__ void finish(double rr, double) const { out2[0] = rr; out2[1] = 0.0; h.raise(); }
-};
-
-template <class Body>
-__global__ void __launch_bounds__(256) k_vec4_peer(int64_t n, Body body, double *__restrict__ partials,
-                                                   unsigned int *__restrict__ ticket) {
-    __shared__ double red[32];
-    __shared__ int s_last;
-    __shared__ typename Body::S s_sc;
-    if (threadIdx.x == 0) s_sc = body.prepare();          // waits for the peers' partial sums, derives the scalars
-    __syncthreads();
-    const typename Body::S sc = s_sc;
-    double d0 = 0.0, d1 = 0.0;
-    bool remote = false;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        typename Body::L l0, l1, l2, l3;
-        body.load(i, l0); body.load(i + stride, l1); body.load(i + 2 * stride, l2); body.load(i + 3 * stride, l3);
-        remote |= body.apply(i, l0, sc, d0, d1); remote |= body.apply(i + stride, l1, sc, d0, d1);
-        remote |= body.apply(i + 2 * stride, l2, sc, d0, d1); remote |= body.apply(i + 3 * stride, l3, sc, d0, d1);
-    }
-    for (; i < n; i += stride) {
-        typename Body::L l0;
-        body.load(i, l0);
-        remote |= body.apply(i, l0, sc, d0, d1);
-    }
-    if (remote) __threadfence_system();                   // this thread's peer stores are out before the block reports
-    d0 = block_sum(d0, red);
-    d1 = block_sum(d1, red);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = d0;
-        partials[gridDim.x + blockIdx.x] = d1;
-        __threadfence();
-        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double a0 = 0.0, a1 = 0.0;
-        for (int k = threadIdx.x; k < (int)gridDim.x; k += 256) {
-            a0 += __ldcg(partials + k);
-            a1 += __ldcg(partials + gridDim.x + k);
-        }
-        a0 = block_sum(a0, red);
-        a1 = block_sum(a1, red);
-        if (threadIdx.x == 0) { __threadfence_system(); body.finish(a0, a1); }
-    }
-}
-
-Ctx make_ctx(const kb_peer_ctx *h) {
-    Ctx c;
-    c.P = h->nranks; c.rank = h->rank;
-    for (int r = 0; r < kbpeer::MAXP; ++r) c.ctrl[r] = (unsigned long long *)h->ctrl[r];
-    return c;
-}
-HaloOut make_halo(const kb_peer_ctx *h, int vec, unsigned long long seq, int64_t nxn, int64_t n, double *dn_dst, double *up_dst) {
-    HaloOut o;
-    o.dn_dst = dn_dst; o.up_dst = up_dst; o.seq = seq; o.nxn = nxn; o.n = n;
-    // rank-1 sees us as its upper neighbour (side 1); rank+1 sees us as its lower neighbour (side 0)
-    o.dn_flag = dn_dst ? (unsigned long long *)h->ctrl[h->rank - 1] + kbpeer::W_HALOFLAG + vec * 2 + 1 : nullptr;
-    o.up_flag = up_dst ? (unsigned long long *)h->ctrl[h->rank + 1] + kbpeer::W_HALOFLAG + vec * 2 + 0 : nullptr;
-    return o;
-}
-}  // namespace
-
-extern "C" int kb_peer_alloc(size_t bytes, void **d_ptr, unsigned char *h_handle64) {
-    if (!d_ptr || !h_handle64 || bytes == 0) return KB_EINVAL;
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    KB_CUDA(cudaMalloc(d_ptr, bytes));
-    KB_CUDA(cudaMemset(*d_ptr, 0, bytes));
-    cudaIpcMemHandle_t hd;
-    KB_CUDA(cudaIpcGetMemHandle(&hd, *d_ptr));
-    memcpy(h_handle64, &hd, 64);
-    return 0;
-}
-extern "C" int kb_peer_open(const unsigned char *h_handle64, void **d_ptr) {
-    if (!d_ptr || !h_handle64) return KB_EINVAL;
-    cudaIpcMemHandle_t hd;
-    memcpy(&hd, h_handle64, 64);
-    KB_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
-    return 0;
-}
-extern "C" int kb_peer_close(void *d_ptr) { if (d_ptr) KB_CUDA(cudaIpcCloseMemHandle(d_ptr)); return 0; }
-extern "C" int kb_peer_free(void *d_ptr) { if (d_ptr) KB_CUDA(cudaFree(d_ptr)); return 0; }
-extern "C" int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *stream) {
-    if (!ctx || !h_err) return KB_EINVAL;
-    unsigned long long e = 0;
-    KB_CUDA(cudaMemcpyAsync(&e, (unsigned long long *)ctx->ctrl[ctx->rank] + kbpeer::W_ERROR, 8, cudaMemcpyDeviceToHost,
-                            (cudaStream_t)stream));
-    KB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    *h_err = (int64_t)e;
-    return 0;
-}
-
-// y = A x on the owned rows; partial dots {<w,y>,<y,y>[,<w2,y>,<w2,w>]} are published to every rank as event `event`.
-// wait_vec: -1 no wait, 0 / 1: wait until the neighbours' halo flags of vector 0 (p) / 1 (r) reached wait_seq.
-extern "C" int kb_peer_spmv(int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
-                            const int16_t *d_cols16, const uint8_t *d_row_pat, const int16_t *d_pat_tab,
-                            const double *d_vals, const int32_t *d_rowblk, const double *d_x, double *d_y,
-                            const double *d_w, const double *d_w2, const kb_peer_ctx *ctx, uint64_t event, int wait_vec,
-                            uint64_t wait_seq, void *d_scratch, void *stream) {
-    if (!d_indptr || !d_indices || !d_vals || !d_rowblk || !d_x || !d_y || !d_w || !ctx || !d_scratch || nrows <= 0 ||
-        ctx->nranks < 1 || ctx->nranks > kbpeer::MAXP)
-        return KB_EINVAL;
-    const Scratch sc = scratch_of(d_scratch);
-    const Ctx c = make_ctx(ctx);
-    kbpeer::Wait w{nullptr, nullptr, wait_seq, c.ctrl[c.rank] + kbpeer::W_ERROR};
-    if (wait_vec >= 0) {
-        if (c.rank > 0) w.f0 = c.ctrl[c.rank] + kbpeer::W_HALOFLAG + wait_vec * 2 + 0;
-        if (c.rank < c.P - 1) w.f1 = c.ctrl[c.rank] + kbpeer::W_HALOFLAG + wait_vec * 2 + 1;
-    }
-    if (d_w2)
-        return launch_spmv_raw<2, FinPostDots>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x,
-                                               d_y, d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, d_w2, w,
-                                               d_row_pat, d_pat_tab);
-    return launch_spmv_raw<1, FinPostDots>(nrows, nnz, d_indptr, d_indices, d_vals, d_rowblk, sc.partials, sc.ticket, d_x, d_y,
-                                           d_w, nullptr, FinPostDots{c, event}, (cudaStream_t)stream, d_cols16, nullptr, w,
-                                           d_row_pat, d_pat_tab);
-}
-extern "C" int kb_peer_bicgstab_s(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event, const double *d_rho,
-                                  const double *d_v, double *d_r, double *d_alpha_out, double *d_dn_dst, double *d_up_dst,
-                                  uint64_t halo_seq, void *d_scratch, void *stream) {
-    if (!ctx || !d_rho || !d_v || !d_r || !d_alpha_out || !d_scratch || n <= 0 || nxn <= 0 || nxn > n) return KB_EINVAL;
-    const Scratch sc = scratch_of(d_scratch);
-    PBiS body{make_ctx(ctx), event, d_rho, d_v, d_r, d_alpha_out, make_halo(ctx, 1, halo_seq, nxn, n, d_dn_dst, d_up_dst)};
-    k_vec4_peer<PBiS><<<kb_grid(kb_cdiv(n, 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(n, body, sc.partials, sc.ticket);
-    KB_LAUNCH_CHECK();
-    return 0;
-}
-extern "C" int kb_peer_bicgstab_update_p(int64_t n, int64_t nxn, const kb_peer_ctx *ctx, uint64_t event,
-                                         const double *d_rho_in, double *d_rho_out, const double *d_alpha,
-                                         const double *d_t, const double *d_v, double *d_x, double *d_r, double *d_p,
-                                         double *d_dn_dst, double *d_up_dst, uint64_t halo_seq, double *d_out2,
-                                         void *d_scratch, void *stream) {
-    if (!ctx || !d_rho_in || !d_rho_out || d_rho_in == d_rho_out || !d_alpha || !d_t || !d_v || !d_x || !d_r || !d_p ||
-        !d_out2 || !d_scratch || n <= 0 || nxn <= 0 || nxn > n)
-        return KB_EINVAL;
-    const Scratch sc = scratch_of(d_scratch);
-    PBiUpdateP body{make_ctx(ctx), event, d_rho_in, d_alpha, d_t, d_v, d_x, d_r, d_p, d_rho_out, d_out2,
-                    make_halo(ctx, 0, halo_seq, nxn, n, d_dn_dst, d_up_dst)};
-    k_vec4_peer<PBiUpdateP><<<kb_grid(kb_cdiv(n, 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(n, body, sc.partials, sc.ticket);
-    KB_LAUNCH_CHECK();
-    return 0;
-}
+#include "krylov_peer.cuh"   // K9 peer-memory solvers (same translation unit: they use the launchers above)
 
 extern "C" int kb_profile_spmv_begin(int every) {
     if (!g_prof.have_events) {

@@ -19,8 +19,9 @@ constexpr int MAXP = 8;
 // control block layout, in 8-byte words
 constexpr int W_DOTS = 0;                 // [parity 2][rank MAXP][4]
 constexpr int W_DOTFLAG = 64;             // [parity 2][rank MAXP]
-constexpr int W_HALOFLAG = 80;            // [vector 2][side 2]   side 0: written by the rank below, 1: by the rank above
-constexpr int W_ERROR = 84;
+constexpr int W_HALOFLAG = 80;            // [vector NVEC][side 2]   side 0: written by the rank below, 1: by the rank above
+constexpr int NVEC = 3;                   // exchanged vectors per region: 0 = p, 1 = r (BiCGSTAB's second SpMV input), 2 = T (transient)
+constexpr int W_ERROR = 96;
 constexpr int CTRL_WORDS = 128;
 
 struct Ctx {
@@ -56,8 +57,14 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned long long *flag, un
     return true;
 }
 
+// once a wait of this rank has timed out, later waits give up at once (the host returns KB_EPEER at its next look)
+__device__ __forceinline__ bool already_failed(const unsigned long long *err) {
+    return err != nullptr && *reinterpret_cast<const volatile unsigned long long *>(err) != 0ull;
+}
+
 __device__ __forceinline__ void wait_flags(const Wait &w) {
     if (w.f0 == nullptr && w.f1 == nullptr) return;
+    if (already_failed(w.err)) return;
     if (!spin_until_ge(w.f0, w.val) || !spin_until_ge(w.f1, w.val)) {
         if (w.err) *w.err = 1ull;
     }
@@ -67,7 +74,7 @@ __device__ __forceinline__ void wait_flags(const Wait &w) {
 __device__ __forceinline__ void wait_flags_rows(const Wait &w, int r_first, int r_last, int nrows) {
     if (w.f0 == nullptr && w.f1 == nullptr) return;
     if (w.edge <= 0) { wait_flags(w); return; }
-    if (r_last <= r_first) return;
+    if (r_last <= r_first || already_failed(w.err)) return;
     bool ok = true;
     if (r_first < w.edge) ok = spin_until_ge(w.f0, w.val) && ok;
     if (r_last > nrows - w.edge) ok = spin_until_ge(w.f1, w.val) && ok;
@@ -91,8 +98,9 @@ __device__ __forceinline__ bool collect_dots(const Ctx &c, unsigned long long ev
     unsigned long long *own = c.ctrl[c.rank];
     bool ok = true;
     d[0] = d[1] = d[2] = d[3] = 0.0;
+    if (already_failed(own + W_ERROR)) ok = false;
     for (int r = 0; r < c.P; ++r) {
-        ok = spin_until_ge(own + W_DOTFLAG + par * MAXP + r, ev) && ok;
+        ok = ok && spin_until_ge(own + W_DOTFLAG + par * MAXP + r, ev);
         const volatile double *slot = reinterpret_cast<const volatile double *>(own + W_DOTS) + (par * MAXP + r) * 4;
         d[0] += slot[0]; d[1] += slot[1]; d[2] += slot[2]; d[3] += slot[3];
     }

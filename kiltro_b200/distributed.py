@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, device as D
+from .partition import StripPartition
 from .MeshGeneration import Mesh
 from .BoundaryCondition import BoundaryCondition
 from .FEMSolver import FEMSolver
@@ -27,44 +28,6 @@ from .FiniteElements.Assembly import Assemble
 # per GPU: no gain (the exchange is short compared with the launch overhead it adds), so it is off by default.
 OVERLAP_HALO = False
 USE_ROW_PATTERNS = True       # row-pattern form of the SpMV (csrc/spmv_pat.cuh) when the local matrix allows it
-
-
-class StripPartition(object):
-    """Mesh rows [j0, j1) of an (nx_nodes x ny_nodes) node grid owned by `rank`, plus one halo row per interior side."""
-
-    def __init__(self, nx_nodes, ny_nodes, world, rank):
-        if world < 1 or not (0 <= rank < world):
-            raise ValueError("bad rank/world")
-        if ny_nodes < 2 * world:
-            raise ValueError("need at least two mesh rows per rank")
-        self.nxn, self.nyn, self.world, self.rank = int(nx_nodes), int(ny_nodes), int(world), int(rank)
-        base, rem = divmod(self.nyn, self.world)
-        self.j0 = rank * base + min(rank, rem)
-        self.j1 = self.j0 + base + (1 if rank < rem else 0)
-        self.hb = 1 if rank > 0 else 0                  # halo row below (owned by rank-1)
-        self.ha = 1 if rank < world - 1 else 0          # halo row above (owned by rank+1)
-        self.j_first = self.j0 - self.hb
-        self.nrows_loc = self.j1 - self.j0 + self.hb + self.ha
-        self.n_own = (self.j1 - self.j0) * self.nxn
-        self.n_loc = self.nrows_loc * self.nxn
-        self.own_off = self.hb * self.nxn
-        self.global_off = self.j0 * self.nxn            # global node id of the first owned node
-
-    # slices of a full local vector
-    def own(self):
-        return slice(self.own_off, self.own_off + self.n_own)
-
-    def first_own_row(self):
-        return slice(self.own_off, self.own_off + self.nxn)
-
-    def last_own_row(self):
-        return slice(self.own_off + self.n_own - self.nxn, self.own_off + self.n_own)
-
-    def halo_below(self):
-        return slice(0, self.nxn) if self.hb else None
-
-    def halo_above(self):
-        return slice(self.own_off + self.n_own, self.own_off + self.n_own + self.nxn) if self.ha else None
 
 
 # ------------------------------------------------------------------------------------------------------ communicators
@@ -259,22 +222,44 @@ def spmv_overlapped(systems, comm, vals, x, y, w, w2, out):
         out[k][0:nd].add_(s.dparts[2][0:nd])
 
 
+def local_system_from(mesh, form, bc, fs, material, transient=False, initial_fn=None):
+    """LocalSystem of one rank from the ordinary API objects: `mesh` made with Mesh.Rectangle(..., partition=...) (or
+    set_arrays(..., partition=...)), `form` / `bc` holding the rank's LOCAL nodal velocity / flags.  Not yet assembled:
+    follow with reassemble()."""
+    part = mesh.partition
+    if part is None:
+        raise ValueError("the mesh carries no StripPartition (Mesh.Rectangle(..., partition=StripPartition(...)))")
+    if mesh.nnodes != part.n_loc:
+        raise ValueError("the mesh has %d nodes, the partition expects %d (owned rows + halo rows)" % (mesh.nnodes, part.n_loc))
+    sysm = LocalSystem(part)
+    sysm.rowblk = None
+    attach_objects(sysm, mesh, form, bc, fs, material, transient, initial_fn)
+    return sysm
+
+
+def attach_objects(sysm, mesh, form, bc, fs, material, transient=False, initial_fn=None):
+    """(Re)binds the API objects of a LocalSystem; the symbolic state (SpMV row partition, index forms, peer mappings, the
+    sparsity pattern cached on fs) is kept -- like the reference's pattern cache, it assumes the same mesh topology."""
+    if mesh.structured_shape is None and getattr(mesh, "partition", None) is not None:
+        mesh.structured_shape = (sysm.part.nxn, sysm.part.nrows_loc)
+    sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material = mesh, form, bc, fs, material
+    sysm.transient, sysm.initial_fn = transient, initial_fn
+    sysm.velocity = form.device_velocity()
+    sysm.flags = D.to_device(bc.dirichlet_flags, torch.float64) if bc.dirichlet_flags is not None else None
+    sysm.symmetric = bool(form.is_symmetric)
+    return sysm
+
+
 def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, dirichlet_fn, neumann_fn=None,
                        transient=False, initial_fn=None):
     """Generates the rank's strip (+ halo rows) of Mesh.Rectangle(*rectangle) on device, assembles it with the ordinary
     single-GPU machinery and prepares the partitioned operators.
     velocity_fn / dirichlet_fn / neumann_fn / initial_fn: callables (points (n_loc, 2) CUDA tensor) -> CUDA tensor
     ((n_loc, 2) velocity or None; (n_loc, 1) flags with NaN = unconstrained; (n_loc, 1) initial field)."""
-    lib = _lib.load()
     (x0, y0), (x1, y1), nx, ny = rectangle
-    if nx + 1 != part.nxn or ny + 1 != part.nyn:
-        raise ValueError("partition does not match the rectangle")
-    pts = D.empty((part.n_loc, 2)); el = D.empty(((part.nrows_loc - 1) * nx, 4), torch.int32)
-    _lib.check(lib.kb_mesh_rectangle_strip(float(x0), float(y0), float(x1), float(y1), nx, ny, part.j_first,
-                                           part.nrows_loc, D.ptr(pts), D.ptr(el), D.stream_ptr()))
     mesh = Mesh(element_type="quad")
-    mesh._set_device(pts, el, 2)
-    mesh.structured_shape = (part.nxn, part.nrows_loc)
+    mesh.Rectangle((x0, y0), (x1, y1), nx, ny, partition=part)
+    pts = mesh.device_points()
     vel = velocity_fn(pts) if velocity_fn is not None else None
     form = formulation_cls(mesh, velocity=vel) if vel is not None else formulation_cls(mesh)
     fs = FEMSolver(analysis_type="transient" if transient else "steady", verbose=False)
@@ -284,12 +269,7 @@ def build_local_system(part, rectangle, material, formulation_cls, velocity_fn, 
     if neumann_fn is not None:
         nfl = neumann_fn(pts)
         bc.SetNeumannCriteria(lambda: nfl)
-    sysm = LocalSystem(part)
-    sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material = mesh, form, bc, fs, material
-    sysm.transient, sysm.initial_fn = transient, initial_fn
-    sysm.velocity, sysm.flags = vel, flags
-    sysm.symmetric = bool(form.is_symmetric)
-    sysm.rowblk = None
+    sysm = local_system_from(mesh, form, bc, fs, material, transient, initial_fn)
     reassemble(sysm)
     return sysm
 
@@ -320,7 +300,12 @@ def reassemble(sysm):
     """Numeric phase of one rank (pattern / tile plan are cached on sysm.fs): assembly, Dirichlet/Neumann, right-hand side."""
     lib, part = sysm.lib, sysm.part
     mesh, form, bc, fs, material = sysm.mesh, sysm.form, sysm.bc, sysm.fs, sysm.material
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    sysm.events = ev
+    ev[0].record()
+    fs.ComputeSparsityFEM(mesh, form)
     K, Flux, M = Assemble(fs, form.function_spaces, form, mesh, material, bc)
+    ev[1].record()
     bc.GetDirichletBoundaryConditions(form, mesh, material, fs)
     Fn = bc.ComputeNeumannFluxes(mesh, material)
     sysm.K, sysm.M = K, M
@@ -361,10 +346,15 @@ def reassemble(sysm):
         F2 = (-F2 - Fn).contiguous()
         sysm.Fm = D.empty(n)
         _lib.check(lib.kb_mask_free(n, D.ptr(bc.renum), D.ptr(F2), D.ptr(sysm.Fm), D.stream_ptr()))
+        T0 = None
         if sysm.initial_fn is not None:
             T0 = sysm.initial_fn(mesh.device_points()).reshape(-1).to(torch.float64).clone()
+        elif bc.initial_field is not None:
+            T0 = D.to_device(bc.initial_field, torch.float64).reshape(-1).clone()
+        if T0 is not None:
             T0 += bc.UpdateFixDoFs(bc.applied_dirichlet_device, n, 1).reshape(-1)
             sysm.T0 = T0
+    ev[2].record()
     return sysm
 
 
@@ -559,123 +549,270 @@ def _align256(x):
 
 
 class PeerRegion(object):
-    """IPC-mapped memory of one rank (control block + the two SpMV input vectors p and r) and the mappings of every
-    other rank's region: what the peer-memory kernels (csrc/peer.cuh) write into.  Needs one process per GPU with NVLink
-    peer access (a B200 HGX node); collectives are only used to exchange the 64-byte IPC handles."""
+    """Peer-mapped memory of one rank -- control block + the three exchanged vectors (p, r, T: full local vectors) -- and
+    the mappings of every other rank's region: what the native partitioned solvers (csrc/krylov_peer.cuh) exchange
+    through.  Two ways to get one:
+      * PeerRegion.create_ipc(part, dist): one process per GPU with NVLink peer access (a B200 HGX node); the collective
+        backend only carries the 64-byte IPC handles, once;
+      * PeerRegion.create_local(parts): all ranks in ONE process on ONE device (plain device memory), driven by one host
+        thread and one stream per rank -- how the kernels' protocol is tested on a single-GPU box.
+    self.part is the kb_peer_part the C entry points take; its event / halo sequence numbers run on across calls."""
     CTRL_BYTES = 1024
+    NVEC = 3
 
-    def __init__(self, part, dist):
-        import ctypes
-        lib = _lib.load()
-        self.part, self.lib = part, lib
+    def __init__(self, part, bases, n_locs, own_offs, n_owns, owner):
+        self.spart, self.lib = part, _lib.load()
         P, rank = part.world, part.rank
         if P > 8:
             raise ValueError("the peer-memory path supports up to 8 ranks")
-        self.stride = _align256(part.n_loc * 8)
-        nbytes = self.CTRL_BYTES + 2 * self.stride
+        self.base, self._owner = bases, owner
+        stride = [_align256(n * 8) for n in n_locs]
+        self.part = _lib.kb_peer_part()
+        kp = self.part
+        kp.ctx.nranks, kp.ctx.rank = P, rank
+        for r in range(P):
+            kp.ctx.ctrl[r] = bases[r]
+        kp.n_loc, kp.n_own, kp.own_off, kp.nxn = part.n_loc, part.n_own, part.own_off, part.nxn
+        kp.ev = 0
+
+        def slot(r, k, offset_elems):
+            return bases[r] + self.CTRL_BYTES + k * stride[r] + 8 * offset_elems
+
+        self.vec = []
+        for k in range(self.NVEC):
+            kp.d_vec[k] = slot(rank, k, 0)
+            # halo-above slot of rank-1 / halo-below slot of rank+1 for vector k
+            kp.d_dn_dst[k] = slot(rank - 1, k, own_offs[rank - 1] + n_owns[rank - 1]) if rank > 0 else None
+            kp.d_up_dst[k] = slot(rank + 1, k, 0) if rank < P - 1 else None
+            kp.hseq[k] = 0
+            self.vec.append(torch.as_tensor(_RawCuda(slot(rank, k, 0), part.n_loc), device="cuda"))
+        self.closed = False
+        self.broken = False
+
+    @staticmethod
+    def nbytes(n_loc):
+        return PeerRegion.CTRL_BYTES + PeerRegion.NVEC * _align256(n_loc * 8)
+
+    @classmethod
+    def create_ipc(cls, part, dist):
+        import ctypes
+        lib = _lib.load()
+        P, rank = part.world, part.rank
         base = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
-        _lib.check(lib.kb_peer_alloc(nbytes, ctypes.byref(base), handle))
-        self.base = [None] * P
-        self.base[rank] = base.value
+        _lib.check(lib.kb_peer_alloc(cls.nbytes(part.n_loc), ctypes.byref(base), handle))
         info = [None] * P
         dist.all_gather_object(info, (bytes(handle.raw), part.n_loc, part.own_off, part.n_own))
+        bases = [None] * P
+        bases[rank] = base.value
         for r in range(P):
             if r != rank:
                 ptr = ctypes.c_void_p()
                 _lib.check(lib.kb_peer_open(info[r][0], ctypes.byref(ptr)))
-                self.base[r] = ptr.value
-        self.ctx = _lib.kb_peer_ctx()
-        self.ctx.nranks, self.ctx.rank = P, rank
-        for r in range(P):
-            self.ctx.ctrl[r] = self.base[r]
-        self.vec = [torch.as_tensor(_RawCuda(self.base[rank] + self.CTRL_BYTES + k * self.stride, part.n_loc), device="cuda")
-                    for k in range(2)]
-
-        def slot(r, k, offset_elems):
-            stride_r = _align256(info[r][1] * 8)
-            return self.base[r] + self.CTRL_BYTES + k * stride_r + 8 * offset_elems
-
-        # halo_above slot of rank-1 / halo_below slot of rank+1, for vector k (0 = p, 1 = r)
-        self.dn_dst = [slot(rank - 1, k, info[rank - 1][2] + info[rank - 1][3]) if rank > 0 else None for k in range(2)]
-        self.up_dst = [slot(rank + 1, k, 0) if rank < P - 1 else None for k in range(2)]
-        self.ev = 0          # dot-product events and halo sequence numbers run on across solves (flags are monotonic)
-        self.hseq = [0, 0]
+                bases[r] = ptr.value
+        reg = cls(part, bases, [i[1] for i in info], [i[2] for i in info], [i[3] for i in info], ("ipc", dist))
         dist.barrier()
+        return reg
+
+    @classmethod
+    def create_local(cls, parts):
+        bufs = [torch.zeros(cls.nbytes(p.n_loc), dtype=torch.uint8, device="cuda") for p in parts]
+        bases = [b.data_ptr() for b in bufs]
+        return [cls(p, bases, [q.n_loc for q in parts], [q.own_off for q in parts], [q.n_own for q in parts], ("local", bufs))
+                for p in parts]
 
     def error(self):
         e = _lib.I64(0)
-        _lib.check(self.lib.kb_peer_error(self.ctx, e, D.stream_ptr()))
+        _lib.check(self.lib.kb_peer_error(self.part.ctx, e, D.stream_ptr()))
         return int(e.value)
 
+    def close(self):
+        """Unmaps the peers' regions and frees the own one (IPC form; collective: every rank must call it)."""
+        if self.closed:
+            return
+        self.closed = True
+        self.vec = []
+        kind, h = self._owner
+        if kind == "ipc":
+            torch.cuda.synchronize()
+            try:
+                h.barrier()                                  # nobody unmaps memory a peer kernel may still write
+            except Exception:
+                pass
+            rank = self.part.ctx.rank
+            for r, bptr in enumerate(self.base):
+                if r != rank and bptr:
+                    self.lib.kb_peer_close(bptr)
+            try:
+                h.barrier()
+            except Exception:
+                pass
+            self.lib.kb_peer_free(self.base[rank])
+        self._owner = (kind, None)
 
-def dist_bicgstab_peer(sysm, comm, region, Ahat, b, x, rtol=1e-10, maxiter=20000, check_every=50):
-    """The partitioned BiCGSTAB iteration with no NCCL call inside: partial dot products and halo rows travel through
-    NVLink peer memory, written by the kernels themselves (kb_peer_*).  One part per process.  NCCL is used for the
-    setup residual and for the ||r|| all-reduce when convergence is looked at (every check_every iterations)."""
-    part, lib, st = sysm.part, sysm.lib, D.stream_ptr
-    n, nxn, off = part.n_own, part.nxn, part.own_off
-    z = lambda: D.zeros(part.n_loc)
-    p, r = region.vec[0], region.vec[1]
-    p.zero_(); r.zero_()
-    rhat, v, t = z(), z(), z()
-    dr = D.zeros(2)
-    rho = [D.zeros(1), D.zeros(1)]; alpha = D.zeros(1)
-    cur = 0
-    own = lambda vec: vec.data_ptr() + 8 * off
-    ip = sysm.indptr.data_ptr() + 4 * off
-    # r = b - A x ; rhat = p = r ; first halo of p through NCCL
-    comm.halo_exchange([part], [x])
-    sysm.spmv(Ahat, x, v)
-    _lib.check(lib.kb_residual(n, own(b), own(v), own(r), D.ptr(dr), D.ptr(sysm.scratch), st()))
-    comm.allreduce([dr])
-    rr0, bb = float(dr[0]), float(dr[1])
-    tol2 = rtol * rtol * bb
-    if not (rr0 > tol2):
-        return {"iterations": 0, "relative_residual": (rr0 / bb) ** 0.5 if bb > 0 else 0.0, "status": 0}
-    rhat.copy_(r); p.copy_(r); rho[0].copy_(dr[0:1])
-    comm.halo_exchange([part], [p])
-    torch.cuda.synchronize(); comm.barrier()            # every rank's setup is complete before peers start writing
-    it, rr, status, first = 0, rr0, 0, True
-    keep = _BestIterate([x], rr0)
-    A = (D.ptr(sysm.indices), D.ptr(Ahat), D.ptr(sysm.rowblk), D.ptr(sysm.cols16))
-    while it < maxiter:
-        for _ in range(min(check_every, maxiter - it)):
-            region.ev += 1                               # v = A p ; {<rhat,v>}
-            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], sysm.pat_ptr(off), D.ptr(sysm.pat_tab), A[1], A[2],
-                                        sysm.xptr(p, off), own(v), own(rhat), None, region.ctx,
-                                        region.ev, -1 if first else 0, region.hseq[0], D.ptr(sysm.scratch), st()))
-            first = False
-            region.hseq[1] += 1                          # alpha ; s = r - alpha v ; boundary rows of s -> neighbours
-            _lib.check(lib.kb_peer_bicgstab_s(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), own(v), own(r), D.ptr(alpha),
-                                              region.dn_dst[1], region.up_dst[1], region.hseq[1], D.ptr(sysm.scratch), st()))
-            region.ev += 1                               # t = A s ; {<s,t>,<t,t>,<rhat,t>,<rhat,s>}
-            _lib.check(lib.kb_peer_spmv(n, sysm.nnz_own, ip, A[0], A[3], sysm.pat_ptr(off), D.ptr(sysm.pat_tab), A[1], A[2],
-                                        sysm.xptr(r, off), own(t), own(r), own(rhat), region.ctx,
-                                        region.ev, 1, region.hseq[1], D.ptr(sysm.scratch), st()))
-            region.hseq[0] += 1                          # omega, rho, beta ; x, r, p ; boundary rows of p -> neighbours
-            _lib.check(lib.kb_peer_bicgstab_update_p(n, nxn, region.ctx, region.ev, D.ptr(rho[cur]), D.ptr(rho[cur ^ 1]),
-                                                     D.ptr(alpha), own(t), own(v), own(x), own(r), own(p), region.dn_dst[0],
-                                                     region.up_dst[0], region.hseq[0], D.ptr(dr), D.ptr(sysm.scratch), st()))
-            cur ^= 1
-            it += 1
-        comm.allreduce([dr])
-        rr = float(dr[0])
-        if region.error():
-            raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
-        if not np.isfinite(rr) or rr > 1.0e10 * rr0:           # non-finite, or diverged 1e5-fold (same bound as krylov.cu)
-            status = _lib.KB_EBREAKDOWN
-            rr = keep.restore([x])
-            break
-        keep.offer([x], rr)
-        if rr <= tol2:
-            break
+    def __del__(self):
+        try:
+            if not self.closed and self._owner[0] == "local":
+                self.closed = True
+        except Exception:
+            pass
+
+
+def _peer_regions(systems, comm):
+    """The systems' PeerRegions (created on first use, kept on the LocalSystem: IPC mappings are expensive)."""
+    if all(getattr(s, "peer_region", None) is not None and not s.peer_region.closed for s in systems):
+        return [s.peer_region for s in systems]
+    if isinstance(comm, DistComm):
+        regs = [PeerRegion.create_ipc(systems[0].part, comm.dist)]
     else:
-        status = _lib.KB_ENOTCONV
-    if status == 0 and rr > tol2:
-        status = _lib.KB_ENOTCONV
-    torch.cuda.synchronize(); comm.barrier()
-    return {"iterations": it, "relative_residual": (rr / bb) ** 0.5 if bb > 0 else 0.0, "status": status}
+        regs = PeerRegion.create_local([s.part for s in systems])
+    for s, r in zip(systems, regs):
+        s.peer_region = r
+    return regs
+
+
+def close_peer_regions(systems):
+    for s in systems:
+        r = getattr(s, "peer_region", None)
+        if r is not None:
+            r.close()
+            s.peer_region = None
+
+
+def _peer_op(sysm, vals):
+    """kb_peer_op of the owned-row view of a LocalSystem with values `vals` (returned with the tensors it points into)."""
+    op = _lib.kb_peer_op()
+    off = sysm.part.own_off
+    op.nnz_own = sysm.nnz_own
+    op.d_indptr_own = sysm.indptr.data_ptr() + 4 * off
+    op.d_indices = sysm.indices.data_ptr()
+    op.d_cols16 = sysm.cols16.data_ptr() if sysm.cols16 is not None else None
+    op.d_row_pat_own = sysm.pat_ptr(off)
+    op.d_pat_tab = sysm.pat_tab.data_ptr() if sysm.pat_tab is not None else None
+    op.d_vals = vals.data_ptr()
+    op.d_rowblk = sysm.rowblk.data_ptr()
+    return op
+
+
+def _run_ranks(systems, comm, fn):
+    """fn(k, system) for every local part: directly for one part per process; one host thread + one stream per part when
+    several ranks share a process / device (their kernels wait for each other, so they must be in flight together)."""
+    if len(systems) == 1:
+        return [fn(0, systems[0])]
+    import threading
+    out, errs = [None] * len(systems), [None] * len(systems)
+    streams = [torch.cuda.Stream() for _ in systems]
+    torch.cuda.synchronize()
+
+    dev = torch.cuda.current_device()
+
+    def work(k):
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(streams[k]):
+                out[k] = fn(k, systems[k])
+                streams[k].synchronize()
+        except BaseException as e:                             # noqa: B902 -- re-raised below
+            errs[k] = e
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(systems))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
+
+
+def _peer_failed_anywhere(comm, regions, rcs):
+    """True when ANY rank saw a peer wait time out (all ranks leave together: ADVICE r01)."""
+    bad = 1.0 if any(rc == _lib.KB_EPEER for rc in rcs) else 0.0
+    if isinstance(comm, DistComm):
+        t = torch.tensor([bad], dtype=torch.float64, device="cuda")
+        comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX, group=comm.group)
+        bad = float(t.item())
+    if bad:
+        for r in regions:
+            r.broken = True
+    return bool(bad)
+
+
+def peer_krylov(systems, comm, Ahat, b, x, scales, sym, rtol, maxiter, check_every):
+    """Native partitioned CG / BiCGSTAB (kb_peer_cg_solve / kb_peer_bicgstab_solve) on the scaled operators.  b, x: full
+    local vectors per part (x: initial guess in / solution out, owned range).  Returns the info dict of rank 0 (every rank
+    computes the same one)."""
+    regions = _peer_regions(systems, comm)
+    if any(r.broken for r in regions):
+        raise _lib.KiltroB200Error("the peer regions of this system are unusable after a timed-out exchange")
+    keep = []
+
+    def one(k, s):
+        lib, part = s.lib, s.part
+        op = _peer_op(s, Ahat[k])
+        nbytes = lib.kb_peer_krylov_workspace_bytes(part.n_own, s.nnz_own)
+        ws = D.empty(nbytes, torch.uint8)
+        info = _lib.kb_solve_info()
+        keep.append((op, ws))
+        if sym:
+            rc = lib.kb_peer_cg_solve(regions[k].part, op, s.own_ptr(b[k]), s.own_ptr(x[k]), s.own_ptr(scales[k]), rtol,
+                                      int(maxiter), int(check_every), D.ptr(ws), nbytes, info, D.stream_ptr())
+        else:
+            rc = lib.kb_peer_bicgstab_solve(regions[k].part, op, s.own_ptr(b[k]), s.own_ptr(x[k]), rtol, int(maxiter),
+                                            int(check_every), D.ptr(ws), nbytes, info, D.stream_ptr())
+        return rc, info
+
+    res = _run_ranks(systems, comm, one)
+    if _peer_failed_anywhere(comm, regions, [r[0] for r in res]):
+        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
+    for rc, _ in res:
+        _lib.check(rc)
+    info = res[0][1]
+    rel = float(info.residual) / float(info.rhs_norm) if info.rhs_norm > 0 else 0.0
+    return {"iterations": int(info.iterations), "status": int(info.status), "relative_residual": rel,
+            "true_relative_residual": rel, "restarts": int(info.restarts),
+            "attainable_accuracy": bool(info.attainable_accuracy), "kernel_launches": int(info.kernel_launches)}
+
+
+def _run_transient_peer(systems, comm, Kff, Ahat, scales, sym, dt, nsteps, rtol, maxiter):
+    regions = _peer_regions(systems, comm)
+    if any(r.broken for r in regions):
+        raise _lib.KiltroB200Error("the peer regions of this system are unusable after a timed-out exchange")
+    for s, reg in zip(systems, regions):
+        reg.vec[2].copy_(s.T0)
+    torch.cuda.synchronize()
+    comm.barrier()
+    keep = []
+
+    def one(k, s):
+        lib, part, off = s.lib, s.part, s.part.own_off
+        op = _peer_op(s, Ahat[k])
+        nbytes = lib.kb_peer_transient_workspace_bytes(part.n_own, s.nnz_own)
+        ws = D.empty(nbytes, torch.uint8)
+        info = _lib.kb_solve_info()
+        keep.append((op, ws))
+        rc = lib.kb_peer_transient_run(regions[k].part, op, D.ptr(Kff[k]), 1 if sym else 0, s.own_ptr(scales[k]),
+                                       s.own_ptr(s.Fm), s.bc.renum.data_ptr() + 4 * off,
+                                       D.ptr(s.bc.applied_dirichlet_device), float(dt), int(nsteps), float(rtol),
+                                       int(maxiter), D.ptr(ws), nbytes, info, D.stream_ptr())
+        return rc, info
+
+    res = _run_ranks(systems, comm, one)
+    if _peer_failed_anywhere(comm, regions, [r[0] for r in res]):
+        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the time loop)")
+    for rc, _ in res:
+        _lib.check(rc)
+    info = res[0][1]
+    if info.status != 0:
+        from warnings import warn
+        warn("partitioned transient loop stopped at step %d of %d: inner solve failed (status %d)" % (
+            info.failed_step, nsteps, info.status))
+    out = [reg.vec[2][s.part.own()].clone() for s, reg in zip(systems, regions)]
+    return out, {"iterations": int(info.iterations), "worst_relative_residual": float(info.residual),
+                 "method": "cg" if sym else "bicgstab", "status": int(info.status), "failed_step": int(info.failed_step),
+                 "steps_done": int(info.steps_done), "exchange": "peer", "kernel_launches": int(info.kernel_launches)}
 
 
 # ------------------------------------------------------------------------------------------------------ drivers
@@ -692,15 +829,37 @@ def _true_residual(systems, comm, Ahat, b, x):
     return float(dres[0][0]), float(dres[0][1])
 
 
+def residual_check(sysm, comm, sol_own):
+    """||b - A' x|| / ||b|| of a returned solution on the UNSCALED operator A' = [Kff 0; 0 I], computed with the host-driven
+    exchange of `comm` (halo rows through the communicator, plain SpMV, all-reduce): an independent check of solutions
+    produced by the peer-memory kernels."""
+    part = sysm.part
+    A = _masked(sysm, 1.0, 0.0, 1)
+    x = D.zeros(part.n_loc)
+    x[part.own()] = sol_own
+    comm.halo_exchange([part], [x])
+    q = D.zeros(part.n_loc)
+    sysm.spmv(A, x, q)
+    d = D.zeros(2)
+    _lib.check(sysm.lib.kb_residual(part.n_own, sysm.own_ptr(sysm.b), sysm.own_ptr(q), sysm.own_ptr(q), D.ptr(d),
+                                    D.ptr(sysm.scratch), D.stream_ptr()))
+    comm.allreduce([d])
+    rr, bb = float(d[0]), float(d[1])
+    return (rr / bb) ** 0.5 if bb > 0 else 0.0
+
+
 def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, method="auto", exchange="nccl",
                  max_restarts=16, cycle_iterations=None):
     """Partitioned steady solve.  Returns (list of owned-solution tensors (n_own,), info).
-    exchange: "nccl" (halo rows and dot products through torch.distributed) or "peer" (BiCGSTAB only, one part per process:
-    the kernels exchange them through NVLink peer memory, no collective inside the iteration).
+    exchange:
+      "peer"  the native loop (csrc/krylov_peer.cuh, CG and BiCGSTAB): halo rows and dot products travel through NVLink
+              peer memory inside the kernels, convergence / breakdown are decided on device, the host looks at its own
+              device's state every check_every iterations -- no collective call inside the solve.  One part per process
+              (DistComm) or several parts in one process on one device (LocalComm: one thread + stream per part);
+      "nccl"  host-driven loops of this module: halo rows and dot products through the communicator (torch.distributed).
     Like the single-GPU driver (csrc/krylov.cu), the iterate is judged by its TRUE residual and the Krylov loop is
-    restarted from it (<= max_restarts times, maxiter iterations in total) when the recurrence broke down / diverged
-    -- from the best checked iterate, see _BestIterate -- or "converged" on an iterate whose true residual does not
-    confirm it.  cycle_iterations caps one cycle (restarted BiCGSTAB/CG; tests use it to exercise the restart path)."""
+    restarted from it when the recurrence broke down / diverged or "converged" on an iterate whose true residual does not
+    confirm it.  cycle_iterations caps one cycle of the host-driven loops (tests use it to exercise the restart path)."""
     mats = [_masked(s, 1.0, 0.0, 1) for s in systems]
     sym = all(s.symmetric for s in systems) if method == "auto" else (method == "cg")
     mode = 1 if sym else 0
@@ -712,9 +871,23 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if mode == 1:
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(s.b), D.ptr(sc), D.ptr(bb), D.stream_ptr()))
         b.append(bb); x.append(D.zeros(s.part.n_loc))
-    peer = exchange == "peer" and not sym and len(systems) == 1 and isinstance(comm, DistComm) and comm.world > 1
-    if peer and getattr(systems[0], "peer_region", None) is None:
-        systems[0].peer_region = PeerRegion(systems[0].part, comm.dist)
+    peer = exchange == "peer" and (isinstance(comm, LocalComm) or (len(systems) == 1 and isinstance(comm, DistComm)))
+    if peer:
+        info = peer_krylov(systems, comm, Ahat, b, x, scales, sym, rtol, maxiter, check_every)
+        info["exchange"] = "peer"
+        info["method"] = "cg" if sym else "bicgstab"
+    else:
+        info = _solve_steady_host_loops(systems, comm, Ahat, b, x, sym, rtol, maxiter, check_every, max_restarts,
+                                        cycle_iterations)
+    sols = []
+    for s, sc, xh in zip(systems, scales, x):
+        out = D.empty(s.part.n_loc)
+        _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(xh), D.ptr(sc), D.ptr(out), D.stream_ptr()))   # x = D^-1 xhat (or D^-1/2)
+        sols.append(out[s.part.own()].clone())
+    return sols, info
+
+
+def _solve_steady_host_loops(systems, comm, Ahat, b, x, sym, rtol, maxiter, check_every, max_restarts, cycle_iterations):
     info = {"iterations": 0, "status": _lib.KB_ENOTCONV, "restarts": 0, "attainable_accuracy": False}
     tol2_factor = rtol * rtol
     prev_true = float("inf")
@@ -724,11 +897,7 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if left <= 0:
             break
         budget = left if cycle_iterations is None else min(left, cycle_iterations)
-        if peer:
-            s0 = systems[0]
-            c = dist_bicgstab_peer(s0, comm, s0.peer_region, Ahat[0], b[0], x[0], rtol, budget, check_every)
-        else:
-            c = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, budget, check_every)
+        c = (dist_cg if sym else dist_bicgstab)(systems, comm, Ahat, b, x, rtol, budget, check_every)
         info["iterations"] += c["iterations"]
         info["status"] = c["status"]
         info["restarts"] = cycle
@@ -749,7 +918,7 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if c["status"] == _lib.KB_ENOTCONV and cycle_iterations is None:
             break                                          # maxiter exhausted
         prev_true = rr_true
-    info["exchange"] = "peer" if peer else ("nccl" if isinstance(comm, DistComm) else "local")
+    info["exchange"] = "nccl" if isinstance(comm, DistComm) else "local"
     info["method"] = "cg" if sym else "bicgstab"
     # the verdict is taken on the TRUE residual only (for CG: of the symmetrically scaled system the loop iterates on)
     info["relative_residual"] = info["true_relative_residual"] = (rr_true / bb_true) ** 0.5 if bb_true > 0 else 0.0
@@ -763,16 +932,14 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         info["status"] = 0 if rr_true <= 100.0 * tol2_factor * bb_true else _lib.KB_ESTAGNATED
     elif info["status"] == 0:
         info["status"] = _lib.KB_ENOTCONV
-    sols = []
-    for s, sc, xh in zip(systems, scales, x):
-        out = D.empty(s.part.n_loc)
-        _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(xh), D.ptr(sc), D.ptr(out), D.stream_ptr()))   # x = D^-1 xhat (or D^-1/2)
-        sols.append(out[s.part.own()].clone())
-    return sols, info
+    return info
 
 
-def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000, check_every=4):
-    """Partitioned theta-method loop (same scheme as kb_transient_run).  Returns (list of owned T^nsteps, info)."""
+def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000, check_every=4, exchange="nccl"):
+    """Partitioned theta-method loop (same scheme as kb_transient_run).  Returns (list of owned T^nsteps, info).
+    exchange="peer": the whole time loop runs inside kb_peer_transient_run (csrc/krylov_peer.cuh) -- halo rows of T and of
+    the inner Krylov vectors and every dot product through peer memory, one or two host round trips per step; "nccl":
+    the host-driven loop below."""
     parts = [s.part for s in systems]
     Kff = [_masked(s, 1.0, 0.0, 0) for s in systems]
     A = [_masked(s, theta * dt, 1.0, 0) for s in systems]                 # M + theta dt Kff  (rows of fixed DOFs: M only)
@@ -780,6 +947,8 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
     mode = 1 if sym else 0
     scales, Ahat = _jacobi_scale(systems, comm, A, mode)
     del A
+    if exchange == "peer" and (isinstance(comm, LocalComm) or (len(systems) == 1 and isinstance(comm, DistComm))):
+        return _run_transient_peer(systems, comm, Kff, Ahat, scales, sym, dt, nsteps, rtol, maxiter)
     T = [s.T0.clone() for s in systems]
     yh = [D.zeros(s.part.n_loc) for s in systems]
     kt = [D.zeros(s.part.n_loc) for s in systems]

@@ -598,6 +598,103 @@ def test_partitioned_transient_matches_single_gpu(theta):
     assert rel_l2(got, ref[:, 0]) < SOL_TOL, (info, fs.solver_info)
 
 
+# ---- the native peer-memory solvers (csrc/krylov_peer.cuh): all ranks of the partition in one process on one device,
+# one host thread + stream per rank, kernels exchanging halo rows / dot products through (here: same-device) peer memory
+@pytest.mark.parametrize("world,sym,nx", [(2, False, 44), (3, False, 63), (4, True, 44), (3, True, 95), (4, False, 63), (8, False, 63)])
+def test_peer_partitioned_steady_matches_single_gpu(world, sym, nx):
+    """kb_peer_cg_solve / kb_peer_bicgstab_solve vs the single-GPU solve of the same global problem (<= 1e-8), and vs the
+    host-driven partitioned loop (iteration counts within a few: same algorithm, different summation order)."""
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(nx, 53, world, False, sym)
+    sols, info = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10, exchange="peer", maxiter=20000)
+    assert info["exchange"] == "peer" and info["method"] == ("cg" if sym else "bicgstab"), info
+    assert info["status"] == 0, info
+    assert info["relative_residual"] <= 1e-12, info
+    solver = K.LinearSolver(tol=1e-13)
+    ref = K.FEMSolver(verbose=False).Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=solver)
+    got = torch.cat(sols).cpu().numpy()
+    assert rel_l2(got, ref.sol.ravel()) < SOL_TOL, (info, solver.info)
+    sols2, info2 = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10, exchange="nccl")
+    assert rel_l2(got, torch.cat(sols2).cpu().numpy()) < SOL_TOL
+    assert abs(info["iterations"] - info2["iterations"]) <= max(20, info2["iterations"] // 5), (info, info2)
+    # a second solve on the same regions (event / halo counters run on)
+    sols3, info3 = KD.solve_steady(systems, comm, rtol=1e-13, check_every=10, exchange="peer")
+    assert info3["status"] == 0 and rel_l2(torch.cat(sols3).cpu().numpy(), got) < 1e-10, info3
+    KD.close_peer_regions(systems)
+
+
+def test_peer_partitioned_solution_is_bitwise_reproducible():
+    """Every rank adds the partial sums in rank order: two runs give the same bits and the same iteration count."""
+    K, KD, systems, comm, _ = _dist_problem(63, 41, 3, False, False)
+    a, ia = KD.solve_steady(systems, comm, rtol=1e-12, check_every=7, exchange="peer")
+    b, ib = KD.solve_steady(systems, comm, rtol=1e-12, check_every=7, exchange="peer")
+    assert ia["iterations"] == ib["iterations"] and ia["status"] == 0
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    KD.close_peer_regions(systems)
+
+
+@pytest.mark.parametrize("theta,sym", [(0.0, False), (0.5, False), (0.5, True)])
+def test_peer_partitioned_transient_matches_single_gpu(theta, sym):
+    """kb_peer_transient_run (time loop + inner CG / BiCGSTAB through peer memory) vs the single-GPU kb_transient_run."""
+    K, KD, systems, comm, (m, form, mat, bc) = _dist_problem(31, 29, 3, True, sym)
+    fs = K.FEMSolver(analysis_type="transient", number_of_increments=13, theta=theta, verbose=False)
+    fs.snapshot_increments = [12]
+    ref = fs.Solve(formulation=form, mesh=m, material=mat, boundary_condition=bc, solver=K.LinearSolver(tol=1e-13))
+    T, info = KD.run_transient(systems, comm, fs.time_increment, 12, theta=theta, rtol=1e-13, exchange="peer")
+    assert info["status"] == 0 and info["steps_done"] == 12 and info["exchange"] == "peer", info
+    assert info["method"] == ("cg" if (theta == 0.0 or sym) else "bicgstab"), info
+    got = torch.cat(T).cpu().numpy()
+    assert rel_l2(got, ref[:, 0]) < SOL_TOL, (info, fs.solver_info)
+    KD.close_peer_regions(systems)
+
+
+def test_partitioned_api_single_rank_equals_ordinary_solve():
+    """FEMSolver(partition="rows") on a one-rank partition (the whole mesh, no halo) goes through the partitioned drivers
+    -- identity rows for prescribed DOFs, native peer loop with P = 1 -- and must reproduce the ordinary Solve(); the
+    transient branch likewise (last increment)."""
+    K = _K()
+    nx, ny = 63, 40
+    part = K.StripPartition(nx + 1, ny + 1, 1, 0)
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (1.0, 0.6), nx, ny, partition=part)
+    m0 = K.Mesh(element_type="quad"); m0.Rectangle((0.0, 0.0), (1.0, 0.6), nx, ny)
+    assert torch.equal(m.device_points(), m0.device_points()) and torch.equal(m.device_elements(), m0.device_elements())
+    assert torch.equal(m.global_node_ids(), torch.arange(m0.nnodes, device="cuda"))
+    P = m.device_points()
+    vel = torch.stack([40.0 * (1.0 + 0.2 * torch.sin(9.0 * P[:, 1])), 5.0 * torch.cos(4.0 * P[:, 0])], dim=1).contiguous()
+    flags = torch.full((m.nnodes, 1), float("nan"), dtype=torch.float64, device="cuda")
+    flags[P[:, 0] == 0.0, 0] = 100.0; flags[P[:, 0] == 1.0, 0] = 500.0
+    mat = K.FourierConduction(2, k=1.0, area=1.0, density=2.0, heat_capacity_v=1.5, q=0.0)
+
+    def solve(mesh, **kw):
+        bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+        fs = K.FEMSolver(verbose=False, **kw)
+        out = fs.Solve(formulation=K.HeatAdvectionDiffusion(mesh, velocity=vel), mesh=mesh, material=mat, boundary_condition=bc,
+                       solver=K.LinearSolver(tol=1e-13))
+        return out, fs
+
+    ref, _ = solve(m0)
+    for ex in ("peer", "nccl"):
+        got, fs = solve(m, partition="rows", exchange=ex)
+        assert fs.solver_info["status"] == 0 and got.partition is part and got.converged, fs.solver_info
+        assert got.sol_device.shape == (m.nnodes, 1, 1)
+        assert rel_l2(got.sol.ravel(), ref.sol.ravel()) < SOL_TOL, (ex, fs.solver_info)
+    with pytest.raises(ValueError):
+        solve(m0, partition="rows")                            # a mesh without a partition
+    # transient
+    T0 = (200.0 + 30.0 * torch.sin(3.0 * P[:, 0] + P[:, 1])).reshape(-1, 1)
+
+    def tsolve(mesh, **kw):
+        bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags); bc.SetInitialConditions(lambda: T0)
+        fs = K.FEMSolver(analysis_type="transient", number_of_increments=9, theta=0.5, time_step=2.0e-5, verbose=False, **kw)
+        fs.snapshot_increments = [8]
+        return fs.Solve(formulation=K.HeatAdvectionDiffusion(mesh, velocity=vel), mesh=mesh, material=mat, boundary_condition=bc,
+                        solver=K.LinearSolver(tol=1e-13)), fs
+
+    tref, _ = tsolve(m0)
+    tgot, fs = tsolve(m, partition="rows")
+    assert fs.solver_info["status"] == 0 and fs.solver_info["steps_done"] == 8, fs.solver_info
+    assert rel_l2(tgot.sol.ravel(), np.asarray(tref)[:, 0]) < SOL_TOL, fs.solver_info
+
+
 # ------------------------------------------------------------------------------------------------- "next" row n1
 def test_load_increments_and_heat_source():
     """cumulative load increments (the reference's loop crashes for L > 1, FEMSolver.py:167-228)
