@@ -191,20 +191,39 @@ int kb_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y
  * ------------------------------------------------------------------------------------------------------- */
 /* :100-122 GetDirichletBoundaryConditions.  flags (ndof) fp64, NaN = free.  d_renum[i] = index of DOF i in the reduced
  * system if free, -1 - (index among the fixed DOFs) otherwise.  d_columns_in / d_columns_out (capacity ndof each, int64
- * like the reference), d_applied (capacity ndof).  h_counts[0]=n_free, h_counts[1]=n_fixed (synchronises). */
-int kb_dirichlet_split(const double *d_flags, int64_t ndof, int32_t *d_renum, int64_t *d_columns_in,
-                       int64_t *d_columns_out, double *d_applied, int64_t *h_counts, void *stream);
+ * like the reference), d_applied (capacity ndof).  d_prev_renum (optional, != d_renum): the renumbering of an earlier
+ * call -- h_counts[2] = 1 when the new one equals it (callers keep their cached reduced structure).  d_workspace:
+ * kb_dirichlet_split_workspace_bytes(ndof) bytes.  h_counts[0]=n_free, h_counts[1]=n_fixed (synchronises). */
+size_t kb_dirichlet_split_workspace_bytes(int64_t ndof);
+int kb_dirichlet_split(const double *d_flags, int64_t ndof, const int32_t *d_prev_renum, int32_t *d_renum,
+                       int64_t *d_columns_in, int64_t *d_columns_out, double *d_applied, void *d_workspace,
+                       size_t workspace_bytes, int64_t *h_counts, void *stream);
 /* :125-140 ComputeNeumannFluxes: F[i] = flag[i] if not NaN else 0 */
 int kb_neumann_fluxes(const double *d_flags, int64_t ndof, double *d_F, void *stream);
-/* :169-200 ApplyDirichletGetReducedMatrices.  d_applied (n_fixed): prescribed values in columns_out order (what
- * kb_dirichlet_split wrote, possibly scaled by the caller's load increment).  In place:
- *   F[free] -= (sum_{j fixed, !isclose(T_j,0)} K_ij T_j, ascending j) * load_factor
- * Reduced CSR (K_b = K[in,:][:,in]) is written to d_Kb_* (d_Kb_indptr n_free+1; capacity nnz for data/indices);
- * d_Mb_data optional (same pattern, from d_M).  d_Fb (n_free) = F[in].  h_nnz_b receives nnz(K_b) (synchronises). */
+/* :169-200 ApplyDirichletGetReducedMatrices, in two phases.  d_applied (n_fixed): prescribed values in columns_out order
+ * (what kb_dirichlet_split wrote, possibly scaled by the caller's load increment).
+ *   symbolic (once per sparsity pattern + Dirichlet set; synchronises): row pointers d_Kb_indptr (n_free+1) and column
+ *     indices d_Kb_indices (capacity nnz) of K_b = K[in,:][:,in], and one 32-bit survival mask per row of K
+ *     (d_row_mask, ndof words).  h_info[0] = nnz(K_b); h_info[1] = 1 when every free row has <= 32 entries, i.e. the masks
+ *     can drive the numeric phase (otherwise use the one-shot form below).  d_workspace: *_workspace_bytes(ndof, n_free).
+ *   numeric (every step; asynchronous, no allocation, no host round trip): d_Kb_data / d_Mb_data (nnz(K_b)) and, in place,
+ *       F[free] -= (sum_{j fixed, !isclose(T_j,0)} K_ij T_j, ascending j) * load_factor ;  d_Fb (n_free) = F[in].
+ *     d_Kb_data = NULL: right-hand side only.  Column indices are read only in rows that lose an entry.
+ *   one-shot (kb_apply_dirichlet_reduce: any row length, structure recomputed on every call; synchronises for nnz). */
+size_t kb_dirichlet_reduce_workspace_bytes(int64_t ndof, int64_t n_free);
+int kb_dirichlet_reduce_symbolic(int64_t ndof, const int32_t *d_indptr, const int32_t *d_indices, const int32_t *d_renum,
+                                 int64_t n_free, uint32_t *d_row_mask, int32_t *d_Kb_indptr, int32_t *d_Kb_indices,
+                                 void *d_workspace, size_t workspace_bytes, int64_t *h_info, void *stream);
+int kb_dirichlet_reduce_numeric(int64_t ndof, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
+                                const double *d_M, const int32_t *d_renum, const double *d_applied, double load_factor,
+                                double *d_F, int64_t n_free, const uint32_t *d_row_mask, const int32_t *d_Kb_indptr,
+                                double *d_Kb_data, double *d_Mb_data, double *d_Fb, void *stream);
+size_t kb_apply_dirichlet_reduce_workspace_bytes(int64_t ndof, int64_t n_free);
 int kb_apply_dirichlet_reduce(int64_t ndof, const int32_t *d_indptr, const int32_t *d_indices, const double *d_K,
                               const double *d_M, const int32_t *d_renum, const double *d_applied, double load_factor,
                               double *d_F, int64_t n_free, int32_t *d_Kb_indptr, int32_t *d_Kb_indices,
-                              double *d_Kb_data, double *d_Mb_data, double *d_Fb, int64_t *h_nnz_b, void *stream);
+                              double *d_Kb_data, double *d_Mb_data, double *d_Fb, void *d_workspace,
+                              size_t workspace_bytes, int64_t *h_nnz_b, void *stream);
 /* :203-241 TotalComponentSol / UpdateFixDoFs / UpdateFreeDoFs: T[i] = sol[renum[i]] if free (or 0 when d_sol NULL),
  * applied[-1-renum[i]] if fixed (or 0 when d_applied NULL) */
 int kb_total_component_sol(int64_t ndof, const int32_t *d_renum, const double *d_sol, const double *d_applied,
@@ -350,6 +369,9 @@ int kb_peer_close(void *d_ptr);
 int kb_peer_free(void *d_ptr);
 int kb_peer_error(const kb_peer_ctx *ctx, int64_t *h_err, void *stream);           /* 0 ok, 1/2: a wait timed out */
 int kb_peer_clear_error(const kb_peer_ctx *ctx, void *stream);
+/* Loads every kernel of the partitioned loops (CUDA loads kernels lazily, and a load may wait for running kernels: ranks
+ * that share one process / device must not meet that while a peer's kernel waits for them).  Synchronises the device. */
+int kb_peer_preload(void);
 
 /* One rank's share of a partitioned system: the mapped control blocks, the rank's exchanged vectors inside its region
  * (full local vectors: [halo row below | owned rows | halo row above]; 0 = p, 1 = r -- the SpMV inputs of the Krylov loops --

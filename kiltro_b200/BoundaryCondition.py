@@ -33,6 +33,10 @@ class BoundaryCondition(object):
         self.n_free = None
         self.n_fixed = None
         self._host = {}
+        # cached structure (symbolic phases): split buffers, renumbering version, reduced pattern + row masks per CSR pattern
+        self._split = None
+        self.renum_version = 0
+        self._reduce_cache = None
 
     # ------------------------------------------------------------------ user data (BoundaryCondition.py:27-63)
     def SetInitialConditions(self, func, *args, **kwargs):
@@ -104,16 +108,31 @@ class BoundaryCondition(object):
         ndof = int(flags.shape[0])
         if ndof != formulation.nvar * mesh.nnodes:
             raise ValueError("dirichlet_flags has %d entries, expected nnodes*nvar = %d" % (ndof, formulation.nvar * mesh.nnodes))
-        renum = D.empty(ndof, torch.int32)
-        cin = D.empty(ndof, torch.int64); cout = D.empty(ndof, torch.int64); td = D.empty(ndof)
-        counts = (_lib.I64 * 2)()
-        _lib.check(lib.kb_dirichlet_split(D.ptr(flags), ndof, D.ptr(renum), D.ptr(cin), D.ptr(cout), D.ptr(td), counts,
-                                          D.stream_ptr()))
+        # buffers are kept across calls (load increments / repeated Solve() reuse them); the renumbering goes to the one of
+        # two buffers the previous call did not use, so that the kernel can tell whether anything changed
+        sp = self._split
+        if sp is None or sp["ndof"] != ndof:
+            sp = {"ndof": ndof, "renum": [D.empty(ndof, torch.int32), D.empty(ndof, torch.int32)], "cur": -1,
+                  "cin": D.empty(ndof, torch.int64), "cout": D.empty(ndof, torch.int64), "td": D.empty(ndof),
+                  "ws": D.empty(int(lib.kb_dirichlet_split_workspace_bytes(ndof)), torch.uint8)}
+            self._split = sp
+        prev = sp["renum"][sp["cur"]] if sp["cur"] >= 0 else None
+        nxt = 0 if sp["cur"] != 0 else 1
+        renum = sp["renum"][nxt]
+        counts = (_lib.I64 * 3)()
+        _lib.check(lib.kb_dirichlet_split(D.ptr(flags), ndof, D.ptr(prev), D.ptr(renum), D.ptr(sp["cin"]), D.ptr(sp["cout"]),
+                                          D.ptr(sp["td"]), D.ptr(sp["ws"]), sp["ws"].numel(), counts, D.stream_ptr()))
         self.n_free, self.n_fixed = int(counts[0]), int(counts[1])
-        self.renum = renum
-        self.columns_in_device = cin[:self.n_free]
-        self.columns_out_device = cout[:self.n_fixed]
-        self.applied_dirichlet_device = td[:self.n_fixed].contiguous()
+        if int(counts[2]) == 1 and self.renum is prev:
+            pass                                                 # same Dirichlet set: renum (and what hangs on it) stays
+        else:
+            sp["cur"] = nxt
+            self.renum = renum
+            self.renum_version += 1
+            self._reduce_cache = None
+        self.columns_in_device = sp["cin"][:self.n_free]
+        self.columns_out_device = sp["cout"][:self.n_fixed]
+        self.applied_dirichlet_device = sp["td"][:self.n_fixed].clone()
         self._host = {}
         if self.n_free == 0:
             warn("Dirichlet boundary conditions have been applied on the entire mesh")
@@ -147,22 +166,53 @@ class BoundaryCondition(object):
         applied = self._applied(AppliedDirichlet)
         want_mass = mass is not None and not isinstance(mass, list)
         nfree = self.n_free
-        kb_ptr = D.empty(nfree + 1, torch.int32)
-        kb_ind = D.empty(K.nnz, torch.int32); kb_dat = D.empty(K.nnz)
-        mb_dat = D.empty(K.nnz) if want_mass else None
+        # symbolic phase, cached per (CSR pattern, Dirichlet set): reduced pattern + one survival mask per row
+        key = (K.indptr.data_ptr(), K.indices.data_ptr(), K.nnz, ndof, self.renum_version)
+        rc = self._reduce_cache
+        if rc is None or rc["key"] != key:
+            ws = D.empty(int(lib.kb_dirichlet_reduce_workspace_bytes(ndof, nfree)), torch.uint8)
+            mask = D.empty(max(ndof, 1), torch.int32)
+            kb_ptr = D.empty(nfree + 1, torch.int32)
+            kb_ind = D.empty(max(K.nnz, 1), torch.int32)
+            h = (_lib.I64 * 2)()
+            _lib.check(lib.kb_dirichlet_reduce_symbolic(ndof, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(self.renum), nfree,
+                                                        D.ptr(mask), D.ptr(kb_ptr), D.ptr(kb_ind), D.ptr(ws), ws.numel(), h,
+                                                        D.stream_ptr()))
+            nb = int(h[0])
+            rc = {"key": key, "mask": mask, "kb_ptr": kb_ptr, "kb_ind": kb_ind[:nb].clone() if nb < K.nnz // 2 else kb_ind[:nb],
+                  "nnz_b": nb, "masks_ok": bool(h[1]), "ws": ws, "indptr": K.indptr, "indices": K.indices}
+            self._reduce_cache = rc
+        nb = rc["nnz_b"]
         Fb = D.empty(nfree)
-        nnzb = _lib.I64(0)
-        _lib.check(lib.kb_apply_dirichlet_reduce(ndof, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(K.data),
-                                                 D.ptr(mass.data) if want_mass else None, D.ptr(self.renum),
-                                                 D.ptr(applied), float(LoadFactor), D.ptr(F), nfree, D.ptr(kb_ptr),
-                                                 D.ptr(kb_ind), D.ptr(kb_dat), D.ptr(mb_dat), D.ptr(Fb),
-                                                 nnzb, D.stream_ptr()))
+        if not rc["masks_ok"]:
+            # rows longer than 32 entries: one-shot form (recomputes the structure, synchronises)
+            kb_ind = D.empty(K.nnz, torch.int32); kb_dat = D.empty(K.nnz)
+            kb_ptr = D.empty(nfree + 1, torch.int32)
+            mb_dat = D.empty(K.nnz) if want_mass else None
+            nnzb = _lib.I64(0)
+            _lib.check(lib.kb_apply_dirichlet_reduce(ndof, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(K.data),
+                                                     D.ptr(mass.data) if want_mass else None, D.ptr(self.renum),
+                                                     D.ptr(applied), float(LoadFactor), D.ptr(F), nfree, D.ptr(kb_ptr),
+                                                     D.ptr(kb_ind), D.ptr(kb_dat), D.ptr(mb_dat), D.ptr(Fb), D.ptr(rc["ws"]),
+                                                     rc["ws"].numel(), nnzb, D.stream_ptr()))
+            if only_residual:
+                return F
+            K_b = DeviceCSR(kb_dat[:nb], kb_ind[:nb], kb_ptr, (nfree, nfree), symmetric=K.symmetric)
+            if want_mass:
+                return K_b, Fb, F, DeviceCSR(mb_dat[:nb], kb_ind[:nb], kb_ptr, (nfree, nfree), symmetric=True)
+            return K_b, Fb, F
+        kb_dat = None if only_residual else D.empty(nb)
+        mb_dat = D.empty(nb) if (want_mass and not only_residual) else None
+        _lib.check(lib.kb_dirichlet_reduce_numeric(ndof, D.ptr(K.indptr), D.ptr(K.indices), D.ptr(K.data),
+                                                   D.ptr(mass.data) if mb_dat is not None else None, D.ptr(self.renum),
+                                                   D.ptr(applied), float(LoadFactor), D.ptr(F), nfree, D.ptr(rc["mask"]),
+                                                   D.ptr(rc["kb_ptr"]), D.ptr(kb_dat), D.ptr(mb_dat), D.ptr(Fb),
+                                                   D.stream_ptr()))
         if only_residual:
             return F
-        nb = int(nnzb.value)
-        K_b = DeviceCSR(kb_dat[:nb], kb_ind[:nb], kb_ptr, (nfree, nfree), symmetric=K.symmetric)
+        K_b = DeviceCSR(kb_dat, rc["kb_ind"], rc["kb_ptr"], (nfree, nfree), symmetric=K.symmetric)
         if want_mass:
-            return K_b, Fb, F, DeviceCSR(mb_dat[:nb], kb_ind[:nb], kb_ptr, (nfree, nfree), symmetric=True)
+            return K_b, Fb, F, DeviceCSR(mb_dat, rc["kb_ind"], rc["kb_ptr"], (nfree, nfree), symmetric=True)
         return K_b, Fb, F
 
     def GetReducedMatrices(self, K, F, M=None):                  # :156-166 (no RHS elimination)

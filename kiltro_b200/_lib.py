@@ -76,10 +76,17 @@ SIGNATURES = {
                                c_vp]),
     "kb_element_operator": (I32, [I32, I32, c_vp, c_vp, I64, c_vp, F64, F64, c_vp, c_vp, c_vp]),
     "kb_axpby": (I32, [I64, F64, c_vp, F64, c_vp, c_vp, c_vp]),
-    "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
+    "kb_dirichlet_split_workspace_bytes": (ctypes.c_size_t, [I64]),
+    "kb_dirichlet_split": (I32, [c_vp, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(I64), c_vp]),
+    "kb_dirichlet_reduce_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
+    "kb_dirichlet_reduce_symbolic": (I32, [I64, c_vp, c_vp, c_vp, I64, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t,
+                                           ctypes.POINTER(I64), c_vp]),
+    "kb_dirichlet_reduce_numeric": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, I64, c_vp, c_vp, c_vp, c_vp,
+                                          c_vp, c_vp]),
+    "kb_apply_dirichlet_reduce_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
     "kb_neumann_fluxes": (I32, [c_vp, I64, c_vp, c_vp]),
     "kb_apply_dirichlet_reduce": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, F64, c_vp, I64, c_vp, c_vp, c_vp,
-                                        c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
+                                        c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(I64), c_vp]),
     "kb_total_component_sol": (I32, [I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_spmv_num_blocks": (I64, [I64]),
     "kb_spmv_force_simple": (None, [I32]),
@@ -130,6 +137,7 @@ SIGNATURES = {
     "kb_peer_close": (I32, [c_vp]),
     "kb_peer_free": (I32, [c_vp]),
     "kb_peer_error": (I32, [ctypes.POINTER(kb_peer_ctx), ctypes.POINTER(I64), c_vp]),
+    "kb_peer_preload": (I32, []),
     "kb_peer_clear_error": (I32, [ctypes.POINTER(kb_peer_ctx), c_vp]),
     "kb_peer_krylov_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
     "kb_peer_cg_solve": (I32, [ctypes.POINTER(kb_peer_part), ctypes.POINTER(kb_peer_op), c_vp, c_vp, c_vp, F64, I32, I32, c_vp,

@@ -176,6 +176,10 @@ __global__ void k_peer_init(Ctx c, unsigned long long ev, double *sc, int *done,
     sc[S_TOL2] = tol2;
     done[0] = dn; done[1] = 0; done[2] = dn;                  // done[2]: verdict of this (re)start alone (the loop never writes it)
 }
+__global__ void __launch_bounds__(256) k_pfill(double *__restrict__ p, int64_t n, double v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
 // a rank leaves this kernel only after every rank entered it (used between cycles / solves; one thread)
 __global__ void k_peer_barrier(Ctx c, unsigned long long ev) {
     kb_pdl_wait();
@@ -381,7 +385,36 @@ Ctx make_ctx(const kb_peer_ctx *h) {
     return c;
 }
 
+// With lazy module loading (the CUDA 12 default) the FIRST launch of a kernel may have to wait for running kernels -- fatal
+// when the running kernel is itself waiting for a peer whose next kernel has not been loaded yet (ranks sharing one
+// process / device in the tests).  Every kernel of the partitioned loops is therefore loaded before the first launch.
+template <class F> void preload_one(F *f) { cudaFuncAttributes a; (void)cudaFuncGetAttributes(&a, f); }
+void peer_preload() {
+    static bool done = false;
+    if (done) return;
+    preload_one(k_pvec<PCopyPush>); preload_one(k_pvec<PResidInit>); preload_one(k_pvec<PBiS>); preload_one(k_pvec<PBiUpdateP>);
+    preload_one(k_pvec<PCgUpdate>); preload_one(k_pvec<PCgP>); preload_one(k_pvec<PRhs>); preload_one(k_pvec<PStep>);
+    preload_one(k_peer_init); preload_one(k_peer_barrier); preload_one(k_reset_state); preload_one(k_pfill);
+    preload_one(k_spmv_pat<0, NoFinal>); preload_one(k_spmv_pat<1, FinPostDots>); preload_one(k_spmv_pat<2, FinPostDots>);
+    preload_one(k_spmv_tma<0, NoFinal, short>); preload_one(k_spmv_tma<1, FinPostDots, short>); preload_one(k_spmv_tma<2, FinPostDots, short>);
+    preload_one(k_spmv_tma<0, NoFinal, int>); preload_one(k_spmv_tma<1, FinPostDots, int>); preload_one(k_spmv_tma<2, FinPostDots, int>);
+    preload_one(k_spmv<0, NoFinal>); preload_one(k_spmv<1, FinPostDots>); preload_one(k_spmv<2, FinPostDots>);
+    // the launcher's one-off shared-memory opt-ins, for the same reason
+    cudaFuncSetAttribute(k_spmv_pat<0, NoFinal>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pat_smem_bytes());
+    cudaFuncSetAttribute(k_spmv_pat<1, FinPostDots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pat_smem_bytes());
+    cudaFuncSetAttribute(k_spmv_pat<2, FinPostDots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pat_smem_bytes());
+    cudaFuncSetAttribute(k_spmv_tma<0, NoFinal, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<short>());
+    cudaFuncSetAttribute(k_spmv_tma<1, FinPostDots, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<short>());
+    cudaFuncSetAttribute(k_spmv_tma<2, FinPostDots, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<short>());
+    cudaFuncSetAttribute(k_spmv_tma<0, NoFinal, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<int>());
+    cudaFuncSetAttribute(k_spmv_tma<1, FinPostDots, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<int>());
+    cudaFuncSetAttribute(k_spmv_tma<2, FinPostDots, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes<int>());
+    (void)cudaGetLastError();
+    done = true;
+}
+
 int peer_check_args(const kb_peer_part *pp, const kb_peer_op *op) {
+    peer_preload();
     if (!pp || !op) return KB_EINVAL;
     const kb_peer_ctx &x = pp->ctx;
     if (x.nranks < 1 || x.nranks > kbpeer::MAXP || x.rank < 0 || x.rank >= x.nranks) return KB_EINVAL;
@@ -464,8 +497,12 @@ int peer_restart(PeerEnv &e, const double *vals, const double *b, const double *
     k_peer_barrier<<<1, 32, 0, e.s>>>(e.c, ++pp->ev);
     KB_LAUNCH_CHECK();
     double *p = own_of(e, 0), *r = own_of(e, 1);
-    if ((rc = launch_pvec(e, PCopyPush{x, p}, make_push(e, 0, ++pp->hseq[0]), nullptr))) return rc;
-    if ((rc = peer_spmv<0>(e, vals, 0, pp->hseq[0], e.w.v, nullptr, nullptr, nullptr, NoFinal{}))) return rc;
+    // x travels through vector 1 (r), NOT vector 0: the residual kernel below pushes the new p into the neighbours' halo
+    // slots of vector 0 at once, and nothing orders that push after the neighbours' SpMV of this sequence -- a faster
+    // rank would overwrite halo entries its neighbour is still reading.  (Inside the iteration two pushes of the same
+    // vector are always separated by a dot event, which every rank posts only after its own SpMV.)
+    if ((rc = launch_pvec(e, PCopyPush{x, r}, make_push(e, 1, ++pp->hseq[1]), nullptr))) return rc;
+    if ((rc = peer_spmv<0>(e, vals, 1, pp->hseq[1], e.w.v, nullptr, nullptr, nullptr, NoFinal{}))) return rc;
     const unsigned long long ev = ++pp->ev;
     if ((rc = launch_pvec(e, PResidInit{e.c, ev, b, e.w.v, scale, r, p, METHOD == 1 ? e.w.rhat : nullptr, e.w.dr},
                           make_push(e, 0, ++pp->hseq[0]), nullptr))) return rc;
@@ -592,6 +629,9 @@ int peer_krylov(PeerEnv &e, const double *vals, const double *b, double *x, cons
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ C ABI
+// loads every kernel of the partitioned loops now (call it before ranks that share a device start waiting for each other)
+extern "C" int kb_peer_preload(void) { peer_preload(); KB_CUDA(cudaDeviceSynchronize()); return 0; }
+
 extern "C" int kb_peer_alloc(size_t bytes, void **d_ptr, unsigned char *h_handle64) {
     if (!d_ptr || !h_handle64 || bytes == 0) return KB_EINVAL;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -676,7 +716,10 @@ extern "C" int kb_peer_transient_run(kb_peer_part *part, const kb_peer_op *op, c
     const int64_t launches0 = g_kb_launches;
     const int64_t n = part->n_own;
     double *T = own_of(e, 2);
-    KB_CUDA(cudaMemsetAsync(yh, 0, sizeof(double) * (size_t)n, e.s));
+    k_pfill<<<kb_grid(n, 256, 8), 256, 0, e.s>>>(yh, n, 0.0);     // (not cudaMemset: see peer_preload)
+    KB_LAUNCH_CHECK();
+    k_reset_state<<<1, 32, 0, e.s>>>(e.w.tickets, e.w.done, e.w.iter, e.w.sc);   // the halo ticket of the first push below
+    KB_LAUNCH_CHECK();
     k_peer_barrier<<<1, 32, 0, e.s>>>(e.c, ++part->ev);
     KB_LAUNCH_CHECK();
     // halo rows of T^0

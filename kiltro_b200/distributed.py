@@ -679,6 +679,14 @@ def close_peer_regions(systems):
             s.peer_region = None
 
 
+def _peer_capable(systems, comm):
+    """The native peer loops need one part per process (or all parts in one process) and 16-byte aligned row views of the
+    local CSR (a multiple of 4 nodes per mesh row: the bulk-copy SpMV kernels); otherwise the host-driven loops run."""
+    if not (isinstance(comm, LocalComm) or (len(systems) == 1 and isinstance(comm, DistComm))):
+        return False
+    return all(s.part.world == 1 or s.cols16 is not None for s in systems)
+
+
 def _peer_op(sysm, vals):
     """kb_peer_op of the owned-row view of a LocalSystem with values `vals` (returned with the tensors it points into)."""
     op = _lib.kb_peer_op()
@@ -702,6 +710,7 @@ def _run_ranks(systems, comm, fn):
     import threading
     out, errs = [None] * len(systems), [None] * len(systems)
     streams = [torch.cuda.Stream() for _ in systems]
+    _lib.check(systems[0].lib.kb_peer_preload())          # no lazy kernel load while a peer's kernel is waiting
     torch.cuda.synchronize()
 
     dev = torch.cuda.current_device()
@@ -747,15 +756,14 @@ def peer_krylov(systems, comm, Ahat, b, x, scales, sym, rtol, maxiter, check_eve
     regions = _peer_regions(systems, comm)
     if any(r.broken for r in regions):
         raise _lib.KiltroB200Error("the peer regions of this system are unusable after a timed-out exchange")
-    keep = []
+    # workspaces are allocated up front (an allocation may synchronise the device -- not while a peer's kernel waits)
+    wss = [D.empty(s.lib.kb_peer_krylov_workspace_bytes(s.part.n_own, s.nnz_own), torch.uint8) for s in systems]
+    ops = [_peer_op(s, Ahat[k]) for k, s in enumerate(systems)]
 
     def one(k, s):
-        lib, part = s.lib, s.part
-        op = _peer_op(s, Ahat[k])
-        nbytes = lib.kb_peer_krylov_workspace_bytes(part.n_own, s.nnz_own)
-        ws = D.empty(nbytes, torch.uint8)
+        lib, op, ws = s.lib, ops[k], wss[k]
+        nbytes = ws.numel()
         info = _lib.kb_solve_info()
-        keep.append((op, ws))
         if sym:
             rc = lib.kb_peer_cg_solve(regions[k].part, op, s.own_ptr(b[k]), s.own_ptr(x[k]), s.own_ptr(scales[k]), rtol,
                                       int(maxiter), int(check_every), D.ptr(ws), nbytes, info, D.stream_ptr())
@@ -766,7 +774,9 @@ def peer_krylov(systems, comm, Ahat, b, x, scales, sym, rtol, maxiter, check_eve
 
     res = _run_ranks(systems, comm, one)
     if _peer_failed_anywhere(comm, regions, [r[0] for r in res]):
-        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration)")
+        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the iteration): return codes %r, "
+                                   "error words %r, events %r" % ([r[0] for r in res], [g.error() for g in regions],
+                                                                  [(int(g.part.ev), list(g.part.hseq)) for g in regions]))
     for rc, _ in res:
         _lib.check(rc)
     info = res[0][1]
@@ -784,15 +794,13 @@ def _run_transient_peer(systems, comm, Kff, Ahat, scales, sym, dt, nsteps, rtol,
         reg.vec[2].copy_(s.T0)
     torch.cuda.synchronize()
     comm.barrier()
-    keep = []
+    wss = [D.empty(s.lib.kb_peer_transient_workspace_bytes(s.part.n_own, s.nnz_own), torch.uint8) for s in systems]
+    ops = [_peer_op(s, Ahat[k]) for k, s in enumerate(systems)]
 
     def one(k, s):
-        lib, part, off = s.lib, s.part, s.part.own_off
-        op = _peer_op(s, Ahat[k])
-        nbytes = lib.kb_peer_transient_workspace_bytes(part.n_own, s.nnz_own)
-        ws = D.empty(nbytes, torch.uint8)
+        lib, off, op, ws = s.lib, s.part.own_off, ops[k], wss[k]
+        nbytes = ws.numel()
         info = _lib.kb_solve_info()
-        keep.append((op, ws))
         rc = lib.kb_peer_transient_run(regions[k].part, op, D.ptr(Kff[k]), 1 if sym else 0, s.own_ptr(scales[k]),
                                        s.own_ptr(s.Fm), s.bc.renum.data_ptr() + 4 * off,
                                        D.ptr(s.bc.applied_dirichlet_device), float(dt), int(nsteps), float(rtol),
@@ -801,7 +809,9 @@ def _run_transient_peer(systems, comm, Kff, Ahat, scales, sym, dt, nsteps, rtol,
 
     res = _run_ranks(systems, comm, one)
     if _peer_failed_anywhere(comm, regions, [r[0] for r in res]):
-        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the time loop)")
+        raise _lib.KiltroB200Error("peer-memory exchange timed out (a rank fell out of the time loop): return codes %r, error "
+                                   "words %r, events %r" % ([r[0] for r in res], [g.error() for g in regions],
+                                                            [(int(g.part.ev), list(g.part.hseq)) for g in regions]))
     for rc, _ in res:
         _lib.check(rc)
     info = res[0][1]
@@ -871,7 +881,7 @@ def solve_steady(systems, comm, rtol=1e-10, maxiter=20000, check_every=50, metho
         if mode == 1:
             _lib.check(s.lib.kb_vec_mul(s.part.n_loc, D.ptr(s.b), D.ptr(sc), D.ptr(bb), D.stream_ptr()))
         b.append(bb); x.append(D.zeros(s.part.n_loc))
-    peer = exchange == "peer" and (isinstance(comm, LocalComm) or (len(systems) == 1 and isinstance(comm, DistComm)))
+    peer = exchange == "peer" and _peer_capable(systems, comm)
     if peer:
         info = peer_krylov(systems, comm, Ahat, b, x, scales, sym, rtol, maxiter, check_every)
         info["exchange"] = "peer"
@@ -947,7 +957,7 @@ def run_transient(systems, comm, dt, nsteps, theta=0.0, rtol=1e-10, maxiter=2000
     mode = 1 if sym else 0
     scales, Ahat = _jacobi_scale(systems, comm, A, mode)
     del A
-    if exchange == "peer" and (isinstance(comm, LocalComm) or (len(systems) == 1 and isinstance(comm, DistComm))):
+    if exchange == "peer" and _peer_capable(systems, comm):
         return _run_transient_peer(systems, comm, Kff, Ahat, scales, sym, dt, nsteps, rtol, maxiter)
     T = [s.T0.clone() for s in systems]
     yh = [D.zeros(s.part.n_loc) for s in systems]
