@@ -419,6 +419,44 @@ int kb_peer_transient_run(kb_peer_part *part, const kb_peer_op *op, const double
                           const double *d_applied, double dt, int nsteps, double rtol, int maxiter, void *d_workspace,
                           size_t workspace_bytes, kb_solve_info *h_info, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Opt-in solver beside the prescribed Jacobi method: BiCGSTAB right-preconditioned by ONE geometric-multigrid V-cycle,
+ * for quad-4 meshes numbered like Mesh.Rectangle (MeshGeneration/Mesh.py:33-58).  Replaces the same call as
+ * kb_bicgstab_solve: LinearSolver.Solve -> scipy.sparse.linalg.spsolve, FEMSolver.py:350-364.  csrc/multigrid.cu,
+ * csrc/krylov_mg.cuh; host mirror kiltro_b200/multigrid.py (LinearSolver(preconditioner=GridMultigrid(...))).
+ *
+ * kb_mg is a HOST-side plan (level shapes, 1-D transfer tables, device pointers into the caller's workspace); it owns no
+ * device memory.  Levels: nxn x nyn nodes, then about half the elements per direction per level down to <= coarsest_nodes
+ * (<= 1024) nodes.  kb_mg_setup builds the operators: level 0 from the reduced CSR matrix K_b of
+ * kb_apply_dirichlet_reduce (every entry must lie in the 9-point neighbourhood of its row: else KB_EINVAL), the coarser
+ * ones rediscretised with the path's element routine and the Petrov-Galerkin weights of TemperaturePG
+ * (VariationalPrinciple.py:216-261,311-342; d_velocity NULL = pure diffusion; with a velocity `mode` must be
+ * KB_MODE_CONSISTENT); coordinates / velocities / Dirichlet flags of a coarse node are those of the nearest finer node.
+ * d_renum: the renumbering of kb_dirichlet_split (reduced index, or < 0 for a prescribed DOF).  The workspace
+ * (kb_mg_workspace_bytes) must stay untouched between kb_mg_setup and the last apply / solve; passing the same pointer to
+ * a later kb_mg_setup (new values, same mesh) skips the one-off initialisation.  kb_mg_setup synchronises the stream
+ * (it reads back an error flag); kb_mg_apply (one V-cycle z = M^-1 v on reduced fp64 vectors; the cycle itself runs in
+ * fp32) is stream-ordered without synchronisation.  kb_mg_transfer_table is host-only arithmetic: fine node i interpolates
+ * (1 - w[i]) * coarse[j[i]] + w[i] * coarse[j[i] + 1]; start[c], c = 0..ncoarse: first fine i with j[i] >= c. */
+typedef struct kb_mg kb_mg;
+int kb_mg_create(int64_t nxn, int64_t nyn, int64_t coarsest_nodes, kb_mg **out);
+void kb_mg_destroy(kb_mg *mg);
+int kb_mg_num_levels(const kb_mg *mg);
+int kb_mg_level_shape(const kb_mg *mg, int level, int64_t *nxn, int64_t *nyn);
+size_t kb_mg_workspace_bytes(const kb_mg *mg);
+int kb_mg_transfer_table(int64_t nfine, int64_t ncoarse, int32_t *h_j, float *h_w, int32_t *h_start);
+int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_velocity, const int32_t *d_renum,
+                const kb_material *material, int mode, int64_t nfree, int64_t nnz, const int32_t *d_indptr,
+                const int32_t *d_indices, const double *d_vals, int nu, double omega, void *d_workspace,
+                size_t workspace_bytes, void *stream);
+int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stream);
+/* x: initial guess in, solution out; verdict, restarts and kb_solve_info as kb_bicgstab_solve (TRUE residual of the
+ * system as handed over).  Synchronises the stream every check_every iterations. */
+size_t kb_mg_bicgstab_workspace_bytes(int64_t nrows, int64_t nnz);
+int kb_mg_bicgstab_solve(kb_mg *mg, int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                         const double *d_vals, const double *d_b, double *d_x, double rtol, int maxiter, int check_every,
+                         void *d_workspace, size_t workspace_bytes, kb_solve_info *h_info, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

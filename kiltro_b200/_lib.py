@@ -147,6 +147,18 @@ SIGNATURES = {
     "kb_peer_transient_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
     "kb_peer_transient_run": (I32, [ctypes.POINTER(kb_peer_part), ctypes.POINTER(kb_peer_op), c_vp, I32, c_vp, c_vp, c_vp, c_vp,
                                     F64, I32, F64, I32, c_vp, ctypes.c_size_t, ctypes.POINTER(kb_solve_info), c_vp]),
+    "kb_mg_create": (I32, [I64, I64, I64, ctypes.POINTER(ctypes.c_void_p)]),
+    "kb_mg_destroy": (None, [c_vp]),
+    "kb_mg_num_levels": (I32, [c_vp]),
+    "kb_mg_level_shape": (I32, [c_vp, I32, ctypes.POINTER(I64), ctypes.POINTER(I64)]),
+    "kb_mg_workspace_bytes": (ctypes.c_size_t, [c_vp]),
+    "kb_mg_transfer_table": (I32, [I64, I64, c_vp, c_vp, c_vp]),
+    "kb_mg_setup": (I32, [c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_material), I32, I64, I64, c_vp, c_vp, c_vp, I32, F64,
+                          c_vp, ctypes.c_size_t, c_vp]),
+    "kb_mg_apply": (I32, [c_vp, c_vp, c_vp, c_vp]),
+    "kb_mg_bicgstab_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
+    "kb_mg_bicgstab_solve": (I32, [c_vp, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, I32, I32, c_vp, ctypes.c_size_t,
+                                   ctypes.POINTER(kb_solve_info), c_vp]),
 }
 
 _LIB = None

@@ -1152,6 +1152,7 @@ extern "C" int kb_scale_matrix(int64_t nrows, const int32_t *d_indptr, const int
 }
 
 #include "krylov_peer.cuh"   // K9 peer-memory solvers (same translation unit: they use the launchers above)
+#include "krylov_mg.cuh"     // opt-in: BiCGSTAB preconditioned by the multigrid V-cycle of multigrid.cu
 
 extern "C" int kb_profile_spmv_begin(int every) {
     if (!g_prof.have_events) {

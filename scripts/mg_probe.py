@@ -42,10 +42,30 @@ print("multigrid       : solve %.1f ms, %d iterations, %d levels, set-up %.2f s,
          mgs.info["relative_residual"], mgs.info["status"],
          mesh.nnodes / (1e-3 * (fs.timings["solve_ms"] + fs.timings["assemble_ms"] + fs.timings["bc_ms"]))), flush=True)
 
-if "sweep" in sys.argv:                                   # residual histories for a few smoother settings
-    for nu, omega in ((2, 0.8), (3, 0.8), (2, 0.67)):
-        mg.nu, mg.omega = nu, omega
-        run(mgs)
-        h = mgs.info["history"]
-        print("nu=%d omega=%.2f: %d iterations, solve %.1f ms, history %s" % (
-            nu, omega, mgs.info["iterations"], fs.timings["solve_ms"], " ".join("%.1e" % v for v in h[:6] + h[-4:])), flush=True)
+# numeric set-up alone (part of every solve): CUDA events around kb_mg_setup
+from kiltro_b200 import device as D
+bc1 = K.BoundaryCondition(); bc1.SetDirichletCriteria(lambda: flags)
+Kc = K.Assemble(fs, form.function_spaces, form, mesh, material, bc1)[0]
+bc1.GetDirichletBoundaryConditions(form, mesh, material, fs)
+F = torch.zeros((mesh.nnodes, 1), dtype=torch.float64, device="cuda")
+Kb, Fb = bc1.ApplyDirichletGetReducedMatrices(Kc, F, bc1.applied_dirichlet_device)[:2]
+mg1 = GridMultigrid(mesh, form, material, bc1)
+mg1.setup(Kb)
+e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+e[0].record(); mg1.setup(Kb); e[1].record()
+r = Fb.reshape(-1).clone()
+z = mg1.apply(r); torch.cuda.synchronize()
+e[2].record()
+for _ in range(10):
+    z = mg1.apply(r)
+e[3].record(); torch.cuda.synchronize()
+red = float(torch.linalg.vector_norm(r - Kb.dot(z)) / torch.linalg.vector_norm(r))
+print("set-up %.3f ms ; V-cycle %.3f ms ; residual reduction of one cycle %.3f ; levels %s" % (
+    e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]) / 10, red, mg1.levels), flush=True)
+
+if "sweep" in sys.argv:                                   # a few smoother settings
+    for nu, omega in ((1, 0.67), (2, 0.8), (3, 0.67), (2, 0.6), (2, 0.67)):
+        bcs = K.BoundaryCondition(); bcs.SetDirichletCriteria(lambda: flags)
+        mgs2 = K.LinearSolver(tol=1e-10, preconditioner=GridMultigrid(mesh, form, material, bcs, nu=nu, omega=omega))
+        run(mgs2)
+        print("nu=%d omega=%.2f: %d iterations, solve %.1f ms" % (nu, omega, mgs2.info["iterations"], fs.timings["solve_ms"]), flush=True)

@@ -1,4 +1,6 @@
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # several ranks share one process in the in-process peer tests
 import sys
 
 import numpy as np
