@@ -427,7 +427,7 @@ int kb_peer_transient_run(kb_peer_part *part, const kb_peer_op *op, const double
  *
  * kb_mg is a HOST-side plan (level shapes, 1-D transfer tables, device pointers into the caller's workspace); it owns no
  * device memory.  Levels: nxn x nyn nodes, then about half the elements per direction per level down to <= coarsest_nodes
- * (<= 1024) nodes.  kb_mg_setup builds the operators: level 0 from the reduced CSR matrix K_b of
+ * (<= 1023) nodes.  kb_mg_setup builds the operators: level 0 from the reduced CSR matrix K_b of
  * kb_apply_dirichlet_reduce (every entry must lie in the 9-point neighbourhood of its row: else KB_EINVAL), the coarser
  * ones rediscretised with the path's element routine and the Petrov-Galerkin weights of TemperaturePG
  * (VariationalPrinciple.py:216-261,311-342; d_velocity NULL = pure diffusion; with a velocity `mode` must be
@@ -450,6 +450,11 @@ int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_velocity, con
                 const int32_t *d_indices, const double *d_vals, int nu, double omega, void *d_workspace,
                 size_t workspace_bytes, void *stream);
 int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stream);
+/* development switches: fused legs of the cycle (one kernel per leg and level instead of one per sweep; bit-identical
+ * results) on / off, and the node rows per warp task of the fused kernels */
+void kb_mg_set_fused(int on);
+void kb_mg_set_rows_per_task(int rows);
+void kb_mg_set_prefetch_rows(int rows);   /* L2 prefetch distance of the fused kernels (0 = off) */
 /* x: initial guess in, solution out; verdict, restarts and kb_solve_info as kb_bicgstab_solve (TRUE residual of the
  * system as handed over).  Synchronises the stream every check_every iterations. */
 size_t kb_mg_bicgstab_workspace_bytes(int64_t nrows, int64_t nnz);

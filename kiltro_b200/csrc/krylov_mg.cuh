@@ -18,7 +18,7 @@ namespace {
 
 struct MgWork {
     Work w;                          // row partition, row-pattern dictionary, partials, scalars, flags (vals_hat/scale/cols16 unused)
-    double *r, *p, *v, *t, *rhat, *ph, *sh;
+    double *r, *s, *p, *v, *t, *rhat, *ph, *sh;
 };
 
 size_t carve_mg(MgWork *m, char *base, int64_t n, int64_t nnz) {
@@ -30,7 +30,7 @@ size_t carve_mg(MgWork *m, char *base, int64_t n, int64_t nnz) {
         if (m) lhs = (type *)(base + off);                        \
         off += align256(sizeof(type) * (size_t)(count));          \
     } while (0)
-    TAKE(m->r, double, n + 1); TAKE(m->p, double, n + 1); TAKE(m->v, double, n + 1); TAKE(m->t, double, n + 1);
+    TAKE(m->r, double, n + 1); TAKE(m->s, double, n + 1); TAKE(m->p, double, n + 1); TAKE(m->v, double, n + 1); TAKE(m->t, double, n + 1);
     TAKE(m->rhat, double, n + 1); TAKE(m->ph, double, n + 1); TAKE(m->sh, double, n + 1);
     TAKE(m->w.bandflag, int, 4);
     TAKE(m->w.row_pat, uint8_t, n + 48);
@@ -47,12 +47,12 @@ size_t carve_mg(MgWork *m, char *base, int64_t n, int64_t nnz) {
     return off;
 }
 
-struct HMgUpdateP {         // x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; d0 = <r,r>   (s is passed in r)
-    const double *alpha, *omega, *beta, *ph, *sh, *t, *v; double *x, *r, *p;
+struct HMgUpdateP {         // x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; d0 = <r,r>
+    const double *alpha, *omega, *beta, *ph, *sh, *t, *v, *s; double *x, *r, *p;
     struct S { double a, om, b; }; struct L { double x, ph, sh, s, t, p, v; };
     __device__ S scalars() const { return S{alpha[0], omega[0], beta[0]}; }
     __device__ void load(int64_t i, L &l) const {
-        l.x = x[i]; l.ph = __ldcs(ph + i); l.sh = __ldcs(sh + i); l.s = r[i]; l.t = __ldcs(t + i); l.p = p[i]; l.v = __ldcs(v + i);
+        l.x = x[i]; l.ph = __ldcs(ph + i); l.sh = __ldcs(sh + i); l.s = __ldcs(s + i); l.t = __ldcs(t + i); l.p = p[i]; l.v = __ldcs(v + i);
     }
     __device__ void apply(int64_t i, const L &l, const S &s, double &d0, double &) const {
         x[i] = l.x + (s.a * l.ph + s.om * l.sh);
@@ -122,12 +122,12 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
         while (!stop && total_iters < maxiter) {
             const int batch = (maxiter - total_iters) < check_every ? (maxiter - total_iters) : check_every;
             for (int it = 0; it < batch; ++it) {
-                if ((rc = kbmg_apply(mg, m.p, m.ph, nullptr, nullptr, w.done, s, true))) return rc;
+                if ((rc = kbmg_apply(mg, m.p, nullptr, m.ph, nullptr, nullptr, w.done, s, true))) return rc;
                 if ((rc = launch_spmv<1>(n, nnz, indptr, indices, vals, w, m.ph, m.v, m.rhat, w.done, FinBiAlpha{w.sc, w.done}, s, nullptr, true))) return rc;
-                // s = r - alpha v is applied by the staging kernel of the V-cycle (r becomes s in place)
-                if ((rc = kbmg_apply(mg, m.r, m.sh, w.sc + S_ALPHA, m.v, w.done, s, true))) return rc;
-                if ((rc = launch_spmv<2>(n, nnz, indptr, indices, vals, w, m.sh, m.t, m.r, w.done, FinBiOmega2{w.sc, w.done, w.iter}, s, m.rhat, true))) return rc;
-                if ((rc = launch_vec4<1>(n, HMgUpdateP{w.sc + S_ALPHA, w.sc + S_OMEGA, w.sc + S_BETA, m.ph, m.sh, m.t, m.v, x, m.r, m.p},
+                // s = r - alpha v is formed by the staging kernel of the V-cycle
+                if ((rc = kbmg_apply(mg, m.r, m.s, m.sh, w.sc + S_ALPHA, m.v, w.done, s, true))) return rc;
+                if ((rc = launch_spmv<2>(n, nnz, indptr, indices, vals, w, m.sh, m.t, m.s, w.done, FinBiOmega2{w.sc, w.done, w.iter}, s, m.rhat, true))) return rc;
+                if ((rc = launch_vec4<1>(n, HMgUpdateP{w.sc + S_ALPHA, w.sc + S_OMEGA, w.sc + S_BETA, m.ph, m.sh, m.t, m.v, m.s, x, m.r, m.p},
                                          FinBiRes{w.sc, w.done, w.iter}, w.partials, w.ticket, w.done, s, true))) return rc;
             }
             if ((rc = read_state(w, &hs, s))) return rc;

@@ -7,18 +7,17 @@
 //   * hierarchy: level l+1 has about half the elements of level l per direction (nx/2+1 nodes; non-nested when the element
 //     count is odd), down to <= `coarsest` nodes; coordinates, velocities and Dirichlet flags of a coarse node are those of
 //     the nearest finer node;
-//   * operators are held as NINE-POINT STENCILS in fp32, one array per neighbour (DIA layout, rows padded to a multiple of
-//     32 floats, one zero guard row above and below, so a sweep needs no index arithmetic and no boundary branch).  Rows
-//     are scaled to a unit diagonal: only the 8 off-diagonal coefficients c_k = a_k / a_diag and the diagonal d are stored
-//     (d = 0 marks a node that is no unknown: Dirichlet node or padding).  Level 0 is converted from the CSR matrix the
-//     solver was handed (kb_apply_dirichlet_reduce's K_b); the coarser levels are REDISCRETISED on the coarser grid by the
-//     path's own element routine (element.cuh) with the Petrov-Galerkin weights of TemperaturePG
-//     (kiltro/VariationalPrinciple.py:216-261,311-342) -- Galerkin products R A P of the central operator diverge once
-//     the coarse cell Peclet number passes 1;
-//   * smoother: nu damped-Jacobi sweeps x += omega (bhat - Ahat x) before and after; 36 B per node cross HBM per sweep
-//     (8 coefficients + rhs, fp32) instead of the 101 B/row of the fp64 CSR SpMV.  fp32 is enough for a preconditioner:
-//     the outer recurrence, its residual and the verdict stay fp64 (right preconditioning: x and r remain consistent
-//     whatever M is);
+//   * operators are held as NINE-POINT STENCILS in fp32: per node the 8 off-diagonal coefficients c_k = a_k / a_diag of the
+//     row scaled to a unit diagonal, interleaved (32 B per node, two 16-byte loads), + the diagonal d and 1/d (d = 0 marks
+//     a node that is no unknown: Dirichlet node or padding).  Rows are padded to a multiple of 32 floats and every array
+//     has MG_GUARD zero rows below and above, so the kernels need neither index arithmetic per neighbour nor boundary
+//     branches.  Level 0 is converted from the CSR matrix the solver was handed (kb_apply_dirichlet_reduce's K_b); the
+//     coarser levels are REDISCRETISED on the coarser grid by the path's own element routine (element.cuh) with the
+//     Petrov-Galerkin weights of TemperaturePG (kiltro/VariationalPrinciple.py:216-261,311-342) -- Galerkin products
+//     R A P of the central operator diverge once the coarse cell Peclet number passes 1;
+//   * smoother: nu damped-Jacobi sweeps x += omega (bhat - Ahat x) before and after; 40 B per node cross HBM per sweep
+//     instead of the 101 B/row of the fp64 CSR SpMV.  fp32 is enough for a preconditioner: the outer recurrence, its
+//     residual and the verdict stay fp64 (right preconditioning: x and r remain consistent whatever M is);
 //   * transfer: bilinear interpolation between the two rectangles from 1-D tables (kb_mg_transfer_table), restriction =
 //     its transpose, both as gather kernels (deterministic);
 //   * coarsest level: dense inverse (Gauss-Jordan on device, one CTA) applied as a mat-vec.
@@ -37,18 +36,19 @@ ElemOpts kb_make_opts(const kb_material *m, int mode, int petrov, int want_mass)
 namespace {
 
 constexpr int MG_MAXLEV = 24;
-constexpr int MG_DENSE_MAX = 1024;        // rows of the coarsest dense system (shared-memory row / factor buffers)
+constexpr int MG_DENSE_MAX = 1023;        // rows of the coarsest dense system (shared-memory row / factor buffers)
+constexpr int MG_DENSE_SMEM = 100;        // up to here the Gauss-Jordan elimination runs in shared memory
+constexpr int MG_GUARD = 8;               // zero rows below / above every padded array (>= NS + unroll overshoot of k_mg_leg)
 
-struct Coef8 { float *c[8]; };            // stencil slots: (dy,dx) = (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
-
+// stencil slots k = 0..7: (dy,dx) = (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1); node pp's coefficients: cf[8 pp + k]
 struct MgLevel {
     int nx = 0, ny = 0, pitch = 0;
-    int64_t np = 0;                       // ny * pitch (padded nodes)
-    Coef8 C = {};
-    float *d = nullptr;                   // diagonal (0: not an unknown)
-    float *bh = nullptr, *xa = nullptr, *xb = nullptr, *r = nullptr;    // fp32 vectors (guarded)
+    int64_t np = 0;                       // ny * pitch (padded nodes, without the guard rows)
+    float *cf = nullptr;                  // 8 coefficients per padded node
+    float *d = nullptr, *dinv = nullptr;  // diagonal (0: not an unknown) and its reciprocal (0 there too)
+    float *bh = nullptr, *xa = nullptr, *xb = nullptr, *r = nullptr;    // fp32 vectors
     double *pts = nullptr, *vel = nullptr;                              // levels >= 1
-    uint8_t *fixed = nullptr;
+    uint8_t *fixed = nullptr;             // compact (nx * ny)
     // transfer to level l+1 (this level is the fine one)
     int *jx = nullptr, *jy = nullptr, *sx = nullptr, *sy = nullptr;
     float *wx = nullptr, *wy = nullptr;
@@ -64,7 +64,8 @@ struct kb_mg {
     int nu = 2;
     float omega = 0.67f;
     int64_t nfree = 0;
-    int *free2pp = nullptr, *free2node = nullptr, *node2free = nullptr;
+    int *free2pp = nullptr, *free2node = nullptr;
+    int *n2f = nullptr;             // level 0, padded like the vectors: unknown of a node, -1 elsewhere
     int ncoarse = 0;
     double *dense = nullptr;
     float *ainv = nullptr;
@@ -77,7 +78,9 @@ struct kb_mg {
 namespace {
 
 size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t vec_floats(const MgLevel &l) { return (size_t)(l.ny + 2) * l.pitch + 64; }
+// elements of a padded array with `w` values per node: guard rows on both sides + 32 values of slack at either end
+size_t padded_elems(const MgLevel &l, int w) { return (size_t)(l.ny + 2 * MG_GUARD) * l.pitch * w + 64; }
+size_t padded_origin(const MgLevel &l, int w) { return (size_t)MG_GUARD * l.pitch * w + 32; }
 
 // 1-D linear interpolation between nf and nc uniformly spaced nodes on the same interval: fine node i sits at
 // s = i (nc-1)/(nf-1) in coarse units -> j = min(floor(s), nc-2), w = s - j  (x_f[i] = (1-w) x_c[j] + w x_c[j+1]);
@@ -104,11 +107,10 @@ size_t carve(kb_mg *mg, char *base, bool assign) {
     for (int l = 0; l < mg->nlev; ++l) {
         MgLevel &L = mg->L[l];
         const size_t nn = (size_t)L.nx * L.ny;
-        for (int k = 0; k < 8; ++k) { float *p = (float *)take(sizeof(float) * L.np); if (assign) L.C.c[k] = p; }
-        { float *p = (float *)take(sizeof(float) * L.np); if (assign) L.d = p; }
-        float *v[4];
-        for (int k = 0; k < 4; ++k) v[k] = (float *)take(sizeof(float) * vec_floats(L)) + L.pitch + 32;
-        if (assign) { L.bh = v[0]; L.xa = v[1]; L.xb = v[2]; L.r = v[3]; }
+        { float *p = (float *)take(sizeof(float) * padded_elems(L, 8)) + padded_origin(L, 8); if (assign) L.cf = p; }
+        float *v[6];
+        for (int k = 0; k < 6; ++k) v[k] = (float *)take(sizeof(float) * padded_elems(L, 1)) + padded_origin(L, 1);
+        if (assign) { L.d = v[0]; L.dinv = v[1]; L.bh = v[2]; L.xa = v[3]; L.xb = v[4]; L.r = v[5]; }
         { uint8_t *p = (uint8_t *)take(nn); if (assign) L.fixed = p; }
         if (l > 0) {
             double *p = (double *)take(sizeof(double) * 2 * nn), *q = (double *)take(sizeof(double) * 2 * nn);
@@ -122,10 +124,12 @@ size_t carve(kb_mg *mg, char *base, bool assign) {
             if (assign) { L.jx = a; L.jy = b; L.sx = c; L.sy = d; L.wx = e; L.wy = f; }
         }
     }
-    const size_t nn0 = (size_t)mg->L[0].nx * mg->L[0].ny;
+    const MgLevel &L0 = mg->L[0];
+    const size_t nn0 = (size_t)L0.nx * L0.ny;
     {
-        int *p = (int *)take(sizeof(int) * nn0), *q = (int *)take(sizeof(int) * nn0), *r = (int *)take(sizeof(int) * nn0);
-        if (assign) { mg->free2pp = p; mg->free2node = q; mg->node2free = r; }
+        int *p = (int *)take(sizeof(int) * nn0), *q = (int *)take(sizeof(int) * nn0);
+        int *r = (int *)take(sizeof(int) * padded_elems(L0, 1)) + padded_origin(L0, 1);
+        if (assign) { mg->free2pp = p; mg->free2node = q; mg->n2f = r; }
     }
     const size_t nc = (size_t)mg->ncoarse;
     { double *p = (double *)take(sizeof(double) * nc * 2 * nc); if (assign) mg->dense = p; }
@@ -138,19 +142,18 @@ __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast
 __device__ __forceinline__ float4 ld4s(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
 
 // ------------------------------------------------------------------------------------------------ set-up kernels
-// reduced DOF -> compact node / padded index (level 0), and the fixed-node mask, from the renumbering of kb_dirichlet_split
+// reduced DOF -> compact node / padded index (level 0), the padded node -> unknown map and the fixed-node mask, from the
+// renumbering of kb_dirichlet_split (n2f is pre-filled with -1)
 __global__ void __launch_bounds__(256) k_mg_free_map(int64_t nn, int nx, int pitch, const int32_t *__restrict__ renum,
                                                      int *__restrict__ free2node, int *__restrict__ free2pp,
-                                                     int *__restrict__ node2free, uint8_t *__restrict__ fixed) {
+                                                     int *__restrict__ n2f, uint8_t *__restrict__ fixed) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += stride) {
         const int f = renum[p];
+        const int pp = (int)(p / nx) * pitch + (int)(p % nx);
         fixed[p] = f < 0;
-        node2free[p] = f >= 0 ? f : -1;
-        if (f >= 0) {
-            free2node[f] = (int)p;
-            free2pp[f] = (int)(p / nx) * pitch + (int)(p % nx);
-        }
+        n2f[pp] = f >= 0 ? f : -1;
+        if (f >= 0) { free2node[f] = (int)p; free2pp[f] = pp; }
     }
 }
 
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(256) k_mg_free_map(int64_t nn, int nx, int pit
 // neighbourhood of its row raises flag[0].
 __global__ void __launch_bounds__(256) k_mg_dia_from_csr(int64_t nfree, const int32_t *__restrict__ indptr,
                                                          const int32_t *__restrict__ indices, const double *__restrict__ vals,
-                                                         const int *__restrict__ free2node, int nx, int pitch, Coef8 C,
-                                                         float *__restrict__ d, int *__restrict__ flag) {
+                                                         const int *__restrict__ free2node, int nx, int pitch,
+                                                         float *__restrict__ cf, float *__restrict__ d,
+                                                         float *__restrict__ dinv, int *__restrict__ flag) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     bool bad = false;
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nfree; f += stride) {
@@ -170,16 +174,23 @@ __global__ void __launch_bounds__(256) k_mg_dia_from_csr(int64_t nfree, const in
         for (int e = e0; e < e1; ++e)
             if (indices[e] == (int)f) dg += vals[e];
         if (!(dg != 0.0) || !isfinite(dg)) dg = 1.0;
-        d[pp] = (float)dg;
         const double inv = 1.0 / dg;
+        d[pp] = (float)dg;
+        dinv[pp] = (float)inv;
+        float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int e = e0; e < e1; ++e) {
             const int c = indices[e];
             if (c == (int)f) continue;
             const int q = free2node[c], dx = q % nx - i, dy = q / nx - j;
             if (dx < -1 || dx > 1 || dy < -1 || dy > 1) { bad = true; continue; }
-            const int k = (dy + 1) * 3 + (dx + 1);
-            C.c[k > 4 ? k - 1 : k][pp] = (float)(vals[e] * inv);
+            const int k = (dy + 1) * 3 + (dx + 1), k8 = k > 4 ? k - 1 : k;
+            const float v = (float)(vals[e] * inv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) out[u] = (u == k8) ? v : out[u];
         }
+        float4 *dst = reinterpret_cast<float4 *>(cf + 8 * pp);
+        dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_float4(out[4], out[5], out[6], out[7]);
     }
     if (bad) flag[0] = 1;
 }
@@ -206,7 +217,8 @@ __global__ void __launch_bounds__(256) k_mg_sample(int nxc, int nyc, int nxf, in
 template <bool VEL>
 __global__ void __launch_bounds__(128) k_mg_assemble_dia(int nx, int ny, int pitch, const double *__restrict__ pts,
                                                          const double *__restrict__ vel, const uint8_t *__restrict__ fixed,
-                                                         ElemOpts o, Coef8 C, float *__restrict__ d) {
+                                                         ElemOpts o, float *__restrict__ cf, float *__restrict__ d,
+                                                         float *__restrict__ dinv) {
     const int64_t nn = (int64_t)nx * ny, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += stride) {
         const int i = (int)(p % nx), j = (int)(p / nx);
@@ -244,22 +256,27 @@ __global__ void __launch_bounds__(128) k_mg_assemble_dia(int nx, int ny, int pit
         }
         double dg = st[4];
         if (!(dg != 0.0) || !isfinite(dg)) dg = 1.0;
-        d[pp] = (float)dg;
         const double inv = 1.0 / dg;
+        d[pp] = (float)dg;
+        dinv[pp] = (float)inv;
+        float out[8];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             if (k == 4) continue;
             const int qi = i + (k % 3) - 1, qj = j + (k / 3) - 1;
             float cv = 0.f;
             if (qi >= 0 && qj >= 0 && qi < nx && qj < ny && !fixed[(int64_t)qj * nx + qi]) cv = (float)(st[k] * inv);
-            C.c[k > 4 ? k - 1 : k][pp] = cv;
+            out[k > 4 ? k - 1 : k] = cv;
         }
+        float4 *dst = reinterpret_cast<float4 *>(cf + 8 * pp);
+        dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_float4(out[4], out[5], out[6], out[7]);
     }
 }
 
 // coarsest level: dense [Ahat | I] (fp64, n x 2n) from the stencil; rows of non-unknowns are identity rows
-__global__ void __launch_bounds__(256) k_mg_dense_build(int nx, int ny, int pitch, Coef8 C, const float *__restrict__ d,
-                                                        double *__restrict__ W) {
+__global__ void __launch_bounds__(256) k_mg_dense_build(int nx, int ny, int pitch, const float *__restrict__ cf,
+                                                        const float *__restrict__ d, double *__restrict__ W) {
     const int n = nx * ny, m = 2 * n, q = blockIdx.x;
     if (q >= n) return;
     double *row = W + (size_t)q * m;
@@ -270,44 +287,74 @@ __global__ void __launch_bounds__(256) k_mg_dense_build(int nx, int ny, int pitc
     if (threadIdx.x < 8 && d[pp] != 0.f) {
         const int k8 = threadIdx.x, k = k8 >= 4 ? k8 + 1 : k8;
         const int qi = i + (k % 3) - 1, qj = j + (k / 3) - 1;
-        if (qi >= 0 && qj >= 0 && qi < nx && qj < ny) row[qj * nx + qi] = (double)C.c[k8][pp];
+        if (qi >= 0 && qj >= 0 && qi < nx && qj < ny) row[qj * nx + qi] = (double)cf[8 * pp + k8];
     }
 }
 
 // Gauss-Jordan without pivoting (rows are scaled to a unit diagonal and the rediscretised operators are diagonally
-// dominant); a vanishing / non-finite pivot raises flag[1].  One CTA; step k touches the window [k, n+k] of every row.
-__global__ void __launch_bounds__(1024) k_mg_dense_invert(int n, double *__restrict__ W, float *__restrict__ ainv,
+// dominant); a vanishing / non-finite pivot raises flag[1].  One CTA.  The matrix is banded (half-width `band` = nodes per
+// grid row + 1): below the pivot, column k is zero outside rows (k, k+band] throughout the elimination (the rows above
+// fill in: the inverse is dense), so step k updates rows [0, k+band] over the window [k, n+k] of columns that can be
+// non-zero.  Thread = one column of the window x every ngrp-th row.  SMEM: the whole [A | I] lives in shared memory
+// (n <= MG_DENSE_SMEM; the default coarsest level) instead of taking an L2 round trip per update.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024) k_mg_dense_invert(int n, int band, double *__restrict__ Wg, float *__restrict__ ainv,
                                                           int *__restrict__ flag) {
+    extern __shared__ double s_dyn[];
     __shared__ double s_row[MG_DENSE_MAX + 1];
     __shared__ double s_fac[MG_DENSE_MAX];
     const int m = 2 * n, tid = threadIdx.x, T = blockDim.x;
+    double *W = Wg;
+    if (SMEM) {
+        W = s_dyn;
+        for (int e = tid; e < n * m; e += T) W[e] = Wg[e];
+        __syncthreads();
+    }
+    const int width = n + 1, ngrp = T / width > 0 ? T / width : 1;
+    const int mycol = tid % width, mygrp = tid / width;
     for (int k = 0; k < n; ++k) {
         const double piv = W[(size_t)k * m + k];
         if (!(fabs(piv) > 1.0e-12) || !isfinite(piv)) { if (tid == 0) flag[1] = 1; return; }   // uniform over the CTA
         const double inv = 1.0 / piv;
+        const int r1 = k + band < n - 1 ? k + band : n - 1;
         for (int c = tid; c <= n; c += T) s_row[c] = W[(size_t)k * m + k + c] * inv;
-        for (int r = tid; r < n; r += T) s_fac[r] = (r == k) ? 0.0 : W[(size_t)r * m + k];
+        for (int r = tid; r <= r1; r += T) s_fac[r] = (r == k) ? 0.0 : W[(size_t)r * m + k];
         __syncthreads();
-        for (int c = tid; c <= n; c += T) W[(size_t)k * m + k + c] = s_row[c];
-        const int width = n + 1;
-        for (int64_t e = tid; e < (int64_t)n * width; e += T) {
-            const int r = (int)(e / width), c = (int)(e % width);
-            const double f = s_fac[r];
-            if (f != 0.0) W[(size_t)r * m + k + c] -= f * s_row[c];
+        if (mygrp < ngrp) {                                  // width <= blockDim.x (n <= MG_DENSE_MAX = 1023)
+            const int c = mycol;
+            const double rc = s_row[c];
+            if (mygrp == 0) W[(size_t)k * m + k + c] = rc;
+            // eight independent read-modify-writes in flight (one dependent round trip per row otherwise)
+            for (int rb = mygrp; rb <= r1; rb += 8 * ngrp) {
+                double wv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = rb + u * ngrp;
+                    wv[u] = r <= r1 ? W[(size_t)r * m + k + c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = rb + u * ngrp;
+                    if (r <= r1) {
+                        const double f = s_fac[r];
+                        if (f != 0.0) W[(size_t)r * m + k + c] = wv[u] - f * rc;
+                    }
+                }
+            }
         }
         __syncthreads();
     }
-    for (int64_t e = tid; e < (int64_t)n * n; e += T) ainv[e] = (float)W[(size_t)(e / n) * m + n + (e % n)];
+    for (int e = tid; e < n * n; e += T) ainv[e] = (float)W[(size_t)(e / n) * m + n + (e % n)];
 }
 
 // ------------------------------------------------------------------------------------------------ V-cycle kernels
 // stage the fp64 reduced vector on the level-0 grid: bh = v / d (0 at non-unknowns), first sweep from zero x = omega bh.
-// With q != NULL the vector is first updated in place, v -= alpha[0] q (BiCGSTAB's s = r - alpha v).
-__global__ void __launch_bounds__(256) k_mg_entry(int nx, int ny, int pitch, const int *__restrict__ node2free,
-                                                  const float *__restrict__ d, double *__restrict__ v,
-                                                  const double *__restrict__ alpha, const double *__restrict__ q,
-                                                  float *__restrict__ bh, float *__restrict__ xa, float omega,
-                                                  const int *__restrict__ done) {
+// With q != NULL the staged vector is s = v - alpha[0] q, also written to s_out (BiCGSTAB's s = r - alpha v).
+__global__ void __launch_bounds__(256) k_mg_entry(int ny, int pitch, const int *__restrict__ n2f,
+                                                  const float *__restrict__ dinv, const double *__restrict__ v,
+                                                  double *__restrict__ s_out, const double *__restrict__ alpha,
+                                                  const double *__restrict__ q, float *__restrict__ bh,
+                                                  float *__restrict__ xa, float omega, const int *__restrict__ done) {
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,13 +363,11 @@ __global__ void __launch_bounds__(256) k_mg_entry(int nx, int ny, int pitch, con
     for (int j = blockIdx.y; j < ny; j += gridDim.y) {
         const int64_t pp = (int64_t)j * pitch + i;
         float b = 0.f;
-        if (i < nx) {
-            const int f = node2free[(int64_t)j * nx + i];
-            if (f >= 0) {
-                double vv = v[f];
-                if (q != nullptr) { vv -= a * __ldcs(q + f); v[f] = vv; }
-                b = (float)(vv / (double)d[pp]);
-            }
+        const int f = n2f[pp];
+        if (f >= 0) {
+            double vv = v[f];
+            if (q != nullptr) { vv -= a * __ldcs(q + f); s_out[f] = vv; }
+            b = (float)vv * dinv[pp];
         }
         bh[pp] = b;
         xa[pp] = omega * b;
@@ -337,52 +382,44 @@ __global__ void __launch_bounds__(256) k_mg_exit(int64_t nfree, const int *__res
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nfree; f += stride) z[f] = (double)x[free2pp[f]];
 }
 
+// the arithmetic of one node, shared by the one-kernel-per-sweep form and the fused legs (same order => same bits):
+// res = bh - x - sum_k c_k x_k ;  sweep: x + omega res ;  residual: d res
+__device__ __forceinline__ float stencil_res(const float (&c)[8], float dl, float dc, float dr, float ml, float mc, float mr,
+                                             float ul, float uc, float ur, float bh) {
+    float acc = c[0] * dl;
+    acc = fmaf(c[1], dc, acc); acc = fmaf(c[2], dr, acc);
+    acc = fmaf(c[3], ml, acc); acc = fmaf(c[4], mr, acc);
+    acc = fmaf(c[5], ul, acc); acc = fmaf(c[6], uc, acc); acc = fmaf(c[7], ur, acc);
+    return bh - mc - acc;
+}
+
 // MODE 0: damped-Jacobi sweep  out = x + omega (bh - x - sum_k c_k x_k)     MODE 1: residual  out = d (bh - x - sum_k c_k x_k)
-// Flat over the padded grid, four nodes per thread (rows are padded to 32 floats, so every float4 is aligned; the guard
-// rows and the zero coefficients of padding / boundary nodes make index arithmetic and branches unnecessary).
+// Flat over the padded grid, one node per thread (the guard rows and the zero coefficients of padding / boundary nodes
+// make index arithmetic and branches unnecessary).  The one-kernel-per-sweep form: fallback for nu > 3 and the
+// cross-check of the fused legs.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_mg_sweep(int64_t np4, int pitch, Coef8 C, const float *__restrict__ d,
-                                                  const float *__restrict__ bh, const float *__restrict__ xi,
-                                                  float *__restrict__ out, float omega, const int *__restrict__ done) {
+__global__ void __launch_bounds__(256) k_mg_sweep(int64_t np, int pitch, const float *__restrict__ cf,
+                                                  const float *__restrict__ d, const float *__restrict__ bh,
+                                                  const float *__restrict__ xi, float *__restrict__ out, float omega,
+                                                  const int *__restrict__ done) {
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < np4; q += stride) {
-        const int64_t p = 4 * q;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
         const float *xc = xi + p, *xd = xc - pitch, *xu = xc + pitch;
-        float m[3][6];
-        {
-            const float4 a = ld4(xd), b = ld4(xc), c = ld4(xu);
-            m[0][1] = a.x; m[0][2] = a.y; m[0][3] = a.z; m[0][4] = a.w; m[0][0] = xd[-1]; m[0][5] = xd[4];
-            m[1][1] = b.x; m[1][2] = b.y; m[1][3] = b.z; m[1][4] = b.w; m[1][0] = xc[-1]; m[1][5] = xc[4];
-            m[2][1] = c.x; m[2][2] = c.y; m[2][3] = c.z; m[2][4] = c.w; m[2][0] = xu[-1]; m[2][5] = xu[4];
-        }
-        float cc[8][4];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float4 v = ld4s(C.c[k] + p);
-            cc[k][0] = v.x; cc[k][1] = v.y; cc[k][2] = v.z; cc[k][3] = v.w;
-        }
-        const float4 bv = ld4(bh + p);
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-        float dd[4] = {0.f, 0.f, 0.f, 0.f};
-        if (MODE == 1) { const float4 dv = ld4(d + p); dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w; }
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float acc = cc[0][e] * m[0][e];
-            acc = fmaf(cc[1][e], m[0][e + 1], acc); acc = fmaf(cc[2][e], m[0][e + 2], acc);
-            acc = fmaf(cc[3][e], m[1][e], acc); acc = fmaf(cc[4][e], m[1][e + 2], acc);
-            acc = fmaf(cc[5][e], m[2][e], acc); acc = fmaf(cc[6][e], m[2][e + 1], acc); acc = fmaf(cc[7][e], m[2][e + 2], acc);
-            const float res = bb[e] - m[1][e + 1] - acc;
-            o[e] = MODE == 0 ? fmaf(omega, res, m[1][e + 1]) : dd[e] * res;
-        }
-        *reinterpret_cast<float4 *>(out + p) = make_float4(o[0], o[1], o[2], o[3]);
+        const float4 lo = ld4s(cf + 8 * p), hi = ld4s(cf + 8 * p + 4);
+        const float cc[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const float mc = xc[0];
+        const float res = stencil_res(cc, xd[-1], xd[0], xd[1], xc[-1], mc, xc[1], xu[-1], xu[0], xu[1], bh[p]);
+        out[p] = MODE == 0 ? fmaf(omega, res, mc) : d[p] * res;
     }
 }
 
-// coarse rhs = P^T (fine residual), scaled to the unit-diagonal system, + the first sweep from zero
-__global__ void __launch_bounds__(128) k_mg_restrict(int nxc, int nyc, int pitch_c, int pitch_f, const float *__restrict__ dc,
+// coarse rhs = P^T (fine residual), scaled to the unit-diagonal system, + the first sweep from zero.  A coarse node
+// gathers the fine nodes of [start[c-1], start[c+1]) in both directions (<= RMAX per direction with the x weights in
+// registers; wider supports -- only when a direction is not coarsened -- fall back to the table walk).
+constexpr int RMAX = 6;
+__global__ void __launch_bounds__(128) k_mg_restrict(int nxc, int nyc, int pitch_c, int pitch_f, const float *__restrict__ dinvc,
                                                      const float *__restrict__ rf, const int *__restrict__ jx,
                                                      const float *__restrict__ wx, const int *__restrict__ sx,
                                                      const int *__restrict__ jy, const float *__restrict__ wy,
@@ -392,35 +429,56 @@ __global__ void __launch_bounds__(128) k_mg_restrict(int nxc, int nyc, int pitch
     if (done != nullptr && *done != 0) return;
     const int ic = blockIdx.x * blockDim.x + threadIdx.x;
     if (ic >= pitch_c) return;
-    int i0 = 0, i1 = 0;
-    if (ic < nxc) { i0 = sx[ic > 0 ? ic - 1 : 0]; i1 = sx[ic + 1 < nxc ? ic + 1 : nxc]; }
+    int i0 = 0, cnt = 0;
+    float wxr[RMAX];
+#pragma unroll
+    for (int u = 0; u < RMAX; ++u) wxr[u] = 0.f;
+    if (ic < nxc) {
+        i0 = sx[ic > 0 ? ic - 1 : 0];
+        cnt = sx[ic + 1 < nxc ? ic + 1 : nxc] - i0;
+        if (cnt <= RMAX) {
+#pragma unroll
+            for (int u = 0; u < RMAX; ++u)
+                if (u < cnt) wxr[u] = (jx[i0 + u] == ic) ? 1.f - wx[i0 + u] : wx[i0 + u];
+        }
+    }
     for (int jc = blockIdx.y; jc < nyc; jc += gridDim.y) {
         const int64_t ppc = (int64_t)jc * pitch_c + ic;
         float b = 0.f;
-        const float dcv = ic < nxc ? dc[ppc] : 0.f;
-        if (dcv != 0.f) {
+        const float dv = ic < nxc ? dinvc[ppc] : 0.f;
+        if (dv != 0.f) {
             const int j0 = sy[jc > 0 ? jc - 1 : 0], j1 = sy[jc + 1 < nyc ? jc + 1 : nyc];
             float acc = 0.f;
             for (int jf = j0; jf < j1; ++jf) {
                 const float wyv = (jy[jf] == jc) ? 1.f - wy[jf] : wy[jf];
-                const float *row = rf + (int64_t)jf * pitch_f;
+                const float *row = rf + (int64_t)jf * pitch_f + i0;
                 float racc = 0.f;
-                for (int f = i0; f < i1; ++f) racc = fmaf((jx[f] == ic) ? 1.f - wx[f] : wx[f], row[f], racc);
+                if (cnt <= RMAX) {
+#pragma unroll
+                    for (int u = 0; u < RMAX; ++u)
+                        if (u < cnt) racc = fmaf(wxr[u], row[u], racc);
+                } else {
+                    for (int u = 0; u < cnt; ++u) racc = fmaf((jx[i0 + u] == ic) ? 1.f - wx[i0 + u] : wx[i0 + u], row[u], racc);
+                }
                 acc = fmaf(wyv, racc, acc);
             }
-            b = acc / dcv;
+            b = acc * dv;
         }
         bhc[ppc] = b;
         xac[ppc] = omega * b;
     }
 }
 
-// x_f += P x_c at the unknowns of the fine level
-__global__ void __launch_bounds__(128) k_mg_prolong(int nxf, int nyf, int pitch_f, int pitch_c, const float *__restrict__ df,
-                                                    const float *__restrict__ xc, const int *__restrict__ jx,
-                                                    const float *__restrict__ wx, const int *__restrict__ jy,
-                                                    const float *__restrict__ wy, float *__restrict__ xf,
-                                                    const int *__restrict__ done) {
+// x_f += P x_c (also at nodes that are no unknowns: nothing reads them -- their columns are zero in every stencil, the
+// residual there is multiplied by d = 0, and the level-0 output is gathered at the unknowns only)
+__device__ __forceinline__ float prolong_value(float c00, float c01, float c10, float c11, float wa, float wb) {
+    const float lo = fmaf(wa, c01 - c00, c00), hi = fmaf(wa, c11 - c10, c10);
+    return fmaf(wb, hi - lo, lo);
+}
+__global__ void __launch_bounds__(128) k_mg_prolong(int nxf, int nyf, int pitch_f, int pitch_c, const float *__restrict__ xc,
+                                                    const int *__restrict__ jx, const float *__restrict__ wx,
+                                                    const int *__restrict__ jy, const float *__restrict__ wy,
+                                                    float *__restrict__ xf, const int *__restrict__ done) {
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,11 +487,8 @@ __global__ void __launch_bounds__(128) k_mg_prolong(int nxf, int nyf, int pitch_
     const float wa = wx[i];
     for (int j = blockIdx.y; j < nyf; j += gridDim.y) {
         const int64_t pp = (int64_t)j * pitch_f + i;
-        if (df[pp] == 0.f) continue;
-        const float wb = wy[j];
         const float *r0 = xc + (int64_t)jy[j] * pitch_c + a, *r1 = r0 + pitch_c;
-        const float lo = fmaf(wa, r0[1] - r0[0], r0[0]), hi = fmaf(wa, r1[1] - r1[0], r1[0]);
-        xf[pp] += fmaf(wb, hi - lo, lo);
+        xf[pp] += prolong_value(r0[0], r0[1], r1[0], r1[1], wa, wy[j]);
     }
 }
 
@@ -443,7 +498,7 @@ __global__ void __launch_bounds__(1024) k_mg_dense_solve(int n, int nx, int pitc
                                                          const int *__restrict__ done) {
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;
-    __shared__ float s_b[MG_DENSE_MAX];
+    __shared__ float s_b[MG_DENSE_MAX + 1];
     for (int q = threadIdx.x; q < n; q += blockDim.x) s_b[q] = bh[(int64_t)(q / nx) * pitch + q % nx];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -454,6 +509,200 @@ __global__ void __launch_bounds__(1024) k_mg_dense_solve(int n, int nx, int pitc
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(KB_FULL, acc, o);
         if (lane == 0) x[(int64_t)(r / nx) * pitch + r % nx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused legs
+// One kernel per leg of the cycle on a level instead of one per sweep (temporal blocking): a WARP sweeps a strip of 32
+// node columns upwards, one node row per step, and runs every stage of the leg on it in a software pipeline --
+//   down-leg:  stage 0  x = omega bh (level 0: bh staged from the fp64 reduced vector, s = r - alpha v on the way)
+//              stages 1..NS-1  damped-Jacobi sweeps, stage NS  residual r = d (bh - Ahat x)           -> x, r (+ bh) out
+//   up-leg:    stage 0  x += P x_coarse, stages 1..NS  sweeps                        -> x out (level 0: fp64 reduced z)
+// Stage s lags stage s-1 by one row; a lane keeps the last three rows (left, centre, right neighbour values, exchanged
+// by warp shuffles) of every stage and the coefficients of the last NS rows in registers, so every coefficient, rhs and
+// x value crosses HBM ONCE per leg instead of once per sweep.  No shared memory, no barrier, no branch in the step: the
+// guard rows and the clamped column index make every load unconditional.  NS halo columns per side and NS halo rows per
+// task are recomputed by the neighbouring strips (valid lanes [NS, 32-NS)); the arithmetic of a node is stencil_res /
+// prolong_value exactly as in the one-kernel-per-sweep form, so both forms agree bit for bit (test_fused_legs_bitwise).
+struct LegArgs {
+    int nx, ny, pitch, rows_per_task, nstrips, ntasks;
+    const float *cf, *d, *dinv;
+    float omega;
+    const float *bh_in;       // rhs (down-leg of levels >= 1, up-leg)
+    float *bh_out;            // level-0 down-leg: rhs staged here
+    const double *v;          // level-0 down-leg: fp64 reduced vector in ...
+    double *s_out;            // ... and where v - alpha q goes when q != NULL
+    const double *alpha, *q;
+    const int *n2f;           // level 0
+    float *x_out, *r_out;
+    const float *x_in;        // up-leg: x after the down-leg
+    const float *xc;          // up-leg: coarse correction
+    int pitch_c;
+    const int *jx, *jy;
+    const float *wx, *wy;
+    double *z;                // level-0 up-leg: fp64 reduced output
+    int pfd;                  // L2 prefetch distance in rows (0 = off)
+    int64_t nfree;
+    const int *done;
+};
+
+template <int NS, bool DOWN, bool L0>
+__global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
+    kb_pdl_wait();
+    if (a.done != nullptr && *a.done != 0) return;
+    static_assert(NS >= 1 && NS + 4 <= MG_GUARD, "guard rows cover the pipeline depth + the unroll overshoot + one row of prefetch");
+    constexpr int U = NS + 1 > 3 ? NS + 1 : 3;        // ring depth of every per-row history (and unroll factor)
+    constexpr int VW = 32 - 2 * NS;                   // columns a warp owns
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= a.ntasks) return;
+    const int strip = task % a.nstrips, ty = task / a.nstrips;
+    const int c = strip * VW - NS + lane;
+    const int pitch = a.pitch;
+    const int cl = c < 0 ? 0 : (c >= pitch ? pitch - 1 : c);          // column the lane loads (results of lanes outside
+                                                                      // the grid are never stored and only ever meet zero
+                                                                      // coefficients in their neighbours' stencils)
+    const int j0 = ty * a.rows_per_task, j1 = j0 + a.rows_per_task < a.ny ? j0 + a.rows_per_task : a.ny;
+    const bool own_col = c >= 0 && c < a.nx && lane >= NS && lane < 32 - NS;
+    const float om = a.omega;
+
+    float cf[U][8], bhh[U], dhh[U], win[NS][U][3];
+    int fhh[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        bhh[u] = 0.f; dhh[u] = 0.f; fhh[u] = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cf[u][k] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { win[s][u][0] = 0.f; win[s][u][1] = 0.f; win[s][u][2] = 0.f; }
+    }
+    int pjx = 0; float pwx = 0.f;                      // per-lane constants of the prolongation
+    if (!DOWN) { const int ci = cl < a.nx ? cl : a.nx - 1; pjx = a.jx[ci]; pwx = a.wx[ci]; }
+    const double alpha = (DOWN && L0 && a.q != nullptr) ? a.alpha[0] : 0.0;
+
+    // L2 prefetch, PFD rows ahead (the loads of a step are consumed one step later: that covers an L2 hit, not a DRAM
+    // round trip).  Lanes 0..15 cover the eight 128-byte lines of the warp's coefficient row segment (+ the misaligned
+    // ninth), lane pairs 16.. the two lines of the other streams.
+    const char *pf_ptr = nullptr;
+    int pf_stride = 0;
+    if (a.pfd > 0) {
+        const int cbase = strip * VW - NS > 0 ? strip * VW - NS : 0;
+        if (lane < 9) { pf_ptr = reinterpret_cast<const char *>(a.cf + 8 * (int64_t)cbase) + 128 * lane; pf_stride = pitch * 32; }
+        else {
+            const int sel = (lane - 9) >> 1, half = (lane - 9) & 1;
+            const void *base = nullptr;
+            if (sel == 0) base = DOWN ? (const void *)a.d : (const void *)a.bh_in;
+            else if (sel == 1) base = DOWN ? (L0 ? (const void *)a.dinv : (const void *)a.bh_in) : (const void *)a.x_in;
+            else if (sel == 2 && L0) base = a.n2f;
+            if (base != nullptr) { pf_ptr = reinterpret_cast<const char *>(base) + 4 * (int64_t)cbase + 128 * half; pf_stride = pitch * 4; }
+        }
+    }
+
+    // stage-0 inputs of the next row, loaded one step ahead (the node -> unknown map of the level-0 down-leg two steps
+    // ahead: the fp64 vector is addressed through it)
+    float p_bh = 0.f, p_d = 0.f, p_di = 0.f, p_x = 0.f, p_c00 = 0.f, p_c01 = 0.f, p_c10 = 0.f, p_c11 = 0.f, p_wy = 0.f;
+    double p_v = 0.0;
+    int p_f = -1, n_f = -1;
+    auto load_stage0 = [&](int row) {
+        const int off = row * pitch + cl;
+        if (DOWN) {
+            p_d = a.d[off];
+            if (L0) {
+                const int f_prev = p_f;
+                p_f = n_f;
+                n_f = a.n2f[off + pitch];
+                p_di = a.dinv[off];
+                p_v = 0.0;
+                if (p_f >= 0) {
+                    p_v = a.v[p_f];
+                    if (a.q != nullptr) p_v -= alpha * __ldcs(a.q + p_f);
+                }
+                if (a.pfd > 2 && (lane & 15) == 0 && p_f >= 0 && f_prev >= 0) {   // predicted address of the vector rows ahead
+                    int64_t fp = (int64_t)p_f + (int64_t)(a.pfd - 1) * (p_f - f_prev);
+                    fp = fp < 0 ? 0 : (fp >= a.nfree ? a.nfree - 1 : fp);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.v + fp));
+                    if (a.q != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.q + fp));
+                }
+            } else {
+                p_bh = a.bh_in[off];
+            }
+        } else {
+            p_bh = a.bh_in[off];
+            p_x = a.x_in[off];
+            const int rr = row < 0 ? 0 : (row >= a.ny ? a.ny - 1 : row);
+            p_wy = a.wy[rr];
+            const float *r0 = a.xc + a.jy[rr] * a.pitch_c + pjx;
+            p_c00 = r0[0]; p_c01 = r0[1]; p_c10 = r0[a.pitch_c]; p_c11 = r0[a.pitch_c + 1];
+            if (L0) p_f = a.n2f[off];
+        }
+    };
+
+    const int T0 = j0 - NS, T1 = j1 + NS;             // stage 0 walks rows [T0, T1)
+    if (DOWN && L0) n_f = a.n2f[T0 * pitch + cl];
+    load_stage0(T0);
+    for (int tb = T0; tb < T1; tb += U) {
+#pragma unroll
+        for (int ph = 0; ph < U; ++ph) {
+            const int t = tb + ph;
+            // ---- stage 0 on row t
+            float b0, x0;
+            if (DOWN) {
+                if (L0) b0 = (p_f >= 0) ? (float)p_v * p_di : 0.f;
+                else b0 = p_bh;
+                x0 = om * b0;
+                const bool st0 = own_col && t >= j0 && t < j1;
+                if (L0 && st0) {
+                    a.bh_out[t * pitch + c] = b0;
+                    if (a.q != nullptr && p_f >= 0) a.s_out[p_f] = p_v;
+                }
+                if (NS == 1 && st0) a.x_out[t * pitch + c] = x0;
+            } else {
+                b0 = p_bh;
+                x0 = p_x + prolong_value(p_c00, p_c01, p_c10, p_c11, pwx, p_wy);
+            }
+            bhh[ph] = b0;
+            dhh[ph] = p_d;
+            fhh[ph] = p_f;
+            win[0][ph][1] = x0;
+            win[0][ph][0] = __shfl_up_sync(KB_FULL, x0, 1);
+            win[0][ph][2] = __shfl_down_sync(KB_FULL, x0, 1);
+            // ---- loads: the coefficients of row t (first used by stage 1 at the next step), stage-0 inputs of row t+1
+            {
+                const float *pc = a.cf + 8 * (int64_t)(t * pitch + cl);
+                const float4 lo = ld4s(pc), hi = ld4s(pc + 4);
+                cf[ph][0] = lo.x; cf[ph][1] = lo.y; cf[ph][2] = lo.z; cf[ph][3] = lo.w;
+                cf[ph][4] = hi.x; cf[ph][5] = hi.y; cf[ph][6] = hi.z; cf[ph][7] = hi.w;
+            }
+            load_stage0(t + 1);
+            if (pf_ptr != nullptr && t + a.pfd < a.ny + MG_GUARD)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (int64_t)(t + a.pfd) * pf_stride));
+            // ---- stages 1..NS on rows t-1 .. t-NS
+#pragma unroll
+            for (int s = 1; s <= NS; ++s) {
+                const int sl = (ph - s + 2 * U) % U, sd = (sl + U - 1) % U, su = (sl + 1) % U;
+                const int js = t - s;
+                const float (&w)[U][3] = win[s - 1];
+                const float xc0 = w[sl][1];
+                const float res = stencil_res(cf[sl], w[sd][0], w[sd][1], w[sd][2], w[sl][0], xc0, w[sl][2],
+                                              w[su][0], w[su][1], w[su][2], bhh[sl]);
+                const bool store = own_col && js >= j0 && js < j1;
+                if (DOWN && s == NS) {
+                    if (store) a.r_out[js * pitch + c] = dhh[sl] * res;
+                } else {
+                    const float val = fmaf(om, res, xc0);
+                    if (s < NS) {
+                        win[s][sl][1] = val;
+                        win[s][sl][0] = __shfl_up_sync(KB_FULL, val, 1);
+                        win[s][sl][2] = __shfl_down_sync(KB_FULL, val, 1);
+                    }
+                    if (DOWN && s == NS - 1 && store) a.x_out[js * pitch + c] = val;
+                    if (!DOWN && s == NS && store) {
+                        if (L0) { if (fhh[sl] >= 0) a.z[fhh[sl]] = (double)val; }
+                        else a.x_out[js * pitch + c] = val;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -468,10 +717,92 @@ dim3 grid2d(int width, int block, int ny) {
 
 template <int MODE>
 int launch_sweep(const MgLevel &L, const float *xi, float *out, float omega, const int *done, cudaStream_t s, bool pdl) {
-    const int64_t np4 = L.np / 4;
-    KB_CUDA(kb_launch_pdl(k_mg_sweep<MODE>, dim3(kb_grid(np4, 256, 8)), dim3(256), 0, s, pdl, np4, L.pitch, L.C,
-                          (const float *)L.d, (const float *)L.bh, xi, out, omega, done));
+    KB_CUDA(kb_launch_pdl(k_mg_sweep<MODE>, dim3(kb_grid(L.np, 256, 8)), dim3(256), 0, s, pdl, L.np, L.pitch,
+                          (const float *)L.cf, (const float *)L.d, (const float *)L.bh, xi, out, omega, done));
     KB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_restrict(const MgLevel &L, const MgLevel &Cn, float omega, const int *done, cudaStream_t s, bool pdl) {
+    // one coarse node per thread (no row loop: the gather is a chain of dependent table and residual loads)
+    const dim3 grid((unsigned)kb_cdiv(Cn.pitch, 128), (unsigned)(Cn.ny < 65535 ? Cn.ny : 65535));
+    KB_CUDA(kb_launch_pdl(k_mg_restrict, grid, dim3(128), 0, s, pdl, Cn.nx, Cn.ny, Cn.pitch,
+                          L.pitch, (const float *)Cn.dinv, (const float *)L.r, (const int *)L.jx, (const float *)L.wx,
+                          (const int *)L.sx, (const int *)L.jy, (const float *)L.wy, (const int *)L.sy, Cn.bh, Cn.xa,
+                          omega, done));
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
+int g_mg_fused = 1;           // 1: fused legs (k_mg_leg) where nu <= 3 ; 0: one kernel per sweep (kb_mg_set_fused)
+int g_mg_rows_per_task = 0;   // node rows per warp task of the fused legs; 0 = chosen per level (kb_mg_set_rows_per_task)
+int g_mg_pfd = 6;             // L2 prefetch distance of the fused legs, in rows (kb_mg_set_prefetch_rows)
+
+template <int NS, bool DOWN, bool L0>
+int launch_leg(LegArgs a, cudaStream_t s, bool pdl) {
+    constexpr int VW = 32 - 2 * NS;
+    a.nstrips = (int)kb_cdiv(a.nx, VW);
+    if (g_mg_rows_per_task > 0) a.rows_per_task = g_mg_rows_per_task;
+    else {      // enough warps to fill the machine a few times over, tasks no longer than 64 rows, no shorter than 8
+        int64_t r = (int64_t)a.nstrips * a.ny / ((int64_t)kb_num_sms() * 48);
+        a.rows_per_task = (int)(r < 8 ? 8 : (r > 64 ? 64 : r));
+    }
+    a.pfd = g_mg_pfd;
+    a.ntasks = a.nstrips * (int)kb_cdiv(a.ny, a.rows_per_task);
+    KB_CUDA(kb_launch_pdl(k_mg_leg<NS, DOWN, L0>, dim3((unsigned)kb_cdiv(a.ntasks, 8)), dim3(256), 0, s, pdl, a));
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+template <bool DOWN, bool L0>
+int launch_leg_ns(int ns, const LegArgs &a, cudaStream_t s, bool pdl) {
+    switch (ns) {
+        case 1: return launch_leg<1, DOWN, L0>(a, s, pdl);
+        case 2: return launch_leg<2, DOWN, L0>(a, s, pdl);
+        case 3: return launch_leg<3, DOWN, L0>(a, s, pdl);
+        default: return KB_EINVAL;
+    }
+}
+
+LegArgs leg_args(const kb_mg *mg, const MgLevel &L, const int *done) {
+    LegArgs a = {};
+    a.nx = L.nx; a.ny = L.ny; a.pitch = L.pitch; a.cf = L.cf; a.d = L.d; a.dinv = L.dinv; a.omega = mg->omega; a.done = done;
+    a.nfree = mg->nfree;
+    return a;
+}
+
+int apply_fused(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const double *d_alpha, const double *d_q,
+                const int *done, cudaStream_t s, bool pdl) {
+    const int nl = mg->nlev, ns = mg->nu;
+    int rc;
+    for (int l = 0; l + 1 < nl; ++l) {                       // down: x -> xa, residual -> r, restricted rhs -> bh of l+1
+        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
+        LegArgs a = leg_args(mg, L, done);
+        a.x_out = L.xa; a.r_out = L.r;
+        if (l == 0) {
+            a.bh_out = L.bh; a.v = d_v; a.s_out = d_s; a.alpha = d_alpha; a.q = d_q; a.n2f = mg->n2f;
+            rc = launch_leg_ns<true, true>(ns, a, s, pdl);
+        } else {
+            a.bh_in = L.bh;
+            rc = launch_leg_ns<true, false>(ns, a, s, pdl);
+        }
+        if (rc) return rc;
+        if ((rc = launch_restrict(L, Cn, mg->omega, done, s, pdl))) return rc;
+    }
+    {
+        const MgLevel &L = mg->L[nl - 1];
+        KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, s, pdl, mg->ncoarse, L.nx, L.pitch,
+                              (const float *)mg->ainv, (const float *)L.bh, L.xb, done));
+        KB_LAUNCH_CHECK();
+    }
+    for (int l = nl - 2; l >= 0; --l) {                      // up: xa (+ P xb of l+1) -> xb ; level 0 -> z
+        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
+        LegArgs a = leg_args(mg, L, done);
+        a.bh_in = L.bh; a.x_in = L.xa; a.xc = Cn.xb; a.pitch_c = Cn.pitch; a.jx = L.jx; a.jy = L.jy; a.wx = L.wx; a.wy = L.wy;
+        a.x_out = L.xb;
+        if (l == 0) { a.z = d_z; a.n2f = mg->n2f; rc = launch_leg_ns<false, true>(ns, a, s, pdl); }
+        else rc = launch_leg_ns<false, false>(ns, a, s, pdl);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -480,18 +811,19 @@ int launch_sweep(const MgLevel &L, const float *xi, float *out, float omega, con
 int64_t kbmg_nfree(const kb_mg *mg) { return mg->nfree; }
 bool kbmg_ready(const kb_mg *mg) { return mg->ready; }
 
-int kbmg_apply(kb_mg *mg, double *d_v, double *d_z, const double *d_alpha, const double *d_q, const int *done,
-               cudaStream_t s, bool pdl) {
-    if (!mg || !mg->ready || !d_v || !d_z) return KB_EINVAL;
+int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const double *d_alpha, const double *d_q,
+               const int *done, cudaStream_t s, bool pdl) {
+    if (!mg || !mg->ready || !d_v || !d_z || (d_q != nullptr && (!d_s || !d_alpha || d_s == d_v))) return KB_EINVAL;
     const int nl = mg->nlev;
+    if (g_mg_fused && mg->nu <= 3 && nl >= 2) return apply_fused(mg, d_v, d_s, d_z, d_alpha, d_q, done, s, pdl);
     const float om = mg->omega;
     float *cur[MG_MAXLEV], *oth[MG_MAXLEV];
     for (int l = 0; l < nl; ++l) { cur[l] = mg->L[l].xa; oth[l] = mg->L[l].xb; }
     int rc;
     {
         const MgLevel &L = mg->L[0];
-        KB_CUDA(kb_launch_pdl(k_mg_entry, grid2d(L.pitch, 256, L.ny), dim3(256), 0, s, pdl, L.nx, L.ny, L.pitch,
-                              (const int *)mg->node2free, (const float *)L.d, d_v, d_alpha, d_q, L.bh, L.xa, om, done));
+        KB_CUDA(kb_launch_pdl(k_mg_entry, grid2d(L.pitch, 256, L.ny), dim3(256), 0, s, pdl, L.ny, L.pitch,
+                              (const int *)mg->n2f, (const float *)L.dinv, d_v, d_s, d_alpha, d_q, L.bh, L.xa, om, done));
         KB_LAUNCH_CHECK();
     }
     for (int l = 0; l + 1 < nl; ++l) {
@@ -501,11 +833,7 @@ int kbmg_apply(kb_mg *mg, double *d_v, double *d_z, const double *d_alpha, const
             float *t = cur[l]; cur[l] = oth[l]; oth[l] = t;
         }
         if ((rc = launch_sweep<1>(L, cur[l], L.r, om, done, s, pdl))) return rc;
-        KB_CUDA(kb_launch_pdl(k_mg_restrict, grid2d(Cn.pitch, 128, Cn.ny), dim3(128), 0, s, pdl, Cn.nx, Cn.ny, Cn.pitch,
-                              L.pitch, (const float *)Cn.d, (const float *)L.r, (const int *)L.jx, (const float *)L.wx,
-                              (const int *)L.sx, (const int *)L.jy, (const float *)L.wy, (const int *)L.sy, Cn.bh, Cn.xa,
-                              om, done));
-        KB_LAUNCH_CHECK();
+        if ((rc = launch_restrict(L, Cn, om, done, s, pdl))) return rc;
     }
     {
         const MgLevel &L = mg->L[nl - 1];
@@ -516,8 +844,8 @@ int kbmg_apply(kb_mg *mg, double *d_v, double *d_z, const double *d_alpha, const
     for (int l = nl - 2; l >= 0; --l) {
         const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
         KB_CUDA(kb_launch_pdl(k_mg_prolong, grid2d(L.nx, 128, L.ny), dim3(128), 0, s, pdl, L.nx, L.ny, L.pitch, Cn.pitch,
-                              (const float *)L.d, (const float *)cur[l + 1], (const int *)L.jx, (const float *)L.wx,
-                              (const int *)L.jy, (const float *)L.wy, cur[l], done));
+                              (const float *)cur[l + 1], (const int *)L.jx, (const float *)L.wx, (const int *)L.jy,
+                              (const float *)L.wy, cur[l], done));
         KB_LAUNCH_CHECK();
         for (int k = 0; k < mg->nu; ++k) {
             if ((rc = launch_sweep<0>(L, cur[l], oth[l], om, done, s, pdl))) return rc;
@@ -539,7 +867,8 @@ extern "C" int kb_mg_transfer_table(int64_t nfine, int64_t ncoarse, int32_t *h_j
 
 extern "C" int kb_mg_create(int64_t nxn, int64_t nyn, int64_t coarsest_nodes, kb_mg **out) {
     if (!out || nxn < 2 || nyn < 2) return KB_EINVAL;
-    if (nxn * nyn > (int64_t)INT32_MAX / 2) return KB_ETOOBIG;
+    // 32-bit indices into the interleaved coefficient array (8 per padded node, guard rows included)
+    if ((nyn + 2 * MG_GUARD) * ((nxn + 32) / 32 * 32) >= ((int64_t)1 << 28) - 64) return KB_ETOOBIG;
     if (coarsest_nodes < 4) coarsest_nodes = 4;
     if (coarsest_nodes > MG_DENSE_MAX) coarsest_nodes = MG_DENSE_MAX;
     kb_mg *mg = new (std::nothrow) kb_mg();
@@ -606,11 +935,12 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
     // coefficient arrays and vectors start from zero (padding, guard rows, absent neighbours)
     for (int l = 0; l < mg->nlev; ++l) {
         MgLevel &L = mg->L[l];
-        for (int k = 0; k < 8; ++k) KB_CUDA(cudaMemsetAsync(L.C.c[k], 0, sizeof(float) * L.np, s));
-        KB_CUDA(cudaMemsetAsync(L.d, 0, sizeof(float) * L.np, s));
+        KB_CUDA(cudaMemsetAsync(L.cf - padded_origin(L, 8), 0, sizeof(float) * padded_elems(L, 8), s));
+        KB_CUDA(cudaMemsetAsync(L.d - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+        KB_CUDA(cudaMemsetAsync(L.dinv - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
         if (first) {
             float *v[4] = {L.bh, L.xa, L.xb, L.r};
-            for (int k = 0; k < 4; ++k) KB_CUDA(cudaMemsetAsync(v[k] - L.pitch - 32, 0, sizeof(float) * vec_floats(L), s));
+            for (int k = 0; k < 4; ++k) KB_CUDA(cudaMemsetAsync(v[k] - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
             if (l + 1 < mg->nlev) {
                 const MgLevel &Cn = mg->L[l + 1];
                 KB_CUDA(cudaMemcpyAsync(L.jx, L.h_jx.data(), sizeof(int) * L.nx, cudaMemcpyHostToDevice, s));
@@ -622,12 +952,13 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
             }
         }
     }
+    KB_CUDA(cudaMemsetAsync(mg->n2f - padded_origin(L0, 1), 0xff, sizeof(int) * padded_elems(L0, 1), s));   // -1
     KB_CUDA(cudaMemsetAsync(mg->flag, 0, sizeof(int) * 8, s));
-    k_mg_free_map<<<kb_grid(nn0, 256, 8), 256, 0, s>>>(nn0, L0.nx, L0.pitch, d_renum, mg->free2node, mg->free2pp,
-                                                       mg->node2free, L0.fixed);
+    k_mg_free_map<<<kb_grid(nn0, 256, 8), 256, 0, s>>>(nn0, L0.nx, L0.pitch, d_renum, mg->free2node, mg->free2pp, mg->n2f,
+                                                       L0.fixed);
     KB_LAUNCH_CHECK();
     k_mg_dia_from_csr<<<kb_grid(nfree, 256, 8), 256, 0, s>>>(nfree, d_indptr, d_indices, d_vals, mg->free2node, L0.nx,
-                                                            L0.pitch, L0.C, L0.d, mg->flag);
+                                                            L0.pitch, L0.cf, L0.d, L0.dinv, mg->flag);
     KB_LAUNCH_CHECK();
     const ElemOpts o = kb_make_opts(material, KB_MODE_CONSISTENT, d_velocity != nullptr ? 1 : 0, 0);
     for (int l = 1; l < mg->nlev; ++l) {
@@ -638,16 +969,28 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         k_mg_sample<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, F.nx, F.ny, pf, vf, F.fixed, L.pts, L.vel, L.fixed);
         KB_LAUNCH_CHECK();
         if (d_velocity != nullptr)
-            k_mg_assemble_dia<true><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.C, L.d);
+            k_mg_assemble_dia<true><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
         else
-            k_mg_assemble_dia<false><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.C, L.d);
+            k_mg_assemble_dia<false><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
         KB_LAUNCH_CHECK();
     }
     {
         const MgLevel &Lc = mg->L[mg->nlev - 1];
-        k_mg_dense_build<<<mg->ncoarse, 256, 0, s>>>(Lc.nx, Lc.ny, Lc.pitch, Lc.C, Lc.d, mg->dense);
+        const int n = mg->ncoarse;
+        k_mg_dense_build<<<n, 256, 0, s>>>(Lc.nx, Lc.ny, Lc.pitch, Lc.cf, Lc.d, mg->dense);
         KB_LAUNCH_CHECK();
-        k_mg_dense_invert<<<1, 1024, 0, s>>>(mg->ncoarse, mg->dense, mg->ainv, mg->flag);
+        if (n <= MG_DENSE_SMEM) {
+            const size_t bytes = sizeof(double) * (size_t)n * 2 * n;
+            static bool configured = false;
+            if (!configured) {
+                KB_CUDA(cudaFuncSetAttribute(k_mg_dense_invert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(double) * MG_DENSE_SMEM * 2 * MG_DENSE_SMEM)));
+                configured = true;
+            }
+            k_mg_dense_invert<true><<<1, 1024, bytes, s>>>(n, Lc.nx + 1, mg->dense, mg->ainv, mg->flag);
+        } else {
+            k_mg_dense_invert<false><<<1, 1024, 0, s>>>(n, Lc.nx + 1, mg->dense, mg->ainv, mg->flag);
+        }
         KB_LAUNCH_CHECK();
     }
     int flag[2] = {0, 0};
@@ -660,5 +1003,11 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
 }
 
 extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stream) {
-    return kbmg_apply(mg, const_cast<double *>(d_v), d_z, nullptr, nullptr, nullptr, (cudaStream_t)stream, false);
+    return kbmg_apply(mg, d_v, nullptr, d_z, nullptr, nullptr, nullptr, (cudaStream_t)stream, false);
 }
+
+/* development switches: fused legs on / off (results are bit-identical), node rows per warp task of the fused legs
+ * (0 = chosen per level), their L2 prefetch distance */
+extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
+extern "C" void kb_mg_set_rows_per_task(int rows) { if (rows >= 0) g_mg_rows_per_task = rows; }
+extern "C" void kb_mg_set_prefetch_rows(int rows) { if (rows >= 0) g_mg_pfd = rows; }

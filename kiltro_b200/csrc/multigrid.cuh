@@ -6,9 +6,10 @@
 struct kb_mg;      // host-side plan + device pointers into the caller's workspace (include/kiltro_b200.h: opaque)
 
 // z = V-cycle(v): v, z fp64 vectors of the REDUCED system (length nfree); stream-ordered, no host synchronisation.
-// With d_alpha / d_q the kernel that stages v first applies  v -= alpha[0] * q  (BiCGSTAB's s = r - alpha v rides along).
+// With d_alpha / d_q the vector that is preconditioned is  s = v - alpha[0] * q, and the kernel that stages it also writes
+// it to d_s (!= d_v): BiCGSTAB's s = r - alpha v rides along.
 // `done` (may be NULL): device flag, a non-zero value turns every kernel of the cycle into an early exit.
-int kbmg_apply(kb_mg *mg, double *d_v, double *d_z, const double *d_alpha, const double *d_q, const int *done,
-               cudaStream_t s, bool pdl);
+int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const double *d_alpha, const double *d_q,
+               const int *done, cudaStream_t s, bool pdl);
 int64_t kbmg_nfree(const kb_mg *mg);
 bool kbmg_ready(const kb_mg *mg);

@@ -22,7 +22,7 @@ from . import _lib, device as D
 
 class GridMultigrid(object):
 
-    def __init__(self, mesh, formulation, material, boundary_condition, nu=2, omega=0.67, coarsest=300, check_every=2):
+    def __init__(self, mesh, formulation, material, boundary_condition, nu=3, omega=0.67, coarsest=100, check_every=2):
         from .FiniteElements.fused import grid_shape
         if formulation.ndim != 2 or formulation.nvar != 1:
             raise ValueError("GridMultigrid needs a 2-D scalar problem")

@@ -1,0 +1,12 @@
+#!/bin/bash
+# ncu evidence for the opt-in multigrid solver (run under gpurun): launch list of one S16 solve through scripts/mg_probe.py
+# (plain run first), then --set full captures of the level-0 sweep and of the outer SpMV.  Usage: scripts/mg_ncu.sh <tag>
+TAG=${1:-r02}
+CMD="python scripts/mg_probe.py 4000 nojac"
+mkdir -p gpurun_out
+$CMD > gpurun_out/mg_plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/mg_plain_$TAG.log; exit 1; }
+tail -3 gpurun_out/mg_plain_$TAG.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/mg_launches_$TAG.csv $CMD > gpurun_out/mg_ncu_list_$TAG.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_mg_sweep -s 30 -c 2 -f -o gpurun_out/prof_mg_sweep_$TAG $CMD > gpurun_out/mg_ncu_full_$TAG.log 2>&1
+echo "full capture (sweep) rc=$?"

@@ -132,6 +132,43 @@ def test_vcycle_is_a_contraction_and_linear():
     assert torch.equal(mg.apply(r1), z1)
 
 
+@pytest.mark.parametrize("nps,nu", [(301, 2), (301, 1), (301, 3), (130, 2), (47, 3)])
+def test_fused_legs_bitwise(nps, nu):
+    """The fused legs (one kernel per leg and level: temporal blocking in registers) reproduce the one-kernel-per-sweep
+    cycle bit for bit, for every task height, with and without the s = r - alpha v update riding in the staging kernel."""
+    import bench
+    import kiltro_b200 as K
+    from kiltro_b200 import _lib
+    from kiltro_b200.multigrid import GridMultigrid
+    lib = _lib.load()
+    mesh, vel, flags, mat = bench.make_problem(K, torch, nps)
+    form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    fs = K.FEMSolver(verbose=False)
+    Kc = K.Assemble(fs, form.function_spaces, form, mesh, mat, bc)[0]
+    bc.GetDirichletBoundaryConditions(form, mesh, mat, fs)
+    F = torch.zeros((mesh.nnodes, 1), dtype=torch.float64, device="cuda")
+    Kb, Fb = bc.ApplyDirichletGetReducedMatrices(Kc, F, bc.applied_dirichlet_device)[:2]
+    mg = GridMultigrid(mesh, form, mat, bc, nu=nu)
+    mg.setup(Kb)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    r = torch.randn(Kb.shape[0], dtype=torch.float64, device="cuda", generator=g)
+    try:
+        lib.kb_mg_set_fused(0)
+        ref = mg.apply(r)
+        x_ref, info_ref = mg.solve(Kb, Fb.reshape(-1), rtol=1e-11, reuse_setup=True)
+        lib.kb_mg_set_fused(1)
+        for rows in (64, 8, 23, 1000):
+            lib.kb_mg_set_rows_per_task(rows)
+            assert torch.equal(mg.apply(r), ref), rows
+        lib.kb_mg_set_rows_per_task(64)
+        x, info = mg.solve(Kb, Fb.reshape(-1), rtol=1e-11, reuse_setup=True)
+        assert info["iterations"] == info_ref["iterations"] and info["status"] == 0, (info, info_ref)
+        assert torch.equal(x, x_ref)
+    finally:
+        lib.kb_mg_set_fused(1); lib.kb_mg_set_rows_per_task(64)
+
+
 def test_multigrid_rejects_what_it_cannot_precondition():
     import kiltro_b200 as K
     from kiltro_b200.multigrid import GridMultigrid
