@@ -279,14 +279,13 @@ int launch_fused(int64_t ntiles, cudaStream_t s, const double *points, const dou
                  const int32_t *indptr, const int32_t *indices, const int32_t *tile_rows, const int32_t *tile_row_ptr,
                  const int32_t *tile_conn, const int32_t *tile_elem_ptr, const uint32_t *pair_rec,
                  const int32_t *pair_ptr, double *K, double *M, double *Flux, uint8_t *scratch) {
-    static bool configured = false;
+    static KbOncePerDevice configured;
     constexpr size_t bytes = Smem<NDIM>::bytes;
-    if (!configured) {
+    if (configured.need()) {
         KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         KB_CUDA(cudaFuncSetAttribute(k_assemble_fused<NDIM, HAS_U, MASS, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
     }
     const int64_t cap = (int64_t)kb_num_sms() * 2;           // persistent: 2 CTAs per SM
     const int grid = (int)(ntiles < cap ? ntiles : cap);

@@ -251,12 +251,11 @@ int launch_tmpl(int64_t ntiles, cudaStream_t s, const double *points, const doub
                 const int32_t *indptr, const int32_t *tile_conn, const int32_t *tile_elem_ptr,
                 const uint8_t *tile_class, const int32_t *trun_ptr, const int32_t *trun_row, const void *templates,
                 double *K, double *M, double *Flux, uint8_t *scratch) {
-    static bool configured = false;
+    static KbOncePerDevice configured;
     constexpr size_t bytes = sizeof(SmemT);
-    if (!configured) {
+    if (configured.need()) {
         KB_CUDA(cudaFuncSetAttribute(k_assemble_tmpl<HAS_U, MASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         KB_CUDA(cudaFuncSetAttribute(k_assemble_tmpl<HAS_U, MASS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
     }
     const int64_t cap = (int64_t)kb_num_sms() * 2;           // persistent: 2 CTAs per SM
     const int grid = (int)(ntiles < cap ? ntiles : cap);

@@ -422,12 +422,11 @@ extern "C" int kb_apply_dirichlet_reduce(int64_t ndof, const int32_t *d_indptr, 
     int nnzb = 0;
     KB_CUDA(cudaMemcpyAsync(&nnzb, ws + kbscan::num_tiles(n_free + 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     if (ndof > 0) {
-        static bool configured = false;
+        static KbOncePerDevice configured;
         constexpr size_t bytes_m = (size_t)FB_CAP * (4 * 8 + 2 * 4), bytes_s = (size_t)FB_CAP * (2 * 8 + 2 * 4);
-        if (!configured) {
+        if (configured.need()) {
             KB_CUDA(cudaFuncSetAttribute(k_reduced_fill_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_m));
             KB_CUDA(cudaFuncSetAttribute(k_reduced_fill_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_s));
-            configured = true;
         }
         const int gf = kb_grid(kb_cdiv(ndof, FB_ROWS) * FB_ROWS, FB_ROWS, 4);
         if (d_M) k_reduced_fill_flat<true><<<gf, FB_ROWS, bytes_m, s>>>(ndof, d_indptr, d_indices, d_K, d_M, d_renum, d_applied,

@@ -25,6 +25,19 @@ extern int64_t g_kb_launches;          // api.cu
 
 static inline int64_t kb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Function attributes (cudaFuncSetAttribute) are per device: `static KbOncePerDevice once; if (once.need()) { ... }`
+// runs the block once for every device ordinal a process uses (a process-wide flag would skip the second device).
+struct KbOncePerDevice {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // Programmatic dependent launch (sm_90+): a kernel launched with kb_launch_pdl may become resident while the previous
 // kernel of the stream is still draining; everything it does before kb_pdl_wait() (shared-memory set-up, loads of data
 // the previous kernel does not write) overlaps that tail and the launch latency.  kb_pdl_wait() returns when the

@@ -417,11 +417,10 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
     if (row_pat != nullptr) {                           // row-pattern form: 8 bytes per non-zero cross HBM
         // like the 16-bit form it addresses x relative to the first row of the view: never fall back silently
         if (pat_tab == nullptr || g_force_simple_spmv || !tma_eligible(indptr, row_pat, vals)) return KB_EINVAL;
-        static bool configured = false;                 // one flag per template instantiation
+        static KbOncePerDevice configured;                 // one flag per template instantiation
         constexpr size_t bytes = pat_smem_bytes();
-        if (!configured) {
+        if (configured.need()) {
             KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured = true;
         }
         KB_CUDA(kb_launch_pdl(k_spmv_pat<DOTS, Final>, dim3(tma_grid(nblk)), dim3(P_THREADS), bytes, s, pdl, nblk, indptr,
                               row_pat, pat_tab, vals, rowblk, x, y, dotw, partials, ticket, done, fin, dotw2, pwait, EpiNone{}));
@@ -431,21 +430,19 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
     // 16-bit offsets change the meaning of x (relative to the first row of the view): never fall back silently
     if (indices16 != nullptr && (g_force_simple_spmv || !tma_eligible(indptr, indices16, vals))) return KB_EINVAL;
     if (indices16 != nullptr) {
-        static bool configured16 = false;
+        static KbOncePerDevice configured16;
         constexpr size_t bytes = tma_smem_bytes<short>();
-        if (!configured16) {
+        if (configured16.need()) {
             KB_CUDA(cudaFuncSetAttribute(k_spmv_tma<DOTS, Final, short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured16 = true;
         }
         k_spmv_tma<DOTS, Final, short><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, (const short *)indices16, vals,
                                                                                rowblk, x, y, dotw, partials, ticket, done, fin,
                                                                                dotw2, pwait);
     } else if (!g_force_simple_spmv && tma_eligible(indptr, indices, vals)) {
-        static bool configured = false;          // one flag per template instantiation
+        static KbOncePerDevice configured;          // one flag per template instantiation
         constexpr size_t bytes = tma_smem_bytes<int>();
-        if (!configured) {
+        if (configured.need()) {
             KB_CUDA(cudaFuncSetAttribute(k_spmv_tma<DOTS, Final, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured = true;
         }
         k_spmv_tma<DOTS, Final, int><<<tma_grid(nblk), T_THREADS, bytes, s>>>(nblk, indptr, indices, vals, rowblk, x, y, dotw,
                                                                              partials, ticket, done, fin, dotw2, pwait);

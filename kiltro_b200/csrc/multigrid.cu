@@ -981,11 +981,10 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         KB_LAUNCH_CHECK();
         if (n <= MG_DENSE_SMEM) {
             const size_t bytes = sizeof(double) * (size_t)n * 2 * n;
-            static bool configured = false;
-            if (!configured) {
+            static KbOncePerDevice configured;
+            if (configured.need()) {
                 KB_CUDA(cudaFuncSetAttribute(k_mg_dense_invert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(sizeof(double) * MG_DENSE_SMEM * 2 * MG_DENSE_SMEM)));
-                configured = true;
             }
             k_mg_dense_invert<true><<<1, 1024, bytes, s>>>(n, Lc.nx + 1, mg->dense, mg->ainv, mg->flag);
         } else {

@@ -20,10 +20,12 @@ namespace {
 // one thread per element entry idx = e*cap + i*ndof + b  (ndof = npe*nvar, cap = ndof^2)
 template <int NPE>
 __global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ elements, int64_t nent, int nvar,
-                                                   int cbits, uint64_t *__restrict__ keys,
-                                                   uint32_t *__restrict__ payload, int32_t *__restrict__ data_local) {
+                                                   int cbits, int64_t nnode, uint64_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ payload, int32_t *__restrict__ data_local,
+                                                   int *__restrict__ bad) {
     const int ndof = NPE * nvar, cap = ndof * ndof;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool out_of_range = false;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nent; idx += stride) {
         const int64_t e = idx / cap;
         const int r = (int)(idx - e * cap);
@@ -31,7 +33,12 @@ __global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ e
         // stable insertion argsort of the element's nodes ("sorter", .pyx:51)
         int node[NPE], sorter[NPE];
 #pragma unroll
-        for (int a = 0; a < NPE; ++a) { node[a] = __ldg(elements + e * NPE + a); sorter[a] = a; }
+        for (int a = 0; a < NPE; ++a) {
+            node[a] = __ldg(elements + e * NPE + a); sorter[a] = a;
+            // a node id outside [0, nnode) would overflow the (row << cbits | col) key and send the head pass out of
+            // bounds: clamp it (the result is discarded) and report KB_EINVAL
+            if (node[a] < 0 || node[a] >= nnode) { out_of_range = true; node[a] = 0; }
+        }
 #pragma unroll
         for (int a = 1; a < NPE; ++a) {
 #pragma unroll
@@ -55,6 +62,7 @@ __global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ e
         payload[idx] = (uint32_t)idx;
         data_local[idx] = (rs * nvar + ic) * ndof + (cs * nvar + bc);                               // .h:114
     }
+    if (out_of_range) *bad = 1;              // benign race: every writer stores the same value
 }
 
 // ----------------------------------------------------------------------------------------------- heads -> CSR
@@ -129,22 +137,27 @@ extern "C" int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int np
         return 0;
     }
 
-    // scratch: double-buffered keys/payload, per-tile histograms, scan spine
+    // scratch: double-buffered keys/payload, per-tile histograms, scan spine -- released on EVERY exit path
     const int64_t nhist = kbradix::hist_ints(nent);
     const int64_t scan_ws = kbscan::workspace_ints(nent > nhist ? nent : nhist);
-    uint64_t *keys[2];
-    uint32_t *vals[2];
-    int *hist, *scanws;
-    KB_CUDA(cudaMallocAsync((void **)&keys[0], sizeof(uint64_t) * nent, s));
-    KB_CUDA(cudaMallocAsync((void **)&keys[1], sizeof(uint64_t) * nent, s));
-    KB_CUDA(cudaMallocAsync((void **)&vals[0], sizeof(uint32_t) * nent, s));
-    KB_CUDA(cudaMallocAsync((void **)&vals[1], sizeof(uint32_t) * nent, s));
-    KB_CUDA(cudaMallocAsync((void **)&hist, sizeof(int) * nhist, s));
-    KB_CUDA(cudaMallocAsync((void **)&scanws, sizeof(int) * scan_ws, s));
+    struct Scratch {
+        cudaStream_t s;
+        void *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        explicit Scratch(cudaStream_t st) : s(st) {}
+        ~Scratch() { for (void *q : p) if (q) cudaFreeAsync(q, s); }
+    } scratch(s);
+    const size_t bytes[7] = {sizeof(uint64_t) * (size_t)nent, sizeof(uint64_t) * (size_t)nent, sizeof(uint32_t) * (size_t)nent,
+                             sizeof(uint32_t) * (size_t)nent, sizeof(int) * (size_t)nhist, sizeof(int) * (size_t)scan_ws,
+                             sizeof(int) * 4};
+    for (int k = 0; k < 7; ++k) KB_CUDA(cudaMallocAsync(&scratch.p[k], bytes[k], s));
+    uint64_t *keys[2] = {(uint64_t *)scratch.p[0], (uint64_t *)scratch.p[1]};
+    uint32_t *vals[2] = {(uint32_t *)scratch.p[2], (uint32_t *)scratch.p[3]};
+    int *hist = (int *)scratch.p[4], *scanws = (int *)scratch.p[5], *bad = (int *)scratch.p[6];
+    KB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int) * 4, s));
 
     const int g = kb_grid(nent, 256, 8);
-    if (npe == 4) k_make_keys<4><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, keys[0], vals[0], d_data_local);
-    else k_make_keys<2><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, keys[0], vals[0], d_data_local);
+    if (npe == 4) k_make_keys<4><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, nnode, keys[0], vals[0], d_data_local, bad);
+    else k_make_keys<2><<<g, 256, 0, s>>>(d_elements, nent, nvar, cbits, nnode, keys[0], vals[0], d_data_local, bad);
     KB_LAUNCH_CHECK();
 
     int cur = 0;
@@ -160,15 +173,11 @@ extern "C" int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int np
     const int64_t nt = kbscan::num_tiles(nent);
     k_pattern_tail<<<1, 256, 0, s>>>(keys[cur], nent, cbits, nrows, scanws + nt, d_indptr, d_seg_ptr);
     KB_LAUNCH_CHECK();
-    int nnz32 = 0;
+    int nnz32 = 0, bad_h = 0;
     KB_CUDA(cudaMemcpyAsync(&nnz32, scanws + nt, sizeof(int), cudaMemcpyDeviceToHost, s));
-    KB_CUDA(cudaFreeAsync(keys[0], s));
-    KB_CUDA(cudaFreeAsync(keys[1], s));
-    KB_CUDA(cudaFreeAsync(vals[0], s));
-    KB_CUDA(cudaFreeAsync(vals[1], s));
-    KB_CUDA(cudaFreeAsync(hist, s));
-    KB_CUDA(cudaFreeAsync(scanws, s));
+    KB_CUDA(cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
     KB_CUDA(cudaStreamSynchronize(s));
+    if (bad_h) return KB_EINVAL;             // connectivity refers to a node outside [0, nnode)
     *h_nnz = nnz32;
     return 0;
 }

@@ -157,10 +157,9 @@ extern "C" int kb_tile_tmpl_build(int npe, int64_t nnode, int64_t ntiles, const 
     h_info[0] = 0; h_info[1] = 0; h_info[2] = 0;
     if (npe != 4 || ntiles < 1 || nnode < 1) return 0;               // templates serve the quad kernel only
     cudaStream_t s = (cudaStream_t)stream;
-    static bool configured = false;
-    if (!configured) {
+    static KbOncePerDevice configured;
+    if (configured.need()) {
         KB_CUDA(cudaFuncSetAttribute(k_tmpl_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        configured = true;
     }
     const PlanView pv{d_indptr, d_tile_rows, d_tile_row_ptr, d_tile_elem_ptr, d_pair_ptr, d_pair_rec};
     unsigned long long *d_hash;
