@@ -171,6 +171,15 @@ int kb_assemble_grid(const double *d_points, const double *d_velocity, const kb_
                      int64_t nxn, int64_t nyn, const int32_t *d_indptr, double *d_K, double *d_M, double *d_Flux,
                      void *d_scratch, void *stream);
 
+/* (e) fused path, grid form for LINE meshes numbered like Mesh.Line (MeshGeneration/Mesh.py:14-30: element i = [i, i+1]).
+ *     kb_line_verify checks the connectivity (*d_flag = 0: it matches); kb_assemble_line evaluates, per node, the element
+ *     matrices of its two elements in registers (VariationalPrinciple.py:42-69,117-161) and writes the node's tridiagonal
+ *     CSR row; contributions are added in ascending element order (Assembly.py:46,60-61), results equal
+ *     kb_assemble_fused's to rounding.  d_M / d_velocity may be NULL. */
+int kb_line_verify(const int32_t *d_elements, int64_t nelem, int64_t nnode, int32_t *d_flag, void *stream);
+int kb_assemble_line(const double *d_points, const double *d_velocity, const kb_material *material, int mode, int petrov,
+                     int64_t nnode, const int32_t *d_indptr, double *d_K, double *d_M, double *d_Flux, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * K10 element operators of the "next" rows (seam form: element matrices to HBM, then kb_assemble_from_elements)
  *   KB_OP_ROBIN         replaces AssemblyRobinForces (FiniteElements/Assembly.py:121-175): Ke = h sum_g N (x) N dV,
@@ -450,11 +459,14 @@ int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_velocity, con
                 const int32_t *d_indices, const double *d_vals, int nu, double omega, void *d_workspace,
                 size_t workspace_bytes, void *stream);
 int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stream);
+/* per-sweep damping factors h_omega[0..nu) (nu <= 4) instead of one omega; pass omega <= 0 to kb_mg_setup to keep them */
+int kb_mg_set_smoother(kb_mg *mg, int nu, const double *h_omega);
 /* development switches: fused legs of the cycle (one kernel per leg and level instead of one per sweep; bit-identical
  * results) on / off, and the node rows per warp task of the fused kernels */
 void kb_mg_set_fused(int on);
 void kb_mg_set_rows_per_task(int rows);
 void kb_mg_set_prefetch_rows(int rows);   /* L2 prefetch distance of the fused kernels (0 = off) */
+void kb_mg_set_prefetch_rows_l1(int rows);   /* L1 prefetch distance (0, 1 or 2 rows) */
 /* x: initial guess in, solution out; verdict, restarts and kb_solve_info as kb_bicgstab_solve (TRUE residual of the
  * system as handed over).  Synchronises the stream every check_every iterations. */
 size_t kb_mg_bicgstab_workspace_bytes(int64_t nrows, int64_t nnz);

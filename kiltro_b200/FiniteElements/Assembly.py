@@ -40,8 +40,13 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
     if method in (("auto", "fused_grid") if GRID_IN_AUTO else ("fused_grid",)) and formulation.nvar == 1 and formulation.ndim == 2:
         from .fused import assemble_grid, grid_shape
         use_grid = grid_shape(sp, mesh) is not None              # Mesh.Rectangle numbering, verified on device (cached)
+    use_line = False
+    if method in (("auto", "fused_grid") if GRID_IN_AUTO else ("fused_grid",)) and formulation.nvar == 1 and formulation.ndim == 1:
+        from .fused import assemble_line, line_numbered
+        use_grid = use_line = bool(line_numbered(sp, mesh))      # Mesh.Line numbering: the 1-D grid form
     if method == "fused_grid" and not use_grid:
-        raise _lib.KiltroB200Error("assembly='fused_grid' needs a quad-4 mesh numbered like Mesh.Rectangle")
+        raise _lib.KiltroB200Error("assembly='fused_grid' needs a quad-4 mesh numbered like Mesh.Rectangle or a line mesh "
+                                   "numbered like Mesh.Line")
     if not use_grid and method != "two_pass" and formulation.nvar == 1:
         from .fused import assemble_fused, build_tile_plan
         if sp.tile_plan is None:
@@ -51,7 +56,9 @@ def Assemble(fem_solver, function_spaces, formulation, mesh, material, boundary_
             raise _lib.KiltroB200Error("the tile plan of this mesh does not fit the fused assembly kernel: %r"
                                        % (sp.tile_plan.info,))
     fem_solver.assembly_used = "fused" if use_fused else "two_pass"
-    if use_grid:
+    if use_line:
+        assemble_line(fem_solver, sp, formulation, mesh, material, K, M, Flux)
+    elif use_grid:
         assemble_grid(fem_solver, sp, formulation, mesh, material, K, M, Flux)
     elif use_fused:
         assemble_fused(fem_solver, sp, formulation, mesh, material, K, M, Flux)

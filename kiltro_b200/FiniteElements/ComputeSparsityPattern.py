@@ -22,6 +22,7 @@ class SparsityPattern(object):
         self.tile_plan = None
         self.grid = None          # None: not checked; False / (nxn, nyn): Mesh.Rectangle numbering (fused.grid_shape)
         self.grid_scratch = None
+        self.line = None          # None: not checked; True / False: Mesh.Line numbering (fused.line_numbered)
 
     def to_numpy(self):
         return (D.to_numpy(self.indices), D.to_numpy(self.indptr), D.to_numpy(self.data_local_indices),

@@ -40,6 +40,27 @@ def grid_shape(sp, mesh):
     return sp.grid or None
 
 
+def line_numbered(sp, mesh):
+    """True when a line-2 mesh is numbered like Mesh.Line (element i = [i, i+1]); checked on device once, cached with the
+    pattern -- csrc/assemble_line.cu."""
+    if getattr(sp, "line", None) is None:
+        sp.line = False
+        el = mesh.device_elements()
+        if sp.nvar == 1 and el.dim() == 2 and int(el.shape[1]) == 2 and int(el.shape[0]) > 0 and int(mesh.nnodes) >= 2:
+            flag = D.empty(1, torch.int32)
+            _lib.check(_lib.load().kb_line_verify(D.ptr(el), int(el.shape[0]), int(mesh.nnodes), D.ptr(flag), D.stream_ptr()))
+            sp.line = int(flag.item()) == 0
+    return sp.line
+
+
+def assemble_line(fem_solver, sp, formulation, mesh, material, K, M, Flux):
+    fem_solver.assembly_used = "fused_line"
+    pts, vel = mesh.device_points(), formulation.device_velocity()
+    _lib.check(_lib.load().kb_assemble_line(D.ptr(pts), D.ptr(vel), material.as_struct(), int(formulation.mode),
+                                            int(bool(formulation.petrov)), int(mesh.nnodes), D.ptr(sp.indptr), D.ptr(K),
+                                            D.ptr(M), D.ptr(Flux), D.stream_ptr()))
+
+
 def assemble_grid(fem_solver, sp, formulation, mesh, material, K, M, Flux):
     nxn, nyn = sp.grid
     fem_solver.assembly_used = "fused_grid"

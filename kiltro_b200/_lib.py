@@ -74,6 +74,8 @@ SIGNATURES = {
     "kb_grid_verify": (I32, [c_vp, I64, I64, I64, c_vp, c_vp]),
     "kb_assemble_grid": (I32, [c_vp, c_vp, ctypes.POINTER(kb_material), I32, I32, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                c_vp]),
+    "kb_line_verify": (I32, [c_vp, I64, I64, c_vp, c_vp]),
+    "kb_assemble_line": (I32, [c_vp, c_vp, ctypes.POINTER(kb_material), I32, I32, I64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_element_operator": (I32, [I32, I32, c_vp, c_vp, I64, c_vp, F64, F64, c_vp, c_vp, c_vp]),
     "kb_axpby": (I32, [I64, F64, c_vp, F64, c_vp, c_vp, c_vp]),
     "kb_dirichlet_split_workspace_bytes": (ctypes.c_size_t, [I64]),
@@ -156,9 +158,11 @@ SIGNATURES = {
     "kb_mg_setup": (I32, [c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(kb_material), I32, I64, I64, c_vp, c_vp, c_vp, I32, F64,
                           c_vp, ctypes.c_size_t, c_vp]),
     "kb_mg_apply": (I32, [c_vp, c_vp, c_vp, c_vp]),
+    "kb_mg_set_smoother": (I32, [c_vp, I32, ctypes.POINTER(F64)]),
     "kb_mg_set_fused": (None, [I32]),
     "kb_mg_set_rows_per_task": (None, [I32]),
     "kb_mg_set_prefetch_rows": (None, [I32]),
+    "kb_mg_set_prefetch_rows_l1": (None, [I32]),
     "kb_mg_bicgstab_workspace_bytes": (ctypes.c_size_t, [I64, I64]),
     "kb_mg_bicgstab_solve": (I32, [c_vp, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, F64, I32, I32, c_vp, ctypes.c_size_t,
                                    ctypes.POINTER(kb_solve_info), c_vp]),

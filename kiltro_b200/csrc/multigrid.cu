@@ -62,7 +62,7 @@ struct kb_mg {
     int nlev = 0;
     MgLevel L[MG_MAXLEV];
     int nu = 2;
-    float omega = 0.67f;
+    float omega[4] = {0.67f, 0.67f, 0.67f, 0.67f};   // damping of sweep 1..nu (pre- and post-smoothing alike)
     int64_t nfree = 0;
     int *free2pp = nullptr, *free2node = nullptr;
     int *n2f = nullptr;             // level 0, padded like the vectors: unknown of a node, -1 elsewhere
@@ -386,11 +386,12 @@ __global__ void __launch_bounds__(256) k_mg_exit(int64_t nfree, const int *__res
 // res = bh - x - sum_k c_k x_k ;  sweep: x + omega res ;  residual: d res
 __device__ __forceinline__ float stencil_res(const float (&c)[8], float dl, float dc, float dr, float ml, float mc, float mr,
                                              float ul, float uc, float ur, float bh) {
-    float acc = c[0] * dl;
-    acc = fmaf(c[1], dc, acc); acc = fmaf(c[2], dr, acc);
-    acc = fmaf(c[3], ml, acc); acc = fmaf(c[4], mr, acc);
-    acc = fmaf(c[5], ul, acc); acc = fmaf(c[6], uc, acc); acc = fmaf(c[7], ur, acc);
-    return bh - mc - acc;
+    // two independent chains of four (a single chain of eight dependent FMAs showed up as fixed-latency stalls)
+    float a0 = c[0] * dl, a1 = c[4] * mr;
+    a0 = fmaf(c[1], dc, a0); a1 = fmaf(c[5], ul, a1);
+    a0 = fmaf(c[2], dr, a0); a1 = fmaf(c[6], uc, a1);
+    a0 = fmaf(c[3], ml, a0); a1 = fmaf(c[7], ur, a1);
+    return (bh - mc) - (a0 + a1);
 }
 
 // MODE 0: damped-Jacobi sweep  out = x + omega (bh - x - sum_k c_k x_k)     MODE 1: residual  out = d (bh - x - sum_k c_k x_k)
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(1024) k_mg_dense_solve(int n, int nx, int pitc
 struct LegArgs {
     int nx, ny, pitch, rows_per_task, nstrips, ntasks;
     const float *cf, *d, *dinv;
-    float omega;
+    float omega[4];           // damping of sweep 1, 2, ... of the leg
     const float *bh_in;       // rhs (down-leg of levels >= 1, up-leg)
     float *bh_out;            // level-0 down-leg: rhs staged here
     const double *v;          // level-0 down-leg: fp64 reduced vector in ...
@@ -542,12 +543,14 @@ struct LegArgs {
     const float *wx, *wy;
     double *z;                // level-0 up-leg: fp64 reduced output
     int pfd;                  // L2 prefetch distance in rows (0 = off)
+    int pf1;                  // L1 prefetch distance in rows (0 = off)
     int64_t nfree;
     const int *done;
 };
 
-template <int NS, bool DOWN, bool L0>
-__global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
+// (two CTAs per SM: nu = 3 needs ~120 registers; capping it at 85 for a third CTA spills and ran 16 % slower)
+template <int NS, bool DOWN, bool L0, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
     kb_pdl_wait();
     if (a.done != nullptr && *a.done != 0) return;
     static_assert(NS >= 1 && NS + 4 <= MG_GUARD, "guard rows cover the pipeline depth + the unroll overshoot + one row of prefetch");
@@ -564,8 +567,6 @@ __global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
                                                                       // coefficients in their neighbours' stencils)
     const int j0 = ty * a.rows_per_task, j1 = j0 + a.rows_per_task < a.ny ? j0 + a.rows_per_task : a.ny;
     const bool own_col = c >= 0 && c < a.nx && lane >= NS && lane < 32 - NS;
-    const float om = a.omega;
-
     float cf[U][8], bhh[U], dhh[U], win[NS][U][3];
     int fhh[U];
 #pragma unroll
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
             if (DOWN) {
                 if (L0) b0 = (p_f >= 0) ? (float)p_v * p_di : 0.f;
                 else b0 = p_bh;
-                x0 = om * b0;
+                x0 = a.omega[0] * b0;
                 const bool st0 = own_col && t >= j0 && t < j1;
                 if (L0 && st0) {
                     a.bh_out[t * pitch + c] = b0;
@@ -676,6 +677,20 @@ __global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
             load_stage0(t + 1);
             if (pf_ptr != nullptr && t + a.pfd < a.ny + MG_GUARD)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (int64_t)(t + a.pfd) * pf_stride));
+            if (a.pf1 > 0) {       // ... and into L1 a couple of rows ahead: the demand loads of the next steps then hit L1
+                const int rp = t + a.pf1 < a.ny + MG_GUARD - 1 ? t + a.pf1 : a.ny + MG_GUARD - 1;
+                const int offp = rp * pitch + cl;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cf + 8 * (int64_t)offp));
+                if (DOWN) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.d + offp));
+                    if (L0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.dinv + offp));
+                    else asm volatile("prefetch.global.L1 [%0];" ::"l"(a.bh_in + offp));
+                } else {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.bh_in + offp));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.x_in + offp));
+                }
+                if (L0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.n2f + offp));
+            }
             // ---- stages 1..NS on rows t-1 .. t-NS
 #pragma unroll
             for (int s = 1; s <= NS; ++s) {
@@ -689,7 +704,7 @@ __global__ void __launch_bounds__(256) k_mg_leg(const LegArgs a) {
                 if (DOWN && s == NS) {
                     if (store) a.r_out[js * pitch + c] = dhh[sl] * res;
                 } else {
-                    const float val = fmaf(om, res, xc0);
+                    const float val = fmaf(a.omega[DOWN ? s : s - 1], res, xc0);   // down: sweep s+1 of nu, up: sweep s
                     if (s < NS) {
                         win[s][sl][1] = val;
                         win[s][sl][0] = __shfl_up_sync(KB_FULL, val, 1);
@@ -737,6 +752,7 @@ int launch_restrict(const MgLevel &L, const MgLevel &Cn, float omega, const int 
 int g_mg_fused = 1;           // 1: fused legs (k_mg_leg) where nu <= 3 ; 0: one kernel per sweep (kb_mg_set_fused)
 int g_mg_rows_per_task = 0;   // node rows per warp task of the fused legs; 0 = chosen per level (kb_mg_set_rows_per_task)
 int g_mg_pfd = 6;             // L2 prefetch distance of the fused legs, in rows (kb_mg_set_prefetch_rows)
+int g_mg_pf1 = 2;             // L1 prefetch distance (kb_mg_set_prefetch_rows_l1)
 
 template <int NS, bool DOWN, bool L0>
 int launch_leg(LegArgs a, cudaStream_t s, bool pdl) {
@@ -748,8 +764,9 @@ int launch_leg(LegArgs a, cudaStream_t s, bool pdl) {
         a.rows_per_task = (int)(r < 8 ? 8 : (r > 64 ? 64 : r));
     }
     a.pfd = g_mg_pfd;
+    a.pf1 = g_mg_pf1;
     a.ntasks = a.nstrips * (int)kb_cdiv(a.ny, a.rows_per_task);
-    KB_CUDA(kb_launch_pdl(k_mg_leg<NS, DOWN, L0>, dim3((unsigned)kb_cdiv(a.ntasks, 8)), dim3(256), 0, s, pdl, a));
+    KB_CUDA(kb_launch_pdl(k_mg_leg<NS, DOWN, L0, 2>, dim3((unsigned)kb_cdiv(a.ntasks, 8)), dim3(256), 0, s, pdl, a));
     KB_LAUNCH_CHECK();
     return 0;
 }
@@ -765,7 +782,8 @@ int launch_leg_ns(int ns, const LegArgs &a, cudaStream_t s, bool pdl) {
 
 LegArgs leg_args(const kb_mg *mg, const MgLevel &L, const int *done) {
     LegArgs a = {};
-    a.nx = L.nx; a.ny = L.ny; a.pitch = L.pitch; a.cf = L.cf; a.d = L.d; a.dinv = L.dinv; a.omega = mg->omega; a.done = done;
+    a.nx = L.nx; a.ny = L.ny; a.pitch = L.pitch; a.cf = L.cf; a.d = L.d; a.dinv = L.dinv; a.done = done;
+    for (int k = 0; k < 4; ++k) a.omega[k] = mg->omega[k];
     a.nfree = mg->nfree;
     return a;
 }
@@ -786,7 +804,7 @@ int apply_fused(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const do
             rc = launch_leg_ns<true, false>(ns, a, s, pdl);
         }
         if (rc) return rc;
-        if ((rc = launch_restrict(L, Cn, mg->omega, done, s, pdl))) return rc;
+        if ((rc = launch_restrict(L, Cn, mg->omega[0], done, s, pdl))) return rc;
     }
     {
         const MgLevel &L = mg->L[nl - 1];
@@ -816,24 +834,24 @@ int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const dou
     if (!mg || !mg->ready || !d_v || !d_z || (d_q != nullptr && (!d_s || !d_alpha || d_s == d_v))) return KB_EINVAL;
     const int nl = mg->nlev;
     if (g_mg_fused && mg->nu <= 3 && nl >= 2) return apply_fused(mg, d_v, d_s, d_z, d_alpha, d_q, done, s, pdl);
-    const float om = mg->omega;
+    const float *om = mg->omega;
     float *cur[MG_MAXLEV], *oth[MG_MAXLEV];
     for (int l = 0; l < nl; ++l) { cur[l] = mg->L[l].xa; oth[l] = mg->L[l].xb; }
     int rc;
     {
         const MgLevel &L = mg->L[0];
         KB_CUDA(kb_launch_pdl(k_mg_entry, grid2d(L.pitch, 256, L.ny), dim3(256), 0, s, pdl, L.ny, L.pitch,
-                              (const int *)mg->n2f, (const float *)L.dinv, d_v, d_s, d_alpha, d_q, L.bh, L.xa, om, done));
+                              (const int *)mg->n2f, (const float *)L.dinv, d_v, d_s, d_alpha, d_q, L.bh, L.xa, om[0], done));
         KB_LAUNCH_CHECK();
     }
     for (int l = 0; l + 1 < nl; ++l) {
         const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
         for (int k = 1; k < mg->nu; ++k) {
-            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om, done, s, pdl))) return rc;
+            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om[k], done, s, pdl))) return rc;
             float *t = cur[l]; cur[l] = oth[l]; oth[l] = t;
         }
-        if ((rc = launch_sweep<1>(L, cur[l], L.r, om, done, s, pdl))) return rc;
-        if ((rc = launch_restrict(L, Cn, om, done, s, pdl))) return rc;
+        if ((rc = launch_sweep<1>(L, cur[l], L.r, 0.f, done, s, pdl))) return rc;
+        if ((rc = launch_restrict(L, Cn, om[0], done, s, pdl))) return rc;
     }
     {
         const MgLevel &L = mg->L[nl - 1];
@@ -848,7 +866,7 @@ int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const dou
                               (const float *)L.wy, cur[l], done));
         KB_LAUNCH_CHECK();
         for (int k = 0; k < mg->nu; ++k) {
-            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om, done, s, pdl))) return rc;
+            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om[k], done, s, pdl))) return rc;
             float *t = cur[l]; cur[l] = oth[l]; oth[l] = t;
         }
     }
@@ -919,7 +937,7 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
                            const int32_t *d_indices, const double *d_vals, int nu, double omega, void *d_workspace,
                            size_t workspace_bytes, void *stream) {
     if (!mg || !d_points || !d_renum || !material || !d_indptr || !d_indices || !d_vals || !d_workspace || nfree < 1 ||
-        nnz < 1 || nu < 1 || !(omega > 0.0 && omega < 2.0))
+        nnz < 1 || nu < 1 || !(omega < 2.0))
         return KB_EINVAL;
     if (d_velocity != nullptr && mode != KB_MODE_CONSISTENT) return KB_EINVAL;   // coarse levels: W (x) u.gradN + PG weights
     if (workspace_bytes < carve(mg, nullptr, false)) return KB_EWORKSPACE;
@@ -928,7 +946,9 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
     const bool first = mg->ws_base != d_workspace;      // new workspace: vectors zeroed, transfer tables uploaded
     carve(mg, (char *)d_workspace, true);
     mg->ws_base = d_workspace;
-    mg->nu = nu; mg->omega = (float)omega; mg->nfree = nfree; mg->has_velocity = d_velocity != nullptr;
+    if (nu > 4 && !(omega > 0.0)) return KB_EINVAL;
+    mg->nu = nu; mg->nfree = nfree;
+    if (omega > 0.0) for (int k = 0; k < 4; ++k) mg->omega[k] = (float)omega;      // omega <= 0: keep kb_mg_set_smoother's factors mg->has_velocity = d_velocity != nullptr;
     MgLevel &L0 = mg->L[0];
     const int64_t nn0 = (int64_t)L0.nx * L0.ny;
     if (nfree > nn0) return KB_EINVAL;
@@ -1010,3 +1030,13 @@ extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stre
 extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
 extern "C" void kb_mg_set_rows_per_task(int rows) { if (rows >= 0) g_mg_rows_per_task = rows; }
 extern "C" void kb_mg_set_prefetch_rows(int rows) { if (rows >= 0) g_mg_pfd = rows; }
+extern "C" void kb_mg_set_prefetch_rows_l1(int rows) { if (rows >= 0 && rows <= 2) g_mg_pf1 = rows; }
+
+/* per-sweep damping factors (a Chebyshev / Richardson sequence instead of one omega): sweep k of the nu pre- and of the nu
+ * post-smoothing sweeps uses h_omega[k]; nu <= 4.  Pass omega <= 0 to kb_mg_setup to keep them. */
+extern "C" int kb_mg_set_smoother(kb_mg *mg, int nu, const double *h_omega) {
+    if (!mg || !h_omega || nu < 1 || nu > 4) return KB_EINVAL;
+    for (int k = 0; k < 4; ++k) mg->omega[k] = (float)h_omega[k < nu ? k : nu - 1];
+    mg->nu = nu;
+    return 0;
+}

@@ -35,7 +35,11 @@ class GridMultigrid(object):
         if shape is None:
             raise _lib.KiltroB200Error("GridMultigrid needs a quad-4 mesh numbered like Mesh.Rectangle")
         self.lib = _lib.load()
-        self.nu, self.omega, self.check_every = int(nu), float(omega), int(check_every)
+        # omega: one damping factor, or a sequence of nu per-sweep factors (e.g. a Chebyshev sequence)
+        self.omegas = [float(w) for w in omega] if hasattr(omega, "__len__") else None
+        self.nu, self.omega, self.check_every = int(nu), (-1.0 if self.omegas else float(omega)), int(check_every)
+        if self.omegas is not None and len(self.omegas) != self.nu:
+            raise ValueError("omega must be one number or nu numbers")
         self.mesh, self.formulation, self.material, self.boundary_condition = mesh, formulation, material, boundary_condition
         handle = ctypes.c_void_p()
         _lib.check(self.lib.kb_mg_create(int(shape[0]), int(shape[1]), int(coarsest), ctypes.byref(handle)))
@@ -45,6 +49,8 @@ class GridMultigrid(object):
             nx, ny = _lib.I64(), _lib.I64()
             _lib.check(self.lib.kb_mg_level_shape(self._h, l, ctypes.byref(nx), ctypes.byref(ny)))
             self.levels.append((int(nx.value), int(ny.value)))
+        if self.omegas is not None:
+            _lib.check(self.lib.kb_mg_set_smoother(self._h, self.nu, (_lib.F64 * self.nu)(*self.omegas)))
         self._ws = D.empty(int(self.lib.kb_mg_workspace_bytes(self._h)), torch.uint8)
         self._solve_ws = None
         self.cycles = 0

@@ -20,7 +20,10 @@ if "MG_ROWS" in os.environ:
     _L.load().kb_mg_set_rows_per_task(int(os.environ["MG_ROWS"]))
 if "MG_PFD" in os.environ:
     _L.load().kb_mg_set_prefetch_rows(int(os.environ["MG_PFD"]))
-NU = int(os.environ.get("MG_NU", "2"))
+if "MG_PF1" in os.environ:
+    _L.load().kb_mg_set_prefetch_rows_l1(int(os.environ["MG_PF1"]))
+NU = int(os.environ.get("MG_NU", "3"))
+OMEGA = [float(v) for v in os.environ["MG_OMEGAS"].split(",")] if "MG_OMEGAS" in os.environ else 0.67
 nps = int(sys.argv[1]) if len(sys.argv) > 1 else 1025
 mesh, vel, flags, material = bench.make_problem(K, torch, nps)
 form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
@@ -40,7 +43,7 @@ if "nojac" not in sys.argv:
     print("jacobi-bicgstab : solve %.1f ms, %d iterations" % (fs.timings["solve_ms"], jac.info["iterations"]), flush=True)
 bc0 = K.BoundaryCondition(); bc0.SetDirichletCriteria(lambda: flags)
 torch.cuda.synchronize(); t0 = time.perf_counter()
-mg = GridMultigrid(mesh, form, material, bc0, nu=NU)
+mg = GridMultigrid(mesh, form, material, bc0, nu=NU, omega=OMEGA)
 torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
 mgs = K.LinearSolver(tol=1e-10, preconditioner=mg)
 run(mgs); got = run(mgs)
@@ -58,7 +61,7 @@ Kc = K.Assemble(fs, form.function_spaces, form, mesh, material, bc1)[0]
 bc1.GetDirichletBoundaryConditions(form, mesh, material, fs)
 F = torch.zeros((mesh.nnodes, 1), dtype=torch.float64, device="cuda")
 Kb, Fb = bc1.ApplyDirichletGetReducedMatrices(Kc, F, bc1.applied_dirichlet_device)[:2]
-mg1 = GridMultigrid(mesh, form, material, bc1, nu=NU)
+mg1 = GridMultigrid(mesh, form, material, bc1, nu=NU, omega=OMEGA)
 mg1.setup(Kb)
 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 e[0].record(); mg1.setup(Kb); e[1].record()

@@ -88,6 +88,22 @@ def test_pattern_nvar2_golden():
     assert np.array_equal(dl, c["data_local"]) and np.array_equal(dg, c["data_global"])
 
 
+@pytest.mark.parametrize("bad_id", [-1, 9, 1 << 20])
+def test_pattern_rejects_out_of_range_connectivity(bad_id):
+    """A node id outside [0, nnode) in a user-provided mesh returns KB_EINVAL instead of overflowing the sort key and
+    writing indptr out of bounds."""
+    from kiltro_b200 import _lib
+    el = PAT.case("rect2x2")["elements"].copy()
+    el[1, 2] = bad_id
+    m = make_mesh(np.zeros((9, 2)), el)
+    with pytest.raises(_lib.KiltroB200Error):
+        _K().ComputeSparsityPattern(m, 1)
+    # the library is still usable afterwards, and the scratch of the failed call was released (no error on the next one)
+    m2 = make_mesh(np.zeros((9, 2)), PAT.case("rect2x2")["elements"])
+    ind, ptr, _, _ = _K().ComputeSparsityPattern(m2, 1)
+    assert np.array_equal(ptr, PAT.case("rect2x2")["indptr"])
+
+
 @pytest.mark.parametrize("nx,ny,scramble", [(40, 31, False), (64, 64, True), (257, 129, False)])
 def test_pattern_vs_oracle_c(nx, ny, scramble):
     from oracle import kiltro_oracle as O, native as ON
@@ -103,6 +119,40 @@ def test_pattern_vs_oracle_c(nx, ny, scramble):
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
     assert got[0].shape[0] == (3 * (nx + 1) - 2) * (3 * (ny + 1) - 2)
+
+
+@pytest.mark.parametrize("n,petrov,transient", [(2, False, False), (3, True, True), (257, True, False), (10001, False, True),
+                                                (100000, True, True)])
+def test_line_grid_assembly_matches_tile_kernels(n, petrov, transient):
+    """csrc/assemble_line.cu (the grid form of Mesh.Line-numbered meshes: what assembly='auto' picks) equals the tile kernel
+    and the two-pass seam to rounding (K, M and the source vector), and a scrambled numbering falls back to the tile kernel."""
+    K = _K()
+    m = K.Mesh(element_type="line"); m.Line(0.0, 2.0, n - 1)
+    g = torch.Generator(device="cuda"); g.manual_seed(n)
+    vel = 3.0 + torch.rand((m.nnodes, 1), dtype=torch.float64, device="cuda", generator=g)
+    form = (K.TemperaturePG if petrov else K.Temperature)(m, velocity=vel)
+    mat = K.FourierConduction(1, k=0.7, area=1.3, density=1.1, heat_capacity_v=0.9, q=2.0)
+    bc = K.BoundaryCondition()
+    out = {}
+    for method in ("auto", "fused_generic", "two_pass"):
+        fs = K.FEMSolver(analysis_type="transient" if transient else "steady", assembly=method, verbose=False)
+        Kc, F, M = K.Assemble(fs, form.function_spaces, form, m, mat, bc)
+        out[method] = (Kc.data.clone(), F.clone(), M.data.clone() if transient else None, fs.assembly_used)
+    assert out["auto"][3] == "fused_line" and out["fused_generic"][3] == "fused"
+    def close(a, b):                                 # rounding level: same sums in the same order, but the element routine is
+        scale = float(b.abs().max())                 # inlined into different kernels and nvcc contracts its products into FMAs
+        return float((a - b).abs().max()) <= 4e-15 * (scale if scale > 0 else 1.0)   # differently (K itself is <= 1e-12 of the
+    assert torch.equal(out["fused_generic"][0], out["two_pass"][0])                  # reference: test_element_matrices_and_assembly_golden)
+    for other in ("fused_generic", "two_pass"):
+        assert close(out["auto"][0], out[other][0]) and close(out["auto"][1], out[other][1])
+        if transient:
+            assert close(out["auto"][2], out[other][2])
+    if n >= 3:
+        pts = K.to_numpy(m.device_points()); el = K.to_numpy(m.device_elements()).astype(np.int64)
+        m2 = K.Mesh(element_type="line"); m2.set_arrays(pts, el[::-1].copy())            # same nodes, elements reversed
+        fs = K.FEMSolver(verbose=False)
+        K.Assemble(fs, form.function_spaces, (K.TemperaturePG if petrov else K.Temperature)(m2, velocity=vel), m2, mat, bc)
+        assert fs.assembly_used != "fused_line"
 
 
 def test_pattern_line_vs_oracle():
