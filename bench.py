@@ -920,7 +920,25 @@ def main():
             mg_e2e = {"value": nn * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps, "ms_per_step": wall * 1e3 / args.e2e_steps,
                       "status": sv.info["status"], "iterations": sv.info["iterations"]}
+        # algorithmic bytes of one V-cycle (fp32 levels): per node of a level the down-leg moves the 8 stencil
+        # coefficients, d, the rhs and writes x and the residual (+ on level 0 the fp64 vector in, the node map, 1/d and the
+        # staged rhs out), the restriction reads the residual, the up-leg moves the coefficients, rhs and x in and x out (on
+        # level 0 the node map and the fp64 result instead)
+        vc_bytes = 0
+        for li, (lx, ly) in enumerate(mg.levels[:-1]):
+            npad = ly * ((lx + 1 + 31) // 32 * 32)
+            down = (32 + 4 + 4 + 4 + 4) * npad + ((8 + 4 + 4 + 4) * npad if li == 0 else 0)
+            up = (32 + 4 + 4) * npad + ((4 + 8) * npad if li == 0 else 4 * npad)
+            vc_bytes += down + 4 * npad + up
+        vc_ms = s2.elapsed_time(s3) / 10
+        mg_roof = {"bound": "hbm", "kernel": "one V-cycle (k_mg_leg down / up legs + k_mg_restrict per level, nu = %d)" % mg.nu,
+                   "achieved": vc_bytes / (vc_ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
+                   "frac": vc_bytes / (vc_ms * 1e-3) * 1e-9 / peak, "algorithmic_bytes_per_cycle": int(vc_bytes),
+                   "ms_per_cycle": vc_ms, "peak_source": peak_src,
+                   "note": "whole cycle (10 levels, 19 + 9 kernels), CUDA events over 10 back-to-back cycles; the levels below "
+                           "251^2 nodes are latency-bound chains of small kernels"}
         mgleg = {"value": nn * args.steps / (mg_ms * 1e-3), "unit": UNIT, "ms_per_step": mg_ms / args.steps,
+                 "roofline": mg_roof, "nu": mg.nu, "omega": mg.omega,
                  "steps": args.steps, "method": minfo["method"], "iterations": minfo["iterations"], "levels": minfo["levels"],
                  "level_shapes": mg.levels, "status": minfo["status"], "relative_residual": minfo["relative_residual"],
                  "rtol": args.rtol, "phases_ms_per_step": {k: v / args.steps for k, v in mg_phase.items()},
