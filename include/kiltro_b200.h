@@ -464,6 +464,8 @@ int kb_mg_set_smoother(kb_mg *mg, int nu, const double *h_omega);
 /* development switches: fused legs of the cycle (one kernel per leg and level instead of one per sweep; bit-identical
  * results) on / off, and the node rows per warp task of the fused kernels */
 void kb_mg_set_fused(int on);
+void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0) */
+void kb_mg_set_overweight(double eta);        /* residual over-weighting factor of the restriction (default 1) */
 void kb_mg_set_rows_per_task(int rows);
 void kb_mg_set_prefetch_rows(int rows);   /* L2 prefetch distance of the fused kernels (0 = off) */
 void kb_mg_set_prefetch_rows_l1(int rows);   /* L1 prefetch distance (0, 1 or 2 rows) */

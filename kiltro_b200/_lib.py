@@ -160,6 +160,8 @@ SIGNATURES = {
     "kb_mg_apply": (I32, [c_vp, c_vp, c_vp, c_vp]),
     "kb_mg_set_smoother": (I32, [c_vp, I32, ctypes.POINTER(F64)]),
     "kb_mg_set_fused": (None, [I32]),
+    "kb_mg_set_upwind_restriction": (None, [I32]),
+    "kb_mg_set_overweight": (None, [F64]),
     "kb_mg_set_rows_per_task": (None, [I32]),
     "kb_mg_set_prefetch_rows": (None, [I32]),
     "kb_mg_set_prefetch_rows_l1": (None, [I32]),

@@ -46,6 +46,7 @@ struct MgLevel {
     int64_t np = 0;                       // ny * pitch (padded nodes, without the guard rows)
     float *cf = nullptr;                  // 8 coefficients per padded node
     float *d = nullptr, *dinv = nullptr;  // diagonal (0: not an unknown) and its reciprocal (0 there too)
+    float *cbx = nullptr, *cby = nullptr; // levels >= 1: Petrov-Galerkin weight coefficients of the node (upwind-biased restriction)
     float *bh = nullptr, *xa = nullptr, *xb = nullptr, *r = nullptr;    // fp32 vectors
     double *pts = nullptr, *vel = nullptr;                              // levels >= 1
     uint8_t *fixed = nullptr;             // compact (nx * ny)
@@ -108,9 +109,9 @@ size_t carve(kb_mg *mg, char *base, bool assign) {
         MgLevel &L = mg->L[l];
         const size_t nn = (size_t)L.nx * L.ny;
         { float *p = (float *)take(sizeof(float) * padded_elems(L, 8)) + padded_origin(L, 8); if (assign) L.cf = p; }
-        float *v[6];
-        for (int k = 0; k < 6; ++k) v[k] = (float *)take(sizeof(float) * padded_elems(L, 1)) + padded_origin(L, 1);
-        if (assign) { L.d = v[0]; L.dinv = v[1]; L.bh = v[2]; L.xa = v[3]; L.xb = v[4]; L.r = v[5]; }
+        float *v[8];
+        for (int k = 0; k < 8; ++k) v[k] = (float *)take(sizeof(float) * padded_elems(L, 1)) + padded_origin(L, 1);
+        if (assign) { L.d = v[0]; L.dinv = v[1]; L.bh = v[2]; L.xa = v[3]; L.xb = v[4]; L.r = v[5]; L.cbx = v[6]; L.cby = v[7]; }
         { uint8_t *p = (uint8_t *)take(nn); if (assign) L.fixed = p; }
         if (l > 0) {
             double *p = (double *)take(sizeof(double) * 2 * nn), *q = (double *)take(sizeof(double) * 2 * nn);
@@ -274,6 +275,26 @@ __global__ void __launch_bounds__(128) k_mg_assemble_dia(int nx, int ny, int pit
     }
 }
 
+// Petrov-Galerkin weight coefficients of a coarse node, cb = (alpha / |u|) u with the reference's alpha(Pe)
+// (kiltro/VariationalPrinciple.py:311-330; Pe from the node's velocity and the x-spacing of the level, like the element
+// routine's h = |X1 - X0|): the coarse operators are assembled with the test functions W = N + cb . grad_parent N, and the
+// restriction tests the fine residual with the same W (k_mg_restrict).
+__global__ void __launch_bounds__(256) k_mg_pg_weights(int nx, int ny, int pitch, const double *__restrict__ pts,
+                                                       const double *__restrict__ vel, double kcond,
+                                                       float *__restrict__ cbx, float *__restrict__ cby) {
+    const int64_t nn = (int64_t)nx * ny, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += stride) {
+        const int i = (int)(p % nx), j = (int)(p / nx);
+        const int64_t q = i + 1 < nx ? p + 1 : p - 1;
+        const double dx = pts[2 * q] - pts[2 * p], dy = pts[2 * q + 1] - pts[2 * p + 1];
+        const double ux = vel[2 * p], uy = vel[2 * p + 1];
+        const double coef = pg_coefficient(sqrt(ux * ux + uy * uy), sqrt(dx * dx + dy * dy), kcond);
+        const int64_t pp = (int64_t)j * pitch + i;
+        cbx[pp] = (float)(coef * ux);
+        cby[pp] = (float)(coef * uy);
+    }
+}
+
 // coarsest level: dense [Ahat | I] (fp64, n x 2n) from the stencil; rows of non-unknowns are identity rows
 __global__ void __launch_bounds__(256) k_mg_dense_build(int nx, int ny, int pitch, const float *__restrict__ cf,
                                                         const float *__restrict__ d, double *__restrict__ W) {
@@ -420,27 +441,40 @@ __global__ void __launch_bounds__(256) k_mg_sweep(int64_t np, int pitch, const f
 // gathers the fine nodes of [start[c-1], start[c+1]) in both directions (<= RMAX per direction with the x weights in
 // registers; wider supports -- only when a direction is not coarsened -- fall back to the table walk).
 constexpr int RMAX = 6;
+// UPWIND: the fine residual is tested with the coarse level's Petrov-Galerkin functions W_c = N_c + cb . grad_parent N_c
+// instead of the hat functions N_c alone (cbx / cby: k_mg_pg_weights; grad_parent N_c = +-1/2 x the hat function of the other
+// direction inside the two elements left / right of the node, 0 on the node's own grid line): the coarse operators are
+// assembled with these test functions, and a restriction that ignores them leaves the coarse problems with the wrong
+// right-hand side for exactly the smooth streamline modes the coarse levels are there for (Richardson factor per cycle on
+// the bench problem: 0.45 without).
 __global__ void __launch_bounds__(128) k_mg_restrict(int nxc, int nyc, int pitch_c, int pitch_f, const float *__restrict__ dinvc,
+                                                     const float *__restrict__ cbx, const float *__restrict__ cby,
                                                      const float *__restrict__ rf, const int *__restrict__ jx,
                                                      const float *__restrict__ wx, const int *__restrict__ sx,
                                                      const int *__restrict__ jy, const float *__restrict__ wy,
                                                      const int *__restrict__ sy, float *__restrict__ bhc,
-                                                     float *__restrict__ xac, float omega, const int *__restrict__ done) {
+                                                     float *__restrict__ xac, float omega, float overweight,
+                                                     const int *__restrict__ done) {
     kb_pdl_wait();
     if (done != nullptr && *done != 0) return;
     const int ic = blockIdx.x * blockDim.x + threadIdx.x;
     if (ic >= pitch_c) return;
     int i0 = 0, cnt = 0;
-    float wxr[RMAX];
+    float wxr[RMAX], sxr[RMAX];
 #pragma unroll
-    for (int u = 0; u < RMAX; ++u) wxr[u] = 0.f;
+    for (int u = 0; u < RMAX; ++u) { wxr[u] = 0.f; sxr[u] = 0.f; }
     if (ic < nxc) {
         i0 = sx[ic > 0 ? ic - 1 : 0];
         cnt = sx[ic + 1 < nxc ? ic + 1 : nxc] - i0;
         if (cnt <= RMAX) {
 #pragma unroll
             for (int u = 0; u < RMAX; ++u)
-                if (u < cnt) wxr[u] = (jx[i0 + u] == ic) ? 1.f - wx[i0 + u] : wx[i0 + u];
+                if (u < cnt) {
+                    const bool right = jx[i0 + u] == ic;
+                    const float w = wx[i0 + u];
+                    wxr[u] = right ? 1.f - w : w;
+                    sxr[u] = right ? (w > 0.f ? -1.f : 0.f) : (w < 1.f ? 1.f : 0.f);
+                }
         }
     }
     for (int jc = blockIdx.y; jc < nyc; jc += gridDim.y) {
@@ -448,22 +482,32 @@ __global__ void __launch_bounds__(128) k_mg_restrict(int nxc, int nyc, int pitch
         float b = 0.f;
         const float dv = ic < nxc ? dinvc[ppc] : 0.f;
         if (dv != 0.f) {
+            const float hx = cbx != nullptr ? 0.5f * cbx[ppc] : 0.f, hy = cby != nullptr ? 0.5f * cby[ppc] : 0.f;
             const int j0 = sy[jc > 0 ? jc - 1 : 0], j1 = sy[jc + 1 < nyc ? jc + 1 : nyc];
             float acc = 0.f;
             for (int jf = j0; jf < j1; ++jf) {
-                const float wyv = (jy[jf] == jc) ? 1.f - wy[jf] : wy[jf];
+                const bool up = jy[jf] == jc;
+                const float wyf = wy[jf];
+                const float wyv = up ? 1.f - wyf : wyf;
+                const float syv = up ? (wyf > 0.f ? -1.f : 0.f) : (wyf < 1.f ? 1.f : 0.f);
                 const float *row = rf + (int64_t)jf * pitch_f + i0;
-                float racc = 0.f;
+                float racc = 0.f, rdx = 0.f;
                 if (cnt <= RMAX) {
 #pragma unroll
                     for (int u = 0; u < RMAX; ++u)
-                        if (u < cnt) racc = fmaf(wxr[u], row[u], racc);
+                        if (u < cnt) { const float rv = row[u]; racc = fmaf(wxr[u], rv, racc); rdx = fmaf(sxr[u], rv, rdx); }
                 } else {
-                    for (int u = 0; u < cnt; ++u) racc = fmaf((jx[i0 + u] == ic) ? 1.f - wx[i0 + u] : wx[i0 + u], row[u], racc);
+                    for (int u = 0; u < cnt; ++u) {
+                        const bool right = jx[i0 + u] == ic;
+                        const float w = wx[i0 + u], rv = row[u];
+                        racc = fmaf(right ? 1.f - w : w, rv, racc);
+                        rdx = fmaf(right ? (w > 0.f ? -1.f : 0.f) : (w < 1.f ? 1.f : 0.f), rv, rdx);
+                    }
                 }
-                acc = fmaf(wyv, racc, acc);
+                acc = fmaf(wyv, fmaf(hx, rdx, racc), acc);
+                acc = fmaf(hy * syv, racc, acc);
             }
-            b = acc * dv;
+            b = (overweight * acc) * dv;
         }
         bhc[ppc] = b;
         xac[ppc] = omega * b;
@@ -738,13 +782,17 @@ int launch_sweep(const MgLevel &L, const float *xi, float *out, float omega, con
     return 0;
 }
 
+int g_mg_upwind = 0;          // 1: restriction with the coarse Petrov-Galerkin test functions (kb_mg_set_upwind_restriction)
+float g_mg_overweight = 1.f;  // residual over-weighting of the restriction (kb_mg_set_overweight)
+
 int launch_restrict(const MgLevel &L, const MgLevel &Cn, float omega, const int *done, cudaStream_t s, bool pdl) {
     // one coarse node per thread (no row loop: the gather is a chain of dependent table and residual loads)
     const dim3 grid((unsigned)kb_cdiv(Cn.pitch, 128), (unsigned)(Cn.ny < 65535 ? Cn.ny : 65535));
     KB_CUDA(kb_launch_pdl(k_mg_restrict, grid, dim3(128), 0, s, pdl, Cn.nx, Cn.ny, Cn.pitch,
-                          L.pitch, (const float *)Cn.dinv, (const float *)L.r, (const int *)L.jx, (const float *)L.wx,
+                          L.pitch, (const float *)Cn.dinv, (const float *)(g_mg_upwind ? Cn.cbx : nullptr),
+                          (const float *)(g_mg_upwind ? Cn.cby : nullptr), (const float *)L.r, (const int *)L.jx, (const float *)L.wx,
                           (const int *)L.sx, (const int *)L.jy, (const float *)L.wy, (const int *)L.sy, Cn.bh, Cn.xa,
-                          omega, done));
+                          omega, g_mg_overweight, done));
     KB_LAUNCH_CHECK();
     return 0;
 }
@@ -958,6 +1006,8 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         KB_CUDA(cudaMemsetAsync(L.cf - padded_origin(L, 8), 0, sizeof(float) * padded_elems(L, 8), s));
         KB_CUDA(cudaMemsetAsync(L.d - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
         KB_CUDA(cudaMemsetAsync(L.dinv - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+        KB_CUDA(cudaMemsetAsync(L.cbx - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+        KB_CUDA(cudaMemsetAsync(L.cby - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
         if (first) {
             float *v[4] = {L.bh, L.xa, L.xb, L.r};
             for (int k = 0; k < 4; ++k) KB_CUDA(cudaMemsetAsync(v[k] - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
@@ -988,6 +1038,10 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         const double *pf = l == 1 ? d_points : F.pts, *vf = d_velocity == nullptr ? nullptr : (l == 1 ? d_velocity : F.vel);
         k_mg_sample<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, F.nx, F.ny, pf, vf, F.fixed, L.pts, L.vel, L.fixed);
         KB_LAUNCH_CHECK();
+        if (d_velocity != nullptr) {
+            k_mg_pg_weights<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, o.k, L.cbx, L.cby);
+            KB_LAUNCH_CHECK();
+        }
         if (d_velocity != nullptr)
             k_mg_assemble_dia<true><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
         else
@@ -1028,6 +1082,8 @@ extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stre
 /* development switches: fused legs on / off (results are bit-identical), node rows per warp task of the fused legs
  * (0 = chosen per level), their L2 prefetch distance */
 extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
+extern "C" void kb_mg_set_upwind_restriction(int on) { g_mg_upwind = on; }
+extern "C" void kb_mg_set_overweight(double eta) { if (eta > 0.0 && eta < 4.0) g_mg_overweight = (float)eta; }
 extern "C" void kb_mg_set_rows_per_task(int rows) { if (rows >= 0) g_mg_rows_per_task = rows; }
 extern "C" void kb_mg_set_prefetch_rows(int rows) { if (rows >= 0) g_mg_pfd = rows; }
 extern "C" void kb_mg_set_prefetch_rows_l1(int rows) { if (rows >= 0 && rows <= 2) g_mg_pf1 = rows; }

@@ -12,6 +12,12 @@ from kiltro_b200.multigrid import GridMultigrid
 import bench
 
 warnings.simplefilter("ignore")
+import os as _os
+from kiltro_b200 import _lib as _LL
+if "MG_OVERWEIGHT" in _os.environ:
+    _LL.load().kb_mg_set_overweight(float(_os.environ["MG_OVERWEIGHT"]))
+if "MG_UPWIND" in _os.environ:
+    _LL.load().kb_mg_set_upwind_restriction(int(_os.environ["MG_UPWIND"]))
 import os
 from kiltro_b200 import _lib as _L
 if "MG_FUSED" in os.environ:
