@@ -467,6 +467,7 @@ void kb_mg_set_fused(int on);
 void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0) */
 void kb_mg_set_overweight(double eta);        /* residual over-weighting factor of the restriction (default 1) */
 void kb_mg_set_rows_per_task(int rows);
+void kb_mg_set_min_rows(int rows);        /* shortest task (rows) the per-level choice may pick */
 void kb_mg_set_prefetch_rows(int rows);   /* L2 prefetch distance of the fused kernels (0 = off) */
 void kb_mg_set_prefetch_rows_l1(int rows);   /* L1 prefetch distance (0, 1 or 2 rows) */
 /* x: initial guess in, solution out; verdict, restarts and kb_solve_info as kb_bicgstab_solve (TRUE residual of the

@@ -163,6 +163,7 @@ SIGNATURES = {
     "kb_mg_set_upwind_restriction": (None, [I32]),
     "kb_mg_set_overweight": (None, [F64]),
     "kb_mg_set_rows_per_task": (None, [I32]),
+    "kb_mg_set_min_rows": (None, [I32]),
     "kb_mg_set_prefetch_rows": (None, [I32]),
     "kb_mg_set_prefetch_rows_l1": (None, [I32]),
     "kb_mg_bicgstab_workspace_bytes": (ctypes.c_size_t, [I64, I64]),

@@ -801,15 +801,18 @@ int g_mg_fused = 1;           // 1: fused legs (k_mg_leg) where nu <= 3 ; 0: one
 int g_mg_rows_per_task = 0;   // node rows per warp task of the fused legs; 0 = chosen per level (kb_mg_set_rows_per_task)
 int g_mg_pfd = 6;             // L2 prefetch distance of the fused legs, in rows (kb_mg_set_prefetch_rows)
 int g_mg_pf1 = 2;             // L1 prefetch distance (kb_mg_set_prefetch_rows_l1)
+int g_mg_min_rows = 2;        // shortest task of the fused legs (kb_mg_set_min_rows)
 
 template <int NS, bool DOWN, bool L0>
 int launch_leg(LegArgs a, cudaStream_t s, bool pdl) {
     constexpr int VW = 32 - 2 * NS;
     a.nstrips = (int)kb_cdiv(a.nx, VW);
     if (g_mg_rows_per_task > 0) a.rows_per_task = g_mg_rows_per_task;
-    else {      // enough warps to fill the machine a few times over, tasks no longer than 64 rows, no shorter than 8
+    else {      // enough warps to fill the machine a few times over, tasks no longer than 64 rows.  On the small levels a
+                // leg is a chain of rows + 2 NS dependent steps (~0.6 us each) and nothing else: keep it short there
+                // (the recomputed halo rows cost nothing on a level that does not fill the machine)
         int64_t r = (int64_t)a.nstrips * a.ny / ((int64_t)kb_num_sms() * 48);
-        a.rows_per_task = (int)(r < 8 ? 8 : (r > 64 ? 64 : r));
+        a.rows_per_task = (int)(r < g_mg_min_rows ? g_mg_min_rows : (r > 64 ? 64 : r));
     }
     a.pfd = g_mg_pfd;
     a.pf1 = g_mg_pf1;
@@ -1085,6 +1088,7 @@ extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
 extern "C" void kb_mg_set_upwind_restriction(int on) { g_mg_upwind = on; }
 extern "C" void kb_mg_set_overweight(double eta) { if (eta > 0.0 && eta < 4.0) g_mg_overweight = (float)eta; }
 extern "C" void kb_mg_set_rows_per_task(int rows) { if (rows >= 0) g_mg_rows_per_task = rows; }
+extern "C" void kb_mg_set_min_rows(int rows) { if (rows >= 1) g_mg_min_rows = rows; }
 extern "C" void kb_mg_set_prefetch_rows(int rows) { if (rows >= 0) g_mg_pfd = rows; }
 extern "C" void kb_mg_set_prefetch_rows_l1(int rows) { if (rows >= 0 && rows <= 2) g_mg_pf1 = rows; }
 

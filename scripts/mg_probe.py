@@ -26,6 +26,8 @@ if "MG_ROWS" in os.environ:
     _L.load().kb_mg_set_rows_per_task(int(os.environ["MG_ROWS"]))
 if "MG_PFD" in os.environ:
     _L.load().kb_mg_set_prefetch_rows(int(os.environ["MG_PFD"]))
+if "MG_MINROWS" in os.environ:
+    _L.load().kb_mg_set_min_rows(int(os.environ["MG_MINROWS"]))
 if "MG_PF1" in os.environ:
     _L.load().kb_mg_set_prefetch_rows_l1(int(os.environ["MG_PF1"]))
 NU = int(os.environ.get("MG_NU", "3"))

@@ -7,8 +7,9 @@ import subprocess
 import sys
 
 tag = sys.argv[1]
+prefix = sys.argv[2] if len(sys.argv) > 2 else ""          # "mg_": the launch list of scripts/mg_ncu.sh
 out = []
-with open("gpurun_out/launches_%s.csv" % tag) as f:
+with open("gpurun_out/%slaunches_%s.csv" % (prefix, tag)) as f:
     lines = [l for l in f if not l.startswith("==")]
 agg = collections.OrderedDict()
 for row in csv.DictReader(lines):
@@ -21,12 +22,13 @@ for row in csv.DictReader(lines):
     k = re.sub(r"\(.*", "", row["Kernel Name"])[:100]
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(v[1] for v in agg.values())
-out.append("# command: see scripts/ncu_round.sh (bench.py --profiler-range under ncu --profile-from-start off: the launches of ONE timed step)")
+out.append("# command: see scripts/ncu_round.sh (bench.py --profiler-range under ncu --profile-from-start off: the launches of ONE timed step)"
+           if not prefix else "# command: see scripts/mg_ncu.sh (python scripts/mg_probe.py 4000 nojac under ncu: two S16 solves through FEMSolver.Solve with the multigrid solver, set-up + 11 extra V-cycles)")
 out.append("# ncu --metrics gpu__time_duration.sum --clock-control none  (tag %s); per-launch times are cold-cache and serialised: compare SHARES" % tag)
 out.append("# launches  total_ms  avg_us  share  kernel")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("%7d  %10.3f  %9.1f  %5.1f%%  %s" % (v[0], v[1] / 1e6, v[1] / v[0] / 1e3, 100 * v[1] / tot, k))
-open("profiles/%s_launches.txt" % tag, "w").write("\n".join(out) + "\n")
+open("profiles/%s_%slaunches.txt" % (tag, prefix), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:14]))
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
