@@ -461,9 +461,13 @@ int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_velocity, con
 int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stream);
 /* per-sweep damping factors h_omega[0..nu) (nu <= 4) instead of one omega; pass omega <= 0 to kb_mg_setup to keep them */
 int kb_mg_set_smoother(kb_mg *mg, int nu, const double *h_omega);
+/* cycle schedule: h_reps[l] (1..8) = coarse-grid corrections per visit of level l -- the coarser levels are cycled that many
+ * times, each from the corrected iterate; levels >= n keep 1 (all 1 = V-cycle) */
+int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps);
 /* development switches: fused legs of the cycle (one kernel per leg and level instead of one per sweep; bit-identical
  * results) on / off, and the node rows per warp task of the fused kernels */
 void kb_mg_set_fused(int on);
+void kb_mg_set_aggressive(int nodes);      /* plans made afterwards coarsen levels with <= nodes per direction by 4 (default 0: off) */
 void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0) */
 void kb_mg_set_overweight(double eta);        /* residual over-weighting factor of the restriction (default 1) */
 void kb_mg_set_rows_per_task(int rows);

@@ -159,7 +159,9 @@ SIGNATURES = {
                           c_vp, ctypes.c_size_t, c_vp]),
     "kb_mg_apply": (I32, [c_vp, c_vp, c_vp, c_vp]),
     "kb_mg_set_smoother": (I32, [c_vp, I32, ctypes.POINTER(F64)]),
+    "kb_mg_set_cycle": (I32, [c_vp, I32, ctypes.POINTER(ctypes.c_int32)]),
     "kb_mg_set_fused": (None, [I32]),
+    "kb_mg_set_aggressive": (None, [I32]),
     "kb_mg_set_upwind_restriction": (None, [I32]),
     "kb_mg_set_overweight": (None, [F64]),
     "kb_mg_set_rows_per_task": (None, [I32]),

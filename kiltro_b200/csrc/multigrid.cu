@@ -65,6 +65,7 @@ struct kb_mg {
     int nu = 2;
     float omega[4] = {0.67f, 0.67f, 0.67f, 0.67f};   // damping of sweep 1..nu (pre- and post-smoothing alike)
     int64_t nfree = 0;
+    int reps[MG_MAXLEV];            // coarse-grid corrections per visit of level l (1 everywhere: V-cycle); kb_mg_set_cycle
     int *free2pp = nullptr, *free2node = nullptr;
     int *n2f = nullptr;             // level 0, padded like the vectors: unknown of a node, -1 elsewhere
     int ncoarse = 0;
@@ -797,6 +798,7 @@ int launch_restrict(const MgLevel &L, const MgLevel &Cn, float omega, const int 
     return 0;
 }
 
+int g_mg_aggressive = 0;      // levels with <= this many nodes per direction are coarsened by 4 instead of 2 (kb_mg_set_aggressive)
 int g_mg_fused = 1;           // 1: fused legs (k_mg_leg) where nu <= 3 ; 0: one kernel per sweep (kb_mg_set_fused)
 int g_mg_rows_per_task = 0;   // node rows per warp task of the fused legs; 0 = chosen per level (kb_mg_set_rows_per_task)
 int g_mg_pfd = 6;             // L2 prefetch distance of the fused legs, in rows (kb_mg_set_prefetch_rows)
@@ -839,38 +841,96 @@ LegArgs leg_args(const kb_mg *mg, const MgLevel &L, const int *done) {
     return a;
 }
 
-int apply_fused(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const double *d_alpha, const double *d_q,
-                const int *done, cudaStream_t s, bool pdl) {
+int launch_prolong(const MgLevel &L, const MgLevel &Cn, const float *xc, float *xf, const int *done, cudaStream_t s, bool pdl) {
+    KB_CUDA(kb_launch_pdl(k_mg_prolong, grid2d(L.nx, 128, L.ny), dim3(128), 0, s, pdl, L.nx, L.ny, L.pitch, Cn.pitch, xc,
+                          (const int *)L.jx, (const float *)L.wx, (const int *)L.jy, (const float *)L.wy, xf, done));
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
+// The cycle with fused legs, recursive: down-leg (pre-smoothing + residual) -> restriction -> cycle on the coarser levels
+// -> up-leg (prolongation + post-smoothing).  mg->reps[l] > 1 repeats the coarse-grid correction of level l from the
+// corrected iterate (prolongation and residual by the one-kernel-per-node forms, no smoothing in between) before the
+// up-leg: the coarser levels are cycled reps[l] times per visit of level l.
+struct FusedCtx {
+    kb_mg *mg; const double *d_v; double *d_s, *d_z; const double *d_alpha, *d_q; const int *done; cudaStream_t s; bool pdl;
+};
+int cycle_fused(FusedCtx &c, int l) {
+    kb_mg *mg = c.mg;
     const int nl = mg->nlev, ns = mg->nu;
+    const MgLevel &L = mg->L[l];
     int rc;
-    for (int l = 0; l + 1 < nl; ++l) {                       // down: x -> xa, residual -> r, restricted rhs -> bh of l+1
-        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
-        LegArgs a = leg_args(mg, L, done);
+    if (l == nl - 1) {
+        KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, c.s, c.pdl, mg->ncoarse, L.nx, L.pitch,
+                              (const float *)mg->ainv, (const float *)L.bh, L.xb, c.done));
+        KB_LAUNCH_CHECK();
+        return 0;
+    }
+    const MgLevel &Cn = mg->L[l + 1];
+    {                                                        // down: x -> xa, residual -> r
+        LegArgs a = leg_args(mg, L, c.done);
         a.x_out = L.xa; a.r_out = L.r;
         if (l == 0) {
-            a.bh_out = L.bh; a.v = d_v; a.s_out = d_s; a.alpha = d_alpha; a.q = d_q; a.n2f = mg->n2f;
-            rc = launch_leg_ns<true, true>(ns, a, s, pdl);
+            a.bh_out = L.bh; a.v = c.d_v; a.s_out = c.d_s; a.alpha = c.d_alpha; a.q = c.d_q; a.n2f = mg->n2f;
+            rc = launch_leg_ns<true, true>(ns, a, c.s, c.pdl);
         } else {
             a.bh_in = L.bh;
-            rc = launch_leg_ns<true, false>(ns, a, s, pdl);
+            rc = launch_leg_ns<true, false>(ns, a, c.s, c.pdl);
         }
         if (rc) return rc;
-        if ((rc = launch_restrict(L, Cn, mg->omega[0], done, s, pdl))) return rc;
     }
-    {
-        const MgLevel &L = mg->L[nl - 1];
-        KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, s, pdl, mg->ncoarse, L.nx, L.pitch,
-                              (const float *)mg->ainv, (const float *)L.bh, L.xb, done));
-        KB_LAUNCH_CHECK();
+    for (int rep = 0;; ++rep) {
+        if ((rc = launch_restrict(L, Cn, mg->omega[0], c.done, c.s, c.pdl))) return rc;      // rhs (and omega rhs) of l+1
+        if ((rc = cycle_fused(c, l + 1))) return rc;                                         // -> Cn.xb
+        if (rep + 1 >= mg->reps[l]) break;
+        if ((rc = launch_prolong(L, Cn, Cn.xb, L.xa, c.done, c.s, c.pdl))) return rc;
+        if ((rc = launch_sweep<1>(L, L.xa, L.r, 0.f, c.done, c.s, c.pdl))) return rc;
     }
-    for (int l = nl - 2; l >= 0; --l) {                      // up: xa (+ P xb of l+1) -> xb ; level 0 -> z
-        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
-        LegArgs a = leg_args(mg, L, done);
+    {                                                        // up: xa + P xb(l+1) -> xb ; level 0 -> z
+        LegArgs a = leg_args(mg, L, c.done);
         a.bh_in = L.bh; a.x_in = L.xa; a.xc = Cn.xb; a.pitch_c = Cn.pitch; a.jx = L.jx; a.jy = L.jy; a.wx = L.wx; a.wy = L.wy;
         a.x_out = L.xb;
-        if (l == 0) { a.z = d_z; a.n2f = mg->n2f; rc = launch_leg_ns<false, true>(ns, a, s, pdl); }
-        else rc = launch_leg_ns<false, false>(ns, a, s, pdl);
+        if (l == 0) { a.z = c.d_z; a.n2f = mg->n2f; rc = launch_leg_ns<false, true>(ns, a, c.s, c.pdl); }
+        else rc = launch_leg_ns<false, false>(ns, a, c.s, c.pdl);
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// One-kernel-per-sweep form of the cycle, recursive: the same arithmetic as cycle_fused, one kernel per sweep (fallback for
+// nu > 3 and the cross-check).  On entry L.bh holds the level's (unit-diagonal) right-hand side and c.cur[l] = omega_1 bh
+// (the first sweep from zero).
+struct CycleCtx {
+    kb_mg *mg; const int *done; cudaStream_t s; bool pdl;
+    float *cur[MG_MAXLEV], *oth[MG_MAXLEV];
+};
+int cycle_unfused(CycleCtx &c, int l) {
+    kb_mg *mg = c.mg;
+    const int nl = mg->nlev;
+    const float *om = mg->omega;
+    const MgLevel &L = mg->L[l];
+    int rc;
+    if (l == nl - 1) {
+        KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, c.s, c.pdl, mg->ncoarse, L.nx, L.pitch,
+                              (const float *)mg->ainv, (const float *)L.bh, c.cur[l], c.done));
+        KB_LAUNCH_CHECK();
+        return 0;
+    }
+    const MgLevel &Cn = mg->L[l + 1];
+    for (int k = 1; k < mg->nu; ++k) {
+        if ((rc = launch_sweep<0>(L, c.cur[l], c.oth[l], om[k], c.done, c.s, c.pdl))) return rc;
+        float *t = c.cur[l]; c.cur[l] = c.oth[l]; c.oth[l] = t;
+    }
+    for (int rep = 0; rep < mg->reps[l]; ++rep) {
+        if ((rc = launch_sweep<1>(L, c.cur[l], L.r, 0.f, c.done, c.s, c.pdl))) return rc;
+        if ((rc = launch_restrict(L, Cn, om[0], c.done, c.s, c.pdl))) return rc;
+        c.cur[l + 1] = Cn.xa; c.oth[l + 1] = Cn.xb;
+        if ((rc = cycle_unfused(c, l + 1))) return rc;
+        if ((rc = launch_prolong(L, Cn, c.cur[l + 1], c.cur[l], c.done, c.s, c.pdl))) return rc;
+    }
+    for (int k = 0; k < mg->nu; ++k) {
+        if ((rc = launch_sweep<0>(L, c.cur[l], c.oth[l], om[k], c.done, c.s, c.pdl))) return rc;
+        float *t = c.cur[l]; c.cur[l] = c.oth[l]; c.oth[l] = t;
     }
     return 0;
 }
@@ -884,45 +944,21 @@ int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const dou
                const int *done, cudaStream_t s, bool pdl) {
     if (!mg || !mg->ready || !d_v || !d_z || (d_q != nullptr && (!d_s || !d_alpha || d_s == d_v))) return KB_EINVAL;
     const int nl = mg->nlev;
-    if (g_mg_fused && mg->nu <= 3 && nl >= 2) return apply_fused(mg, d_v, d_s, d_z, d_alpha, d_q, done, s, pdl);
-    const float *om = mg->omega;
-    float *cur[MG_MAXLEV], *oth[MG_MAXLEV];
-    for (int l = 0; l < nl; ++l) { cur[l] = mg->L[l].xa; oth[l] = mg->L[l].xb; }
+    if (g_mg_fused && mg->nu <= 3 && nl >= 2) {
+        FusedCtx f = {mg, d_v, d_s, d_z, d_alpha, d_q, done, s, pdl};
+        return cycle_fused(f, 0);
+    }
+    CycleCtx c;
+    c.mg = mg; c.done = done; c.s = s; c.pdl = pdl;
+    const MgLevel &L0 = mg->L[0];
+    KB_CUDA(kb_launch_pdl(k_mg_entry, grid2d(L0.pitch, 256, L0.ny), dim3(256), 0, s, pdl, L0.ny, L0.pitch,
+                          (const int *)mg->n2f, (const float *)L0.dinv, d_v, d_s, d_alpha, d_q, L0.bh, L0.xa, mg->omega[0], done));
+    KB_LAUNCH_CHECK();
+    c.cur[0] = L0.xa; c.oth[0] = L0.xb;
     int rc;
-    {
-        const MgLevel &L = mg->L[0];
-        KB_CUDA(kb_launch_pdl(k_mg_entry, grid2d(L.pitch, 256, L.ny), dim3(256), 0, s, pdl, L.ny, L.pitch,
-                              (const int *)mg->n2f, (const float *)L.dinv, d_v, d_s, d_alpha, d_q, L.bh, L.xa, om[0], done));
-        KB_LAUNCH_CHECK();
-    }
-    for (int l = 0; l + 1 < nl; ++l) {
-        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
-        for (int k = 1; k < mg->nu; ++k) {
-            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om[k], done, s, pdl))) return rc;
-            float *t = cur[l]; cur[l] = oth[l]; oth[l] = t;
-        }
-        if ((rc = launch_sweep<1>(L, cur[l], L.r, 0.f, done, s, pdl))) return rc;
-        if ((rc = launch_restrict(L, Cn, om[0], done, s, pdl))) return rc;
-    }
-    {
-        const MgLevel &L = mg->L[nl - 1];
-        KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, s, pdl, mg->ncoarse, L.nx, L.pitch,
-                              (const float *)mg->ainv, (const float *)L.bh, cur[nl - 1], done));
-        KB_LAUNCH_CHECK();
-    }
-    for (int l = nl - 2; l >= 0; --l) {
-        const MgLevel &L = mg->L[l], &Cn = mg->L[l + 1];
-        KB_CUDA(kb_launch_pdl(k_mg_prolong, grid2d(L.nx, 128, L.ny), dim3(128), 0, s, pdl, L.nx, L.ny, L.pitch, Cn.pitch,
-                              (const float *)cur[l + 1], (const int *)L.jx, (const float *)L.wx, (const int *)L.jy,
-                              (const float *)L.wy, cur[l], done));
-        KB_LAUNCH_CHECK();
-        for (int k = 0; k < mg->nu; ++k) {
-            if ((rc = launch_sweep<0>(L, cur[l], oth[l], om[k], done, s, pdl))) return rc;
-            float *t = cur[l]; cur[l] = oth[l]; oth[l] = t;
-        }
-    }
+    if ((rc = cycle_unfused(c, 0))) return rc;
     KB_CUDA(kb_launch_pdl(k_mg_exit, dim3(kb_grid(mg->nfree, 256, 8)), dim3(256), 0, s, pdl, mg->nfree,
-                          (const int *)mg->free2pp, (const float *)cur[0], d_z, done));
+                          (const int *)mg->free2pp, (const float *)c.cur[0], d_z, done));
     KB_LAUNCH_CHECK();
     return 0;
 }
@@ -942,6 +978,7 @@ extern "C" int kb_mg_create(int64_t nxn, int64_t nyn, int64_t coarsest_nodes, kb
     if (coarsest_nodes > MG_DENSE_MAX) coarsest_nodes = MG_DENSE_MAX;
     kb_mg *mg = new (std::nothrow) kb_mg();
     if (!mg) return KB_EINVAL;
+    for (int l = 0; l < MG_MAXLEV; ++l) mg->reps[l] = 1;
     int nx = (int)nxn, ny = (int)nyn;
     for (;;) {
         MgLevel &L = mg->L[mg->nlev++];
@@ -949,7 +986,9 @@ extern "C" int kb_mg_create(int64_t nxn, int64_t nyn, int64_t coarsest_nodes, kb
         L.pitch = (nx + 1 + 31) / 32 * 32;
         L.np = (int64_t)ny * L.pitch;
         if ((int64_t)nx * ny <= coarsest_nodes || mg->nlev == MG_MAXLEV) break;
-        const int nxc = nx > 3 ? nx / 2 + 1 : nx, nyc = ny > 3 ? ny / 2 + 1 : ny;
+        // below g_mg_aggressive nodes per direction a level is coarsened by 4 (development switch, default off)
+        const int fx = nx <= g_mg_aggressive ? 4 : 2, fy = ny <= g_mg_aggressive ? 4 : 2;
+        const int nxc = nx > 3 ? (nx - 1 + fx - 1) / fx + 1 : nx, nyc = ny > 3 ? (ny - 1 + fy - 1) / fy + 1 : ny;
         if (nxc == nx && nyc == ny) break;
         nx = nxc; ny = nyc;
     }
@@ -1085,6 +1124,13 @@ extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stre
 /* development switches: fused legs on / off (results are bit-identical), node rows per warp task of the fused legs
  * (0 = chosen per level), their L2 prefetch distance */
 extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
+/* cycle schedule: h_reps[l] = coarse-grid corrections per visit of level l (levels beyond n keep 1 = V-cycle) */
+extern "C" int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps) {
+    if (!mg || !h_reps || n < 0 || n > MG_MAXLEV) return KB_EINVAL;
+    for (int l = 0; l < MG_MAXLEV; ++l) mg->reps[l] = (l < n && h_reps[l] >= 1 && h_reps[l] <= 8) ? h_reps[l] : 1;
+    return 0;
+}
+extern "C" void kb_mg_set_aggressive(int nodes) { g_mg_aggressive = nodes; }
 extern "C" void kb_mg_set_upwind_restriction(int on) { g_mg_upwind = on; }
 extern "C" void kb_mg_set_overweight(double eta) { if (eta > 0.0 && eta < 4.0) g_mg_overweight = (float)eta; }
 extern "C" void kb_mg_set_rows_per_task(int rows) { if (rows >= 0) g_mg_rows_per_task = rows; }

@@ -21,8 +21,14 @@ from . import _lib, device as D
 
 
 class GridMultigrid(object):
+    # coarse-grid corrections per visit of level 0, 1, 2: the correction of level 2 (one sixteenth of the fine nodes) is
+    # repeated three times, each from the corrected iterate.  With rediscretised upwind-type coarse operators a V-cycle's
+    # asymptotic factor is ~0.5; this schedule costs 1.3x a V-cycle and halves the iteration count
+    # (S16: 6 instead of 13; 1025^2 / 2001^2 nodes: 6 instead of 9 / 10).  () = V-cycle.
+    DEFAULT_CYCLE = (1, 1, 3)
 
-    def __init__(self, mesh, formulation, material, boundary_condition, nu=3, omega=0.67, coarsest=100, check_every=2):
+    def __init__(self, mesh, formulation, material, boundary_condition, nu=3, omega=0.67, coarsest=100, check_every=2,
+                 cycle=None):
         from .FiniteElements.fused import grid_shape
         if formulation.ndim != 2 or formulation.nvar != 1:
             raise ValueError("GridMultigrid needs a 2-D scalar problem")
@@ -51,6 +57,9 @@ class GridMultigrid(object):
             self.levels.append((int(nx.value), int(ny.value)))
         if self.omegas is not None:
             _lib.check(self.lib.kb_mg_set_smoother(self._h, self.nu, (_lib.F64 * self.nu)(*self.omegas)))
+        # cycle: coarse-grid corrections per visit of level 0, 1, 2, ... (missing levels: 1); None = the default schedule
+        self.cycle = list(self.DEFAULT_CYCLE if cycle is None else cycle)
+        _lib.check(self.lib.kb_mg_set_cycle(self._h, len(self.cycle), (ctypes.c_int32 * max(1, len(self.cycle)))(*self.cycle)))
         self._ws = D.empty(int(self.lib.kb_mg_workspace_bytes(self._h)), torch.uint8)
         self._solve_ws = None
         self.cycles = 0

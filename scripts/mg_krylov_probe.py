@@ -16,6 +16,9 @@ import os as _os
 from kiltro_b200 import _lib as _LL
 if "MG_OVERWEIGHT" in _os.environ:
     _LL.load().kb_mg_set_overweight(float(_os.environ["MG_OVERWEIGHT"]))
+if "MG_CYCLE" in _os.environ:
+    from kiltro_b200.multigrid import GridMultigrid as _GM
+    _GM.DEFAULT_CYCLE = tuple(int(v) for v in _os.environ["MG_CYCLE"].split(","))
 if "MG_UPWIND" in _os.environ:
     _LL.load().kb_mg_set_upwind_restriction(int(_os.environ["MG_UPWIND"]))
 nps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000

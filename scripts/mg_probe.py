@@ -16,6 +16,9 @@ import os as _os
 from kiltro_b200 import _lib as _LL
 if "MG_OVERWEIGHT" in _os.environ:
     _LL.load().kb_mg_set_overweight(float(_os.environ["MG_OVERWEIGHT"]))
+if "MG_CYCLE" in _os.environ:
+    from kiltro_b200.multigrid import GridMultigrid as _GM
+    _GM.DEFAULT_CYCLE = tuple(int(v) for v in _os.environ["MG_CYCLE"].split(","))
 if "MG_UPWIND" in _os.environ:
     _LL.load().kb_mg_set_upwind_restriction(int(_os.environ["MG_UPWIND"]))
 import os
@@ -28,6 +31,8 @@ if "MG_PFD" in os.environ:
     _L.load().kb_mg_set_prefetch_rows(int(os.environ["MG_PFD"]))
 if "MG_MINROWS" in os.environ:
     _L.load().kb_mg_set_min_rows(int(os.environ["MG_MINROWS"]))
+if "MG_AGGR" in os.environ:
+    _L.load().kb_mg_set_aggressive(int(os.environ["MG_AGGR"]))
 if "MG_PF1" in os.environ:
     _L.load().kb_mg_set_prefetch_rows_l1(int(os.environ["MG_PF1"]))
 NU = int(os.environ.get("MG_NU", "3"))

@@ -132,11 +132,13 @@ def test_vcycle_is_a_contraction_and_linear():
     assert torch.equal(mg.apply(r1), z1)
 
 
-@pytest.mark.parametrize("nps,nu,omega", [(301, 2, 0.67), (301, 1, 0.67), (301, 3, 0.67), (130, 2, 0.6), (47, 3, 0.67),
-                                          (130, 3, (0.6, 0.67, 0.55))])
-def test_fused_legs_bitwise(nps, nu, omega):
+@pytest.mark.parametrize("nps,nu,omega,cycle", [(301, 2, 0.67, ()), (301, 1, 0.67, ()), (301, 3, 0.67, ()), (130, 2, 0.6, ()),
+                                                (47, 3, 0.67, ()), (130, 3, (0.6, 0.67, 0.55), ()), (301, 3, 0.67, (1, 2, 3)),
+                                                (130, 2, 0.67, (2, 1, 2, 2))])
+def test_fused_legs_bitwise(nps, nu, omega, cycle):
     """The fused legs (one kernel per leg and level: temporal blocking in registers) reproduce the one-kernel-per-sweep
-    cycle bit for bit, for every task height, with and without the s = r - alpha v update riding in the staging kernel."""
+    cycle bit for bit, for every task height, with and without the s = r - alpha v update riding in the staging kernel,
+    for V-cycles and for schedules that repeat the coarse-grid correction of some levels."""
     import bench
     import kiltro_b200 as K
     from kiltro_b200 import _lib
@@ -150,7 +152,7 @@ def test_fused_legs_bitwise(nps, nu, omega):
     bc.GetDirichletBoundaryConditions(form, mesh, mat, fs)
     F = torch.zeros((mesh.nnodes, 1), dtype=torch.float64, device="cuda")
     Kb, Fb = bc.ApplyDirichletGetReducedMatrices(Kc, F, bc.applied_dirichlet_device)[:2]
-    mg = GridMultigrid(mesh, form, mat, bc, nu=nu, omega=omega)
+    mg = GridMultigrid(mesh, form, mat, bc, nu=nu, omega=omega, cycle=cycle)
     mg.setup(Kb)
     g = torch.Generator(device="cuda"); g.manual_seed(5)
     r = torch.randn(Kb.shape[0], dtype=torch.float64, device="cuda", generator=g)
