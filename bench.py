@@ -924,21 +924,27 @@ def main():
         # coefficients, d, the rhs and writes x and the residual (+ on level 0 the fp64 vector in, the node map, 1/d and the
         # staged rhs out), the restriction reads the residual, the up-leg moves the coefficients, rhs and x in and x out (on
         # level 0 the node map and the fp64 result instead)
-        vc_bytes = 0
+        vc_bytes, visits = 0, 1
         for li, (lx, ly) in enumerate(mg.levels[:-1]):
             npad = ly * ((lx + 1 + 31) // 32 * 32)
             down = (32 + 4 + 4 + 4 + 4) * npad + ((8 + 4 + 4 + 4) * npad if li == 0 else 0)
             up = (32 + 4 + 4) * npad + ((4 + 8) * npad if li == 0 else 4 * npad)
-            vc_bytes += down + 4 * npad + up
+            reps = mg.cycle[li] if li < len(mg.cycle) else 1
+            # a repeated coarse-grid correction adds a prolongation (x in / out + coarse x), a residual (coefficients, d, rhs,
+            # x in, r out) and a restriction per repetition
+            extra = (reps - 1) * ((4 + 4 + 1) * npad + (32 + 4 + 4 + 4 + 4) * npad + 4 * npad)
+            vc_bytes += visits * (down + 4 * npad + up + extra)
+            visits *= reps
         vc_ms = s2.elapsed_time(s3) / 10
-        mg_roof = {"bound": "hbm", "kernel": "one V-cycle (k_mg_leg down / up legs + k_mg_restrict per level, nu = %d)" % mg.nu,
+        mg_roof = {"bound": "hbm", "kernel": "one multigrid cycle (k_mg_leg down / up legs + k_mg_restrict per level, nu = %d, coarse-grid corrections "
+                                       "per level %s)" % (mg.nu, list(mg.cycle)),
                    "achieved": vc_bytes / (vc_ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
                    "frac": vc_bytes / (vc_ms * 1e-3) * 1e-9 / peak, "algorithmic_bytes_per_cycle": int(vc_bytes),
                    "ms_per_cycle": vc_ms, "peak_source": peak_src,
-                   "note": "whole cycle (10 levels, 19 + 9 kernels), CUDA events over 10 back-to-back cycles; the levels below "
-                           "251^2 nodes are latency-bound chains of small kernels"}
+                   "note": "whole cycle (all levels), CUDA events over 10 back-to-back cycles; the levels below 251^2 nodes are "
+                           "latency-bound chains of small kernels"}
         mgleg = {"value": nn * args.steps / (mg_ms * 1e-3), "unit": UNIT, "ms_per_step": mg_ms / args.steps,
-                 "roofline": mg_roof, "nu": mg.nu, "omega": mg.omega,
+                 "roofline": mg_roof, "nu": mg.nu, "omega": mg.omega, "cycle": list(mg.cycle),
                  "steps": args.steps, "method": minfo["method"], "iterations": minfo["iterations"], "levels": minfo["levels"],
                  "level_shapes": mg.levels, "status": minfo["status"], "relative_residual": minfo["relative_residual"],
                  "rtol": args.rtol, "phases_ms_per_step": {k: v / args.steps for k, v in mg_phase.items()},
