@@ -68,6 +68,7 @@ struct kb_mg {
     int reps[MG_MAXLEV];            // coarse-grid corrections per visit of level l (1 everywhere: V-cycle); kb_mg_set_cycle
     int *free2pp = nullptr, *free2node = nullptr;
     int *n2f = nullptr;             // level 0, padded like the vectors: unknown of a node, -1 elsewhere
+    int tail_first = -1;            // first level of the shared-memory tail (k_mg_tail), -1: none
     int ncoarse = 0;
     double *dense = nullptr;
     float *ainv = nullptr;
@@ -766,6 +767,178 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ coarse tail
+// The coarsest levels (<= TAIL_NODES nodes each, e.g. 33^2, 17^2, 9^2) as ONE kernel of one CTA with everything in shared
+// memory: as separate kernels each of them is three launches of pure latency per visit (~28 us), and the cycle schedule
+// visits them several times per cycle.  Same operations in the same order as the per-level kernels -- first sweep from
+// zero, nu-1 sweeps, residual, restriction ... dense solve ... prolongation, nu sweeps -- through the same device functions
+// (stencil_res, prolong_value), so the result is bit-identical (test_fused_legs_bitwise runs with and without it).
+// Arrays live in shared memory with a one-node zero border (pitch nx+2), coefficients as eight planes.
+constexpr int TAIL_MAXLEV = 4;
+constexpr int TAIL_NODES = 1200;            // a level joins the tail when nx * ny <= TAIL_NODES
+struct TailLevelArgs {
+    int nx, ny, pitch;                      // global layout
+    const float *cf, *d, *dinv;             // global
+    const int *jx, *jy, *sx, *sy;           // transfer tables towards the next (coarser) tail level
+    const float *wx, *wy;
+    int off;                                // first float of the level's block in shared memory
+};
+struct TailArgs {
+    int nlev, nu, ncoarse;
+    TailLevelArgs L[TAIL_MAXLEV];
+    const float *bh_in;                     // global rhs of the first tail level (padded layout)
+    float *x_out;                           // global x of the first tail level after the sub-cycle (padded layout)
+    const float *ainv;
+    float omega[4];
+    const int *done;
+};
+__host__ __device__ inline int tail_ps(int nx) { return nx + 2; }
+__host__ __device__ inline int tail_block_floats(int nx, int ny) { return 14 * (nx + 2) * (ny + 2); }   // 8 c + d + dinv + bh + xa + xb + r
+
+__global__ void __launch_bounds__(1024) k_mg_tail(const TailArgs a) {
+    kb_pdl_wait();
+    if (a.done != nullptr && *a.done != 0) return;
+    extern __shared__ float s_tail[];
+    __shared__ float s_b[MG_DENSE_MAX + 1];
+    const int tid = threadIdx.x, T = blockDim.x;
+    // ---- load: coefficients, d, 1/d of every tail level; vectors zeroed (borders stay zero)
+    for (int l = 0; l < a.nlev; ++l) {
+        const TailLevelArgs &L = a.L[l];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        float *base = s_tail + L.off;
+        for (int e = tid; e < 14 * plane; e += T) base[e] = 0.f;
+    }
+    __syncthreads();
+    for (int l = 0; l < a.nlev; ++l) {
+        const TailLevelArgs &L = a.L[l];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        float *base = s_tail + L.off;
+        for (int q = tid; q < L.nx * L.ny; q += T) {
+            const int i = q % L.nx, j = q / L.nx;
+            const int64_t pp = (int64_t)j * L.pitch + i;
+            const int sp = (j + 1) * ps + i + 1;
+            const float4 lo = ld4(L.cf + 8 * pp), hi = ld4(L.cf + 8 * pp + 4);
+            base[0 * plane + sp] = lo.x; base[1 * plane + sp] = lo.y; base[2 * plane + sp] = lo.z; base[3 * plane + sp] = lo.w;
+            base[4 * plane + sp] = hi.x; base[5 * plane + sp] = hi.y; base[6 * plane + sp] = hi.z; base[7 * plane + sp] = hi.w;
+            base[8 * plane + sp] = L.d[pp];
+            base[9 * plane + sp] = L.dinv[pp];
+            if (l == 0) base[10 * plane + sp] = a.bh_in[pp];
+        }
+    }
+    __syncthreads();
+    auto sweep = [&](int l, int src, int dst, float om, bool residual) {          // planes: 10 bh, 11 xa, 12 xb, 13 r
+        const TailLevelArgs &L = a.L[l];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        const float *base = s_tail + L.off;
+        const float *x = base + src * plane;
+        float *out = s_tail + L.off + dst * plane;
+        for (int q = tid; q < L.nx * L.ny; q += T) {
+            const int i = q % L.nx, j = q / L.nx;
+            const int sp = (j + 1) * ps + i + 1;
+            float cc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cc[k] = base[k * plane + sp];
+            const float mc = x[sp];
+            const float res = stencil_res(cc, x[sp - ps - 1], x[sp - ps], x[sp - ps + 1], x[sp - 1], mc, x[sp + 1],
+                                          x[sp + ps - 1], x[sp + ps], x[sp + ps + 1], base[10 * plane + sp]);
+            out[sp] = residual ? base[8 * plane + sp] * res : fmaf(om, res, mc);
+        }
+        __syncthreads();
+    };
+    int cur[TAIL_MAXLEV];
+    // ---- down
+    for (int l = 0; l + 1 < a.nlev; ++l) {
+        const TailLevelArgs &L = a.L[l], &C = a.L[l + 1];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        float *base = s_tail + L.off;
+        for (int q = tid; q < L.nx * L.ny; q += T) {                                  // first sweep from zero
+            const int sp = (q / L.nx + 1) * ps + q % L.nx + 1;
+            base[11 * plane + sp] = a.omega[0] * base[10 * plane + sp];
+        }
+        __syncthreads();
+        int c = 11, o = 12;
+        for (int k = 1; k < a.nu; ++k) { sweep(l, c, o, a.omega[k], false); const int t = c; c = o; o = t; }
+        sweep(l, c, 13, 0.f, true);
+        cur[l] = c;
+        // restriction (the arithmetic of k_mg_restrict with the Petrov-Galerkin / over-weighting switches off)
+        const int psc = tail_ps(C.nx), planec = psc * (C.ny + 2);
+        float *cb = s_tail + C.off;
+        const float *r = base + 13 * plane;
+        for (int q = tid; q < C.nx * C.ny; q += T) {
+            const int ic = q % C.nx, jc = q / C.nx;
+            const int spc = (jc + 1) * psc + ic + 1;
+            const float dv = cb[9 * planec + spc];
+            float b = 0.f;
+            if (dv != 0.f) {
+                const int i0 = L.sx[ic > 0 ? ic - 1 : 0], cnt = L.sx[ic + 1 < C.nx ? ic + 1 : C.nx] - i0;
+                const int j0 = L.sy[jc > 0 ? jc - 1 : 0], j1 = L.sy[jc + 1 < C.ny ? jc + 1 : C.ny];
+                float acc = 0.f;
+                for (int jf = j0; jf < j1; ++jf) {
+                    const float wyf = L.wy[jf];
+                    const float wyv = (L.jy[jf] == jc) ? 1.f - wyf : wyf;
+                    const float *row = r + (jf + 1) * ps + i0 + 1;
+                    float racc = 0.f;
+                    for (int u = 0; u < cnt; ++u) {
+                        const float w = L.wx[i0 + u];
+                        racc = fmaf((L.jx[i0 + u] == ic) ? 1.f - w : w, row[u], racc);
+                    }
+                    acc = fmaf(wyv, racc, acc);
+                }
+                b = acc * dv;
+            }
+            cb[10 * planec + spc] = b;
+        }
+        __syncthreads();
+    }
+    // ---- coarsest: x = Ainv bh (one warp per row, as k_mg_dense_solve)
+    {
+        const int l = a.nlev - 1;
+        const TailLevelArgs &L = a.L[l];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2), n = a.ncoarse;
+        float *base = s_tail + L.off;
+        for (int q = tid; q < n; q += T) s_b[q] = base[10 * plane + (q / L.nx + 1) * ps + q % L.nx + 1];
+        __syncthreads();
+        const int lane = tid & 31, w = tid >> 5, nw = T >> 5;
+        for (int r = w; r < n; r += nw) {
+            const float *row = a.ainv + (size_t)r * n;
+            float acc = 0.f;
+            for (int c = lane; c < n; c += 32) acc = fmaf(row[c], s_b[c], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(KB_FULL, acc, o);
+            if (lane == 0) base[12 * plane + (r / L.nx + 1) * ps + r % L.nx + 1] = acc;
+        }
+        cur[l] = 12;
+        __syncthreads();
+    }
+    // ---- up
+    for (int l = a.nlev - 2; l >= 0; --l) {
+        const TailLevelArgs &L = a.L[l], &C = a.L[l + 1];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        const int psc = tail_ps(C.nx), planec = psc * (C.ny + 2);
+        float *xf = s_tail + L.off + cur[l] * plane;
+        const float *xc = s_tail + C.off + cur[l + 1] * planec;
+        for (int q = tid; q < L.nx * L.ny; q += T) {
+            const int i = q % L.nx, j = q / L.nx;
+            const float *r0 = xc + (L.jy[j] + 1) * psc + L.jx[i] + 1, *r1 = r0 + psc;
+            xf[(j + 1) * ps + i + 1] += prolong_value(r0[0], r0[1], r1[0], r1[1], L.wx[i], L.wy[j]);
+        }
+        __syncthreads();
+        int c = cur[l], o = (c == 11) ? 12 : 11;
+        for (int k = 0; k < a.nu; ++k) { sweep(l, c, o, a.omega[k], false); const int t = c; c = o; o = t; }
+        cur[l] = c;
+    }
+    // ---- out
+    {
+        const TailLevelArgs &L = a.L[0];
+        const int ps = tail_ps(L.nx), plane = ps * (L.ny + 2);
+        const float *x = s_tail + L.off + cur[0] * plane;
+        for (int q = tid; q < L.nx * L.ny; q += T) {
+            const int i = q % L.nx, j = q / L.nx;
+            a.x_out[(int64_t)j * L.pitch + i] = x[(j + 1) * ps + i + 1];
+        }
+    }
+}
+
 dim3 grid2d(int width, int block, int ny) {
     const int gx = (int)kb_cdiv(width, block);
     int gy = (int)((int64_t)kb_num_sms() * 16 / gx);
@@ -848,6 +1021,41 @@ int launch_prolong(const MgLevel &L, const MgLevel &Cn, const float *xc, float *
     return 0;
 }
 
+int g_mg_tail = 1;            // 1: the coarsest levels run as one shared-memory kernel (kb_mg_set_tail)
+
+size_t tail_smem_bytes(const kb_mg *mg, int first) {
+    size_t f = 0;
+    for (int l = first; l < mg->nlev; ++l) f += (size_t)tail_block_floats(mg->L[l].nx, mg->L[l].ny);
+    return f * sizeof(float);
+}
+bool tail_usable(const kb_mg *mg) {
+    if (!g_mg_tail || mg->tail_first < 0 || g_mg_upwind || g_mg_overweight != 1.f || mg->nu > 4) return false;
+    for (int l = mg->tail_first; l < mg->nlev; ++l) if (mg->reps[l] != 1) return false;
+    return true;
+}
+int launch_tail(kb_mg *mg, const int *done, cudaStream_t s, bool pdl) {
+    TailArgs a = {};
+    const int first = mg->tail_first;
+    a.nlev = mg->nlev - first; a.nu = mg->nu; a.ncoarse = mg->ncoarse; a.ainv = mg->ainv; a.done = done;
+    for (int k = 0; k < 4; ++k) a.omega[k] = mg->omega[k];
+    int off = 0;
+    for (int k = 0; k < a.nlev; ++k) {
+        const MgLevel &L = mg->L[first + k];
+        TailLevelArgs &t = a.L[k];
+        t.nx = L.nx; t.ny = L.ny; t.pitch = L.pitch; t.cf = L.cf; t.d = L.d; t.dinv = L.dinv;
+        t.jx = L.jx; t.jy = L.jy; t.sx = L.sx; t.sy = L.sy; t.wx = L.wx; t.wy = L.wy;
+        t.off = off;
+        off += tail_block_floats(L.nx, L.ny);
+    }
+    a.bh_in = mg->L[first].bh; a.x_out = mg->L[first].xb;
+    const size_t bytes = (size_t)off * sizeof(float);
+    static KbOncePerDevice configured;
+    if (configured.need()) KB_CUDA(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KB_CUDA(kb_launch_pdl(k_mg_tail, dim3(1), dim3(1024), bytes, s, pdl, a));
+    KB_LAUNCH_CHECK();
+    return 0;
+}
+
 // The cycle with fused legs, recursive: down-leg (pre-smoothing + residual) -> restriction -> cycle on the coarser levels
 // -> up-leg (prolongation + post-smoothing).  mg->reps[l] > 1 repeats the coarse-grid correction of level l from the
 // corrected iterate (prolongation and residual by the one-kernel-per-node forms, no smoothing in between) before the
@@ -860,6 +1068,7 @@ int cycle_fused(FusedCtx &c, int l) {
     const int nl = mg->nlev, ns = mg->nu;
     const MgLevel &L = mg->L[l];
     int rc;
+    if (l == mg->tail_first && l > 0 && tail_usable(mg)) return launch_tail(mg, c.done, c.s, c.pdl);   // bh of l -> xb of l
     if (l == nl - 1) {
         KB_CUDA(kb_launch_pdl(k_mg_dense_solve, dim3(1), dim3(1024), 0, c.s, c.pdl, mg->ncoarse, L.nx, L.pitch,
                               (const float *)mg->ainv, (const float *)L.bh, L.xb, c.done));
@@ -995,6 +1204,9 @@ extern "C" int kb_mg_create(int64_t nxn, int64_t nyn, int64_t coarsest_nodes, kb
     const MgLevel &Lc = mg->L[mg->nlev - 1];
     if ((int64_t)Lc.nx * Lc.ny > MG_DENSE_MAX) { delete mg; return KB_ETOOBIG; }
     mg->ncoarse = Lc.nx * Lc.ny;
+    for (int l = 1; l + 1 < mg->nlev; ++l)                  // shared-memory tail: >= 2 levels of <= TAIL_NODES nodes that fit
+        if ((int64_t)mg->L[l].nx * mg->L[l].ny <= TAIL_NODES && mg->nlev - l <= TAIL_MAXLEV &&
+            tail_smem_bytes(mg, l) <= 200 * 1024) { mg->tail_first = l; break; }
     for (int l = 0; l + 1 < mg->nlev; ++l) {
         MgLevel &L = mg->L[l];
         const MgLevel &Cn = mg->L[l + 1];
@@ -1124,6 +1336,7 @@ extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stre
 /* development switches: fused legs on / off (results are bit-identical), node rows per warp task of the fused legs
  * (0 = chosen per level), their L2 prefetch distance */
 extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
+extern "C" void kb_mg_set_tail(int on) { g_mg_tail = on; }
 /* cycle schedule: h_reps[l] = coarse-grid corrections per visit of level l (levels beyond n keep 1 = V-cycle) */
 extern "C" int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps) {
     if (!mg || !h_reps || n < 0 || n > MG_MAXLEV) return KB_EINVAL;

@@ -33,6 +33,8 @@ if "MG_MINROWS" in os.environ:
     _L.load().kb_mg_set_min_rows(int(os.environ["MG_MINROWS"]))
 if "MG_AGGR" in os.environ:
     _L.load().kb_mg_set_aggressive(int(os.environ["MG_AGGR"]))
+if "MG_TAIL" in os.environ:
+    _L.load().kb_mg_set_tail(int(os.environ["MG_TAIL"]))
 if "MG_PF1" in os.environ:
     _L.load().kb_mg_set_prefetch_rows_l1(int(os.environ["MG_PF1"]))
 NU = int(os.environ.get("MG_NU", "3"))

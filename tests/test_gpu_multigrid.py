@@ -164,12 +164,15 @@ def test_fused_legs_bitwise(nps, nu, omega, cycle):
         for rows in (64, 8, 23, 1000):
             lib.kb_mg_set_rows_per_task(rows)
             assert torch.equal(mg.apply(r), ref), rows
-        lib.kb_mg_set_rows_per_task(64)
+        lib.kb_mg_set_tail(0)                                  # the coarsest levels as separate kernels instead of k_mg_tail
+        assert torch.equal(mg.apply(r), ref)
+        lib.kb_mg_set_tail(1)
+        lib.kb_mg_set_rows_per_task(0)
         x, info = mg.solve(Kb, Fb.reshape(-1), rtol=1e-11, reuse_setup=True)
         assert info["iterations"] == info_ref["iterations"] and info["status"] == 0, (info, info_ref)
         assert torch.equal(x, x_ref)
     finally:
-        lib.kb_mg_set_fused(1); lib.kb_mg_set_rows_per_task(64)
+        lib.kb_mg_set_fused(1); lib.kb_mg_set_rows_per_task(0); lib.kb_mg_set_tail(1)
 
 
 def test_multigrid_rejects_what_it_cannot_precondition():
