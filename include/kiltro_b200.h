@@ -476,7 +476,10 @@ void kb_mg_set_min_rows(int rows);        /* shortest task (rows) the per-level 
 void kb_mg_set_prefetch_rows(int rows);   /* L2 prefetch distance of the fused kernels (0 = off) */
 void kb_mg_set_prefetch_rows_l1(int rows);   /* L1 prefetch distance (0, 1 or 2 rows) */
 /* x: initial guess in, solution out; verdict, restarts and kb_solve_info as kb_bicgstab_solve (TRUE residual of the
- * system as handed over).  Synchronises the stream every check_every iterations. */
+ * system as handed over).  Synchronises the stream every check_every iterations.  The row partition and row-pattern
+ * dictionary of the matrix are kept in d_workspace and reused while the SAME d_indptr / d_indices / d_workspace pointers
+ * (and sizes) are passed again: the caller must not change the pattern arrays in place, nor let their storage be recycled
+ * for another pattern, between such calls (values may change freely). */
 size_t kb_mg_bicgstab_workspace_bytes(int64_t nrows, int64_t nnz);
 int kb_mg_bicgstab_solve(kb_mg *mg, int64_t nrows, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
                          const double *d_vals, const double *d_b, double *d_x, double rtol, int maxiter, int check_every,

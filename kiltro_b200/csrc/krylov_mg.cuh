@@ -79,12 +79,19 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
     Work &w = m.w;
     k_reset_state<<<1, 32, 0, s>>>(w.ticket, w.done, w.iter, w.sc);
     KB_LAUNCH_CHECK();
-    {   // row partition + row-pattern dictionary of the matrix as handed over
+    // row partition + row-pattern dictionary of the matrix as handed over: kept in the workspace and reused while the same
+    // pattern arrays and the same workspace come back (a FEM pattern is built once per mesh; the values may change)
+    KbMgSolveCache *cache = kbmg_solve_cache(mg);
+    if (cache->indptr == indptr && cache->indices == indices && cache->workspace == workspace && cache->n == n &&
+        cache->nnz == nnz) {
+        w.usepat = cache->usepat != 0 && !g_no_patterns && !g_force_idx32 && !g_force_simple_spmv && tma_eligible(indptr, w.row_pat, vals);
+    } else {
         const int64_t nblk = num_blocks(nnz);
         k_partition<<<(unsigned)kb_cdiv(nblk + 1, 256), 256, 0, s>>>(n, nblk, indptr, w.rowblk);
         KB_LAUNCH_CHECK();
         KB_CUDA(cudaMemsetAsync(w.bandflag, 0, sizeof(int) * 4, s));
         w.usepat = false;
+        int have = 0;
         if (!g_force_idx32 && !g_no_patterns) {
             const int g = kb_grid(n, 256, 8);
             KB_CUDA(cudaMemsetAsync(w.pat_keys, 0, sizeof(unsigned long long) * P_SLOTS, s));
@@ -96,7 +103,9 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
             int flag[2] = {1, 1};
             KB_CUDA(cudaMemcpyAsync(flag, w.bandflag, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
             KB_CUDA(cudaStreamSynchronize(s));
-            w.usepat = (flag[1] == 0) && !g_force_simple_spmv && tma_eligible(indptr, w.row_pat, vals);
+            have = flag[1] == 0;
+            w.usepat = have && !g_force_simple_spmv && tma_eligible(indptr, w.row_pat, vals);
+            *cache = KbMgSolveCache{indptr, indices, workspace, n, nnz, have};
         }
     }
     int rc;

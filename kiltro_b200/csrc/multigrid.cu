@@ -76,6 +76,7 @@ struct kb_mg {
     bool has_velocity = false;
     bool ready = false;
     void *ws_base = nullptr;        // workspace the device pointers above were carved from
+    KbMgSolveCache solve_cache = {nullptr, nullptr, nullptr, 0, 0, 0};
 };
 
 namespace {
@@ -160,40 +161,41 @@ __global__ void __launch_bounds__(256) k_mg_free_map(int64_t nn, int nx, int pit
     }
 }
 
-// level 0: CSR rows of the reduced system -> unit-diagonal stencil coefficients.  An entry outside the 9-point
-// neighbourhood of its row raises flag[0].
+// level 0: CSR rows of the reduced system -> unit-diagonal stencil coefficients.  The stencil slot of an entry is found by
+// comparing its column with the unknowns of the row's eight grid neighbours (read from the padded node -> unknown map:
+// consecutive rows read consecutive addresses) instead of gathering the node of every column.  An entry that belongs to
+// none of them -- outside the 9-point neighbourhood -- raises flag[0].
 __global__ void __launch_bounds__(256) k_mg_dia_from_csr(int64_t nfree, const int32_t *__restrict__ indptr,
                                                          const int32_t *__restrict__ indices, const double *__restrict__ vals,
-                                                         const int *__restrict__ free2node, int nx, int pitch,
+                                                         const int *__restrict__ free2pp, const int *__restrict__ n2f, int pitch,
                                                          float *__restrict__ cf, float *__restrict__ d,
                                                          float *__restrict__ dinv, int *__restrict__ flag) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     bool bad = false;
     for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nfree; f += stride) {
-        const int p = free2node[f], i = p % nx, j = p / nx;
-        const int64_t pp = (int64_t)j * pitch + i;
+        const int pp = free2pp[f];
+        const int *c = n2f + pp;
+        const int nb[8] = {c[-pitch - 1], c[-pitch], c[-pitch + 1], c[-1], c[1], c[pitch - 1], c[pitch], c[pitch + 1]};
         const int e0 = indptr[f], e1 = indptr[f + 1];
         double dg = 0.0;
-        for (int e = e0; e < e1; ++e)
-            if (indices[e] == (int)f) dg += vals[e];
+        double off[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int e = e0; e < e1; ++e) {
+            const int col = indices[e];
+            const double v = vals[e];
+            if (col == (int)f) { dg += v; continue; }
+            bool hit = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (col == nb[k]) { off[k] += v; hit = true; }
+            bad |= !hit;
+        }
         if (!(dg != 0.0) || !isfinite(dg)) dg = 1.0;
         const double inv = 1.0 / dg;
         d[pp] = (float)dg;
         dinv[pp] = (float)inv;
-        float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int e = e0; e < e1; ++e) {
-            const int c = indices[e];
-            if (c == (int)f) continue;
-            const int q = free2node[c], dx = q % nx - i, dy = q / nx - j;
-            if (dx < -1 || dx > 1 || dy < -1 || dy > 1) { bad = true; continue; }
-            const int k = (dy + 1) * 3 + (dx + 1), k8 = k > 4 ? k - 1 : k;
-            const float v = (float)(vals[e] * inv);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) out[u] = (u == k8) ? v : out[u];
-        }
-        float4 *dst = reinterpret_cast<float4 *>(cf + 8 * pp);
-        dst[0] = make_float4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+        float4 *dst = reinterpret_cast<float4 *>(cf + 8 * (int64_t)pp);
+        dst[0] = make_float4((float)(off[0] * inv), (float)(off[1] * inv), (float)(off[2] * inv), (float)(off[3] * inv));
+        dst[1] = make_float4((float)(off[4] * inv), (float)(off[5] * inv), (float)(off[6] * inv), (float)(off[7] * inv));
     }
     if (bad) flag[0] = 1;
 }
@@ -1147,6 +1149,7 @@ int cycle_unfused(CycleCtx &c, int l) {
 }  // namespace
 
 int64_t kbmg_nfree(const kb_mg *mg) { return mg->nfree; }
+KbMgSolveCache *kbmg_solve_cache(kb_mg *mg) { return &mg->solve_cache; }
 bool kbmg_ready(const kb_mg *mg) { return mg->ready; }
 
 int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const double *d_alpha, const double *d_q,
@@ -1281,7 +1284,7 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
     k_mg_free_map<<<kb_grid(nn0, 256, 8), 256, 0, s>>>(nn0, L0.nx, L0.pitch, d_renum, mg->free2node, mg->free2pp, mg->n2f,
                                                        L0.fixed);
     KB_LAUNCH_CHECK();
-    k_mg_dia_from_csr<<<kb_grid(nfree, 256, 8), 256, 0, s>>>(nfree, d_indptr, d_indices, d_vals, mg->free2node, L0.nx,
+    k_mg_dia_from_csr<<<kb_grid(nfree, 256, 8), 256, 0, s>>>(nfree, d_indptr, d_indices, d_vals, mg->free2pp, mg->n2f,
                                                             L0.pitch, L0.cf, L0.d, L0.dinv, mg->flag);
     KB_LAUNCH_CHECK();
     const ElemOpts o = kb_make_opts(material, KB_MODE_CONSISTENT, d_velocity != nullptr ? 1 : 0, 0);

@@ -13,3 +13,8 @@ int kbmg_apply(kb_mg *mg, const double *d_v, double *d_s, double *d_z, const dou
                const int *done, cudaStream_t s, bool pdl);
 int64_t kbmg_nfree(const kb_mg *mg);
 bool kbmg_ready(const kb_mg *mg);
+
+// What kb_mg_bicgstab_solve keeps between calls in the caller's solve workspace (row partition + row-pattern dictionary of
+// the matrix): valid while the same pattern arrays and the same workspace are passed again.
+struct KbMgSolveCache { const void *indptr, *indices, *workspace; int64_t n, nnz; int usepat; };
+KbMgSolveCache *kbmg_solve_cache(kb_mg *mg);

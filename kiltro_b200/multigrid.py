@@ -114,6 +114,9 @@ class GridMultigrid(object):
             self._solve_ws = D.empty(nbytes, torch.uint8)
         x = D.zeros(n) if x0 is None else D.to_device(x0, torch.float64).reshape(-1).clone()
         info = _lib.kb_solve_info()
+        # the library keeps the SpMV's row-pattern dictionary of (indptr, indices) in the solve workspace and reuses it while
+        # the same arrays come back: holding the tensors keeps their addresses from being recycled for another pattern
+        self._pattern_ref = (A.indptr, A.indices)
         _lib.check(lib.kb_mg_bicgstab_solve(self._h, n, A.nnz, D.ptr(A.indptr), D.ptr(A.indices), D.ptr(A.data), D.ptr(b),
                                             D.ptr(x), float(rtol), int(maxiter), self.check_every, D.ptr(self._solve_ws),
                                             self._solve_ws.numel(), info, D.stream_ptr()))
