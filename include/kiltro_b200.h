@@ -101,6 +101,12 @@ int kb_element_matrices(int ndim, const double *d_points, const int32_t *d_eleme
 int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode, int nvar,
                      int32_t *d_indptr, int32_t *d_indices, int32_t *d_data_local, int32_t *d_data_global,
                      int32_t *d_seg_ptr, int32_t *d_gather_src, int32_t *d_diag_pos, int64_t *h_nnz, void *stream);
+/* The same indptr / indices / diag_pos for a quad-4 mesh numbered like Mesh.Rectangle (verified with kb_grid_verify),
+ * written down from the shape without forming or sorting the element entries; *h_nnz = (3 nxn - 2)(3 nyn - 2); stream-ordered,
+ * no synchronisation.  d_indices must hold that many entries.  The reference's two scatter maps and the gather map still
+ * come from kb_pattern_build (the host mirror builds them lazily, on first use). */
+int kb_pattern_grid(int64_t nxn, int64_t nyn, int32_t *d_indptr, int32_t *d_indices, int32_t *d_diag_pos, int64_t *h_nnz,
+                    void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K3  numeric assembly                      replaces FiniteElements/Assembly.py:46-72 (element loop, scatter-add)

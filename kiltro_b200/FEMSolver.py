@@ -27,6 +27,10 @@ def _say(*a):
 
 
 class FEMSolver(object):
+    # the reference stashes the two scatter maps on the solver (FEMSolver.py:321-322); here they are views of the cached
+    # pattern, built on first access (they are not needed on Mesh.Rectangle-numbered meshes)
+    data_local_indices = property(lambda self: None if self.sparsity is None else self.sparsity.data_local_indices)
+    data_global_indices = property(lambda self: None if self.sparsity is None else self.sparsity.data_global_indices)
 
     def __init__(self, analysis_type="steady", analysis_nature="linear",
                  number_of_load_increments=1, print_incremental_log=False,
@@ -275,7 +279,6 @@ class FEMSolver(object):
                 sp = ComputeSparsityPatternDevice(mesh, formulation.nvar)
                 self.sparsity = sp
                 self.indices, self.indptr = sp.indices, sp.indptr
-                self.data_local_indices, self.data_global_indices = sp.data_local_indices, sp.data_global_indices
                 self.is_sparsity_pattern_computed = True
                 torch.cuda.synchronize()
                 self.timings["pattern_s"] = time() - t_sp

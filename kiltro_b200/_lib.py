@@ -60,6 +60,7 @@ SIGNATURES = {
                                   c_vp]),
     "kb_pattern_build": (I32, [c_vp, I64, I32, I64, I32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                ctypes.POINTER(I64), c_vp]),
+    "kb_pattern_grid": (I32, [I64, I64, c_vp, c_vp, c_vp, ctypes.POINTER(I64), c_vp]),
     "kb_assemble_from_elements": (I32, [I32, I64, I64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kb_tile_plan_sizes": (I32, [I64, I64, I32, I64, I64, ctypes.POINTER(I64)]),
     "kb_tile_plan_build": (I32, [c_vp, I64, I32, I64, c_vp, c_vp, c_vp, c_vp, c_vp, I64, I64, c_vp, c_vp, c_vp, c_vp,

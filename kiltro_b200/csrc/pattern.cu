@@ -109,7 +109,41 @@ __global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ p, int64
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+// CSR pattern of a quad-4 mesh numbered like Mesh.Rectangle (node (i,j) = j nxn + i), written down from the shape: row (i,j)
+// holds the nodes of its <= 3 x 3 neighbourhood in ascending order -- exactly what the sort-based phase finds
+// (test_pattern_grid_shortcut_bit_exact), without forming or sorting the 16 nelem element entries.
+__global__ void __launch_bounds__(256) k_pattern_grid(int nxn, int nyn, int32_t *__restrict__ indptr,
+                                                      int32_t *__restrict__ indices, int32_t *__restrict__ diag_pos) {
+    const int64_t nn = (int64_t)nxn * nyn, stride = (int64_t)gridDim.x * blockDim.x;
+    const int rowlen = 3 * nxn - 2;                       // entries of a mesh row of nodes, per neighbouring mesh row
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += stride) {
+        const int i = (int)(p % nxn), j = (int)(p / nxn);
+        const int cy = (j > 0) + 1 + (j < nyn - 1);
+        const int before_y = j > 0 ? 3 * j - 1 : 0;       // sum of cy over the mesh rows below
+        const int before_x = i > 0 ? 3 * i - 1 : 0;       // sum of cx over the nodes to the left
+        int q = rowlen * before_y + cy * before_x;
+        indptr[p] = q;
+        for (int dj = (j > 0 ? -1 : 0); dj <= (j < nyn - 1 ? 1 : 0); ++dj)
+            for (int di = (i > 0 ? -1 : 0); di <= (i < nxn - 1 ? 1 : 0); ++di) {
+                if (dj == 0 && di == 0) diag_pos[p] = q;
+                indices[q++] = (int32_t)(p + (int64_t)dj * nxn + di);
+            }
+        if (p == nn - 1) indptr[nn] = q;
+    }
+}
+
 }  // namespace
+
+extern "C" int kb_pattern_grid(int64_t nxn, int64_t nyn, int32_t *d_indptr, int32_t *d_indices, int32_t *d_diag_pos,
+                               int64_t *h_nnz, void *stream) {
+    if (!d_indptr || !d_indices || !d_diag_pos || !h_nnz || nxn < 2 || nyn < 2) return KB_EINVAL;
+    const int64_t nnz = (3 * nxn - 2) * (3 * nyn - 2);
+    if (nnz >= INT32_MAX || nxn * nyn >= INT32_MAX) return KB_ETOOBIG;
+    k_pattern_grid<<<kb_grid(nxn * nyn, 256, 8), 256, 0, (cudaStream_t)stream>>>((int)nxn, (int)nyn, d_indptr, d_indices, d_diag_pos);
+    KB_LAUNCH_CHECK();
+    *h_nnz = nnz;
+    return 0;
+}
 
 extern "C" int kb_pattern_build(const int32_t *d_elements, int64_t nelem, int npe, int64_t nnode, int nvar,
                                 int32_t *d_indptr, int32_t *d_indices, int32_t *d_data_local, int32_t *d_data_global,

@@ -8,10 +8,11 @@ $CMD > gpurun_out/mg_plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 g
 tail -3 gpurun_out/mg_plain_$TAG.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/mg_launches_$TAG.csv $CMD > gpurun_out/mg_ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
-# 10 levels -> 18 leg launches per cycle: launch 18 k is a level-0 down-leg, 18 k + 17 a level-0 up-leg; 9 restrictions per cycle
-ncu --set full --clock-control none --import-source on -k regex:k_mg_leg -s 180 -c 1 -f -o gpurun_out/prof_mg_down_$TAG $CMD > gpurun_out/mg_ncu_full_$TAG.log 2>&1
+# default hierarchy of S16 (10 levels, schedule (1,1,3), the three coarsest levels in k_mg_tail): 30 leg launches per cycle
+# (launch 30 k is a level-0 down-leg, 30 k + 29 a level-0 up-leg) and 17 restrictions (17 k: level 0)
+ncu --set full --clock-control none --import-source on -k regex:k_mg_leg -s 300 -c 1 -f -o gpurun_out/prof_mg_down_$TAG $CMD > gpurun_out/mg_ncu_full_$TAG.log 2>&1
 echo "full capture (level-0 down-leg) rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_mg_leg -s 197 -c 1 -f -o gpurun_out/prof_mg_up_$TAG $CMD >> gpurun_out/mg_ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_mg_leg -s 329 -c 1 -f -o gpurun_out/prof_mg_up_$TAG $CMD >> gpurun_out/mg_ncu_full_$TAG.log 2>&1
 echo "full capture (level-0 up-leg) rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_mg_restrict -s 90 -c 1 -f -o gpurun_out/prof_mg_restrict_$TAG $CMD >> gpurun_out/mg_ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_mg_restrict -s 170 -c 1 -f -o gpurun_out/prof_mg_restrict_$TAG $CMD >> gpurun_out/mg_ncu_full_$TAG.log 2>&1
 echo "full capture (level-0 restriction) rc=$?"

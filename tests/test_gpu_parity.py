@@ -88,6 +88,26 @@ def test_pattern_nvar2_golden():
     assert np.array_equal(dl, c["data_local"]) and np.array_equal(dg, c["data_global"])
 
 
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 5), (7, 1), (2, 2), (40, 31), (257, 129)])
+def test_pattern_grid_shortcut_bit_exact(nx, ny):
+    """kb_pattern_grid (pattern of a Mesh.Rectangle-numbered mesh written down from the shape) equals the sort-based
+    phase bit for bit -- indptr, indices, diagonal positions -- and the lazily built scatter maps are the sort-based ones."""
+    import kiltro_b200.FiniteElements.ComputeSparsityPattern as CSP
+    K = _K()
+    m = K.Mesh(element_type="quad"); m.Rectangle((0.0, 0.0), (1.0, 2.0), nx, ny)
+    fast = CSP.ComputeSparsityPatternDevice(m, 1)
+    assert fast._maps_builder is not None and fast.grid == (nx + 1, ny + 1)          # the shortcut was taken, maps not built yet
+    CSP.GRID_SHORTCUT = False
+    try:
+        slow = CSP.ComputeSparsityPatternDevice(m, 1)
+    finally:
+        CSP.GRID_SHORTCUT = True
+    assert fast.nnz == slow.nnz
+    for name in ("indptr", "indices", "diag_pos", "data_local_indices", "data_global_indices", "seg_ptr", "gather_src"):
+        assert torch.equal(getattr(fast, name), getattr(slow, name)), name
+    assert fast._maps_builder is None
+
+
 @pytest.mark.parametrize("bad_id", [-1, 9, 1 << 20])
 def test_pattern_rejects_out_of_range_connectivity(bad_id):
     """A node id outside [0, nnode) in a user-provided mesh returns KB_EINVAL instead of overflowing the sort key and
