@@ -133,14 +133,29 @@ __global__ void __launch_bounds__(NR_ROWS) k_reduced_numeric(int64_t ndof, const
                 if (tid < nr)
                     for (int i = s_ip[tid] - p0, ie = s_ip[tid + 1] - p0; i < ie; ++i) s_row[i] = (uint8_t)tid;
                 __syncthreads();
-                for (int i = tid; i < np; i += NR_ROWS) {
-                    const int row = s_row[i];
-                    const int k = i - (s_ip[row] - p0);
-                    const uint32_t mm = s_mask[row];
-                    if ((mm >> k) & 1u) {
-                        const int dest = s_q[row] + __popc(mm & ((1u << k) - 1u));
-                        kb_data[dest] = ld_stream(K + p0 + i);
-                        if (MASS) mb_data[dest] = ld_stream(M + p0 + i);
+                // four entries per thread in flight: the loads are issued unconditionally (every i < np is a valid entry of
+                // K) before the mask tests, which the compiler would otherwise serialise load -> store -> load
+                for (int i0 = tid; i0 < np; i0 += 4 * NR_ROWS) {
+                    double kv[4], mv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * NR_ROWS;
+                        kv[u] = i < np ? ld_stream(K + p0 + i) : 0.0;
+                        mv[u] = (MASS && i < np) ? ld_stream(M + p0 + i) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * NR_ROWS;
+                        if (i < np) {
+                            const int row = s_row[i];
+                            const int k = i - (s_ip[row] - p0);
+                            const uint32_t mm = s_mask[row];
+                            if ((mm >> k) & 1u) {
+                                const int dest = s_q[row] + __popc(mm & ((1u << k) - 1u));
+                                kb_data[dest] = kv[u];
+                                if (MASS) mb_data[dest] = mv[u];
+                            }
+                        }
                     }
                 }
             } else if (r >= 0) {                                           // oversized block: per-row walk
