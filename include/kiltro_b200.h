@@ -2,8 +2,11 @@
  *
  * Conventions:
  *   - every pointer named d_* is a DEVICE pointer owned by the caller (torch tensor storage, cudaMalloc, ...);
- *     h_* is a HOST pointer; nothing is allocated behind the caller's back except where a function says so
- *     (kb_pattern_build allocates its sort scratch with cudaMallocAsync and frees it before returning);
+ *     h_* is a HOST pointer; nothing is allocated behind the caller's back except where a function says so: the
+ *     once-per-mesh symbolic builders (kb_pattern_build, kb_tile_plan_build, kb_tile_tmpl_build) take their sort scratch
+ *     with cudaMallocAsync and free it before returning, kb_peer_alloc creates the region it exports, kb_mg_create a host
+ *     plan.  Nothing on the per-step path (assembly, boundary conditions, solvers, time loops, multigrid set-up and
+ *     cycles) allocates: those functions take caller-owned workspaces sized by their *_workspace_bytes() queries;
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered; functions that return a count or a
  *     convergence record to the host synchronise that stream themselves and say so;
  *   - return value: 0 on success, >0 a cudaError_t, <0 a KB_E* code; kb_error_string() decodes both;

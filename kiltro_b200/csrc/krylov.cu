@@ -1101,9 +1101,10 @@ extern "C" int kb_make_row_patterns(int64_t nrows, const int32_t *d_indptr, cons
                                     void *d_pat_keys, int16_t *d_pat_tab, int32_t *d_flag, void *stream) {
     if (!d_indptr || !d_indices || !d_row_pat || !d_pat_keys || !d_pat_tab || !d_flag || nrows < 0) return KB_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    int *flag2;
-    KB_CUDA(cudaMallocAsync((void **)&flag2, sizeof(int) * 2, s));
-    KB_CUDA(cudaMemsetAsync(flag2, 0, sizeof(int) * 2, s));
+    // k_pattern_insert / k_pattern_verify raise slot [1] of the flag block they are given (slot [0] belongs to the 16-bit
+    // band test of the solver set-up and is not touched by them): hand them d_flag - 1, so that slot is the caller's word
+    int *flag2 = d_flag - 1;
+    KB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
     KB_CUDA(cudaMemsetAsync(d_pat_keys, 0, sizeof(unsigned long long) * P_SLOTS, s));
     KB_CUDA(cudaMemsetAsync(d_row_pat, 0, (size_t)((nrows + 15) / 16 * 16 + 16), s));
     if (nrows > 0) {
@@ -1113,8 +1114,6 @@ extern "C" int kb_make_row_patterns(int64_t nrows, const int32_t *d_indptr, cons
         k_pattern_verify<<<g, 256, 0, s>>>(nrows, d_indptr, d_indices, d_pat_tab, d_row_pat, flag2);
         KB_LAUNCH_CHECK();
     }
-    KB_CUDA(cudaMemcpyAsync(d_flag, flag2 + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    KB_CUDA(cudaFreeAsync(flag2, s));
     return 0;
 }
 

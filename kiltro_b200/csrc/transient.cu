@@ -86,9 +86,8 @@ extern "C" int kb_time_step_rule(int ndim, const double *d_points, const int32_t
                                  const kb_material *material, double factor, double *d_dt, void *stream) {
     if (!d_points || !d_elements || !material || !d_dt || nelem < 1 || (ndim != 1 && ndim != 2)) return KB_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long *tmp;
-    KB_CUDA(cudaMallocAsync((void **)&tmp, sizeof(unsigned long long), s));
-    KB_CUDA(cudaMemsetAsync(tmp, 0xff, sizeof(unsigned long long), s));
+    unsigned long long *tmp = reinterpret_cast<unsigned long long *>(d_dt);    // the 8 bytes of the result double as the
+    KB_CUDA(cudaMemsetAsync(tmp, 0xff, sizeof(unsigned long long), s));          // atomic-min accumulator: nothing is allocated
     const double c = material->rho * material->c_v / (2.0 * material->k);
     const int g = kb_grid(nelem, 256, 8);
     if (ndim == 2) k_dt_rule<2><<<g, 256, 0, s>>>(d_points, d_elements, nelem, c, tmp);
@@ -96,7 +95,6 @@ extern "C" int kb_time_step_rule(int ndim, const double *d_points, const int32_t
     KB_LAUNCH_CHECK();
     k_dt_finish<<<1, 1, 0, s>>>(tmp, factor, d_dt);
     KB_LAUNCH_CHECK();
-    KB_CUDA(cudaFreeAsync(tmp, s));
     return 0;
 }
 
