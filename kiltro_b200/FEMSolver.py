@@ -198,6 +198,9 @@ class FEMSolver(object):
             raise ValueError("FEMSolver(partition='rows') needs a mesh made with Mesh.Rectangle(..., partition=StripPartition(...))")
         if self.analysis_nature == "nonlinear":
             raise ValueError("nonlinear analysis is not available (the reference's branch is unreachable too)")
+        if getattr(solver, "preconditioner", None) is not None:
+            raise ValueError("LinearSolver(preconditioner=...) is a single-GPU option: the partitioned solvers are the "
+                             "prescribed Jacobi-CG / Jacobi-BiCGSTAB")
         comm = self.comm
         if comm is None:
             comm = KD.DistComm() if part.world > 1 else KD.LocalComm(1)

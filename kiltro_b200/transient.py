@@ -18,6 +18,10 @@ def snapshot_indices(nincr):
 
 def run_transient(fem_solver, function_spaces, formulation, solver, mesh, material, boundary_condition, NeumannFluxes):
     lib = _lib.load()
+    if getattr(solver, "preconditioner", None) is not None:
+        from warnings import warn
+        warn("LinearSolver(preconditioner=...) is ignored by the transient loop: its inner systems (M + theta dt K) are "
+             "solved with the prescribed Jacobi-CG / Jacobi-BiCGSTAB")
     nincr = fem_solver.number_of_increments
     if nincr is None or int(nincr) < 2:
         raise ValueError("transient analysis needs FEMSolver(number_of_increments=N) with N >= 2")
