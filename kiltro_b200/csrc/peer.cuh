@@ -81,26 +81,54 @@ __device__ __forceinline__ void wait_flags_rows(const Wait &w, int r_first, int 
     if (!ok && w.err) *w.err = 1ull;
 }
 
-// post this rank's partial sums of event `ev` to every rank (one thread)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// post this rank's partial sums of event `ev` to every rank (one thread).  ONE fence between the data stores and the flag
+// stores (fence + relaxed store = a release): P release stores in a row each wait for the one before to be performed
+// across NVLink -- P serialised round trips per reduction, the part of the iteration overhead that grew with P.
 __device__ __forceinline__ void post_dots(const Ctx &c, unsigned long long ev, double a0, double a1, double a2, double a3) {
     const int par = (int)(ev & 1ull);
     for (int r = 0; r < c.P; ++r) {
         double *slot = reinterpret_cast<double *>(c.ctrl[r] + W_DOTS) + (par * MAXP + c.rank) * 4;
         slot[0] = a0; slot[1] = a1; slot[2] = a2; slot[3] = a3;
     }
-    __threadfence_system();
-    for (int r = 0; r < c.P; ++r) st_release_sys(c.ctrl[r] + W_DOTFLAG + par * MAXP + c.rank, ev);
+    fence_acq_rel_sys();
+    for (int r = 0; r < c.P; ++r) st_relaxed_sys(c.ctrl[r] + W_DOTFLAG + par * MAXP + c.rank, ev);
 }
 
-// wait for the partial sums of event `ev` from all ranks and add them in rank order (one thread); false on timeout
+// wait for the partial sums of event `ev` from all ranks and add them in rank order (one thread); false on timeout.
+// The P flags are polled together with relaxed loads (independent, in flight at once) and ONE acquire fence follows the
+// successful poll, instead of P acquire loads one after the other.
 __device__ __forceinline__ bool collect_dots(const Ctx &c, unsigned long long ev, double (&d)[4]) {
     const int par = (int)(ev & 1ull);
     unsigned long long *own = c.ctrl[c.rank];
-    bool ok = true;
+    bool ok = !already_failed(own + W_ERROR);
     d[0] = d[1] = d[2] = d[3] = 0.0;
-    if (already_failed(own + W_ERROR)) ok = false;
+    if (ok) {
+        const unsigned long long *flags = own + W_DOTFLAG + par * MAXP;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long f[MAXP];
+#pragma unroll
+            for (int r = 0; r < MAXP; ++r) f[r] = r < c.P ? ld_relaxed_sys(flags + r) : ev;
+            bool all = true;
+#pragma unroll
+            for (int r = 0; r < MAXP; ++r) all = all && (f[r] >= ev);
+            if (all) break;
+            if (clock64() - t0 > 4000000000LL) { ok = false; break; }
+            __nanosleep(32);
+        }
+        fence_acq_rel_sys();
+    }
     for (int r = 0; r < c.P; ++r) {
-        ok = ok && spin_until_ge(own + W_DOTFLAG + par * MAXP + r, ev);
         const volatile double *slot = reinterpret_cast<const volatile double *>(own + W_DOTS) + (par * MAXP + r) * 4;
         d[0] += slot[0]; d[1] += slot[1]; d[2] += slot[2]; d[3] += slot[3];
     }
