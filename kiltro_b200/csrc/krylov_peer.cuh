@@ -39,9 +39,9 @@ struct HaloPush {                          // where the first / last owned mesh 
         if (dn_dst != nullptr && i < nxn) dn_dst[i] = v;
         if (up_dst != nullptr && i >= n - nxn) up_dst[i - (n - nxn)] = v;
     }
-    __device__ __forceinline__ void raise() const {
-        if (dn_flag != nullptr) kbpeer::st_release_sys(dn_flag, seq);
-        if (up_flag != nullptr) kbpeer::st_release_sys(up_flag, seq);
+    __device__ __forceinline__ void raise() const {        // the caller has fenced (system scope) after the pushed rows:
+        if (dn_flag != nullptr) kbpeer::st_relaxed_sys(dn_flag, seq);   // fence + relaxed stores = releases, without the second
+        if (up_flag != nullptr) kbpeer::st_relaxed_sys(up_flag, seq);   // store waiting for the first one's round trip
     }
 };
 

@@ -652,8 +652,7 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
     float p_bh = 0.f, p_d = 0.f, p_di = 0.f, p_x = 0.f, p_c00 = 0.f, p_c01 = 0.f, p_c10 = 0.f, p_c11 = 0.f, p_wy = 0.f;
     double p_v = 0.0;
     int p_f = -1, n_f = -1;
-    auto load_stage0 = [&](int row) {
-        const int off = row * pitch + cl;
+    auto load_stage0 = [&](int row, int off) {                    // off = row * pitch + cl
         if (DOWN) {
             p_d = a.d[off];
             if (L0) {
@@ -687,8 +686,16 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
     };
 
     const int T0 = j0 - NS, T1 = j1 + NS;             // stage 0 walks rows [T0, T1)
-    if (DOWN && L0) n_f = a.n2f[T0 * pitch + cl];
-    load_stage0(T0);
+    // running offsets instead of row * pitch + column per access (the index arithmetic was two thirds of the instructions
+    // of a step): off = (row t, column cl); a lane that stores has c == cl, and stage s stores at off - s * pitch
+    int off = T0 * pitch + cl;
+    int tj = T0 - j0;                                  // t - j0: stage s stores when 0 <= tj - s < nrows
+    const unsigned nrows = (unsigned)(j1 - j0);
+    const float *pcf = a.cf + 8 * (int64_t)off;
+    const char *pf_run = pf_ptr != nullptr ? pf_ptr + (int64_t)(T0 + a.pfd) * pf_stride : nullptr;
+    const int row_end = a.ny + MG_GUARD;               // rows < row_end exist in every padded array
+    if (DOWN && L0) n_f = a.n2f[off];
+    load_stage0(T0, off);
     for (int tb = T0; tb < T1; tb += U) {
 #pragma unroll
         for (int ph = 0; ph < U; ++ph) {
@@ -699,12 +706,12 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
                 if (L0) b0 = (p_f >= 0) ? (float)p_v * p_di : 0.f;
                 else b0 = p_bh;
                 x0 = a.omega[0] * b0;
-                const bool st0 = own_col && t >= j0 && t < j1;
+                const bool st0 = own_col && (unsigned)tj < nrows;
                 if (L0 && st0) {
-                    a.bh_out[t * pitch + c] = b0;
+                    a.bh_out[off] = b0;
                     if (a.q != nullptr && p_f >= 0) a.s_out[p_f] = p_v;
                 }
-                if (NS == 1 && st0) a.x_out[t * pitch + c] = x0;
+                if (NS == 1 && st0) a.x_out[off] = x0;
             } else {
                 b0 = p_bh;
                 x0 = p_x + prolong_value(p_c00, p_c01, p_c10, p_c11, pwx, p_wy);
@@ -717,18 +724,15 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
             win[0][ph][2] = __shfl_down_sync(KB_FULL, x0, 1);
             // ---- loads: the coefficients of row t (first used by stage 1 at the next step), stage-0 inputs of row t+1
             {
-                const float *pc = a.cf + 8 * (int64_t)(t * pitch + cl);
-                const float4 lo = ld4s(pc), hi = ld4s(pc + 4);
+                const float4 lo = ld4s(pcf), hi = ld4s(pcf + 4);
                 cf[ph][0] = lo.x; cf[ph][1] = lo.y; cf[ph][2] = lo.z; cf[ph][3] = lo.w;
                 cf[ph][4] = hi.x; cf[ph][5] = hi.y; cf[ph][6] = hi.z; cf[ph][7] = hi.w;
             }
-            load_stage0(t + 1);
-            if (pf_ptr != nullptr && t + a.pfd < a.ny + MG_GUARD)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (int64_t)(t + a.pfd) * pf_stride));
-            if (a.pf1 > 0) {       // ... and into L1 a couple of rows ahead: the demand loads of the next steps then hit L1
-                const int rp = t + a.pf1 < a.ny + MG_GUARD - 1 ? t + a.pf1 : a.ny + MG_GUARD - 1;
-                const int offp = rp * pitch + cl;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cf + 8 * (int64_t)offp));
+            load_stage0(t + 1, off + pitch);
+            if (pf_run != nullptr && t + a.pfd < row_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_run));
+            if (a.pf1 > 0 && t + a.pf1 < row_end) {   // ... and into L1 a couple of rows ahead: the next steps' loads hit L1
+                const int offp = off + a.pf1 * pitch;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pcf + 8 * (int64_t)(a.pf1 * pitch)));
                 if (DOWN) {
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(a.d + offp));
                     if (L0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.dinv + offp));
@@ -743,14 +747,14 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
 #pragma unroll
             for (int s = 1; s <= NS; ++s) {
                 const int sl = (ph - s + 2 * U) % U, sd = (sl + U - 1) % U, su = (sl + 1) % U;
-                const int js = t - s;
                 const float (&w)[U][3] = win[s - 1];
                 const float xc0 = w[sl][1];
                 const float res = stencil_res(cf[sl], w[sd][0], w[sd][1], w[sd][2], w[sl][0], xc0, w[sl][2],
                                               w[su][0], w[su][1], w[su][2], bhh[sl]);
-                const bool store = own_col && js >= j0 && js < j1;
+                const bool store = own_col && (unsigned)(tj - s) < nrows;
+                const int offs = off - s * pitch;
                 if (DOWN && s == NS) {
-                    if (store) a.r_out[js * pitch + c] = dhh[sl] * res;
+                    if (store) a.r_out[offs] = dhh[sl] * res;
                 } else {
                     const float val = fmaf(a.omega[DOWN ? s : s - 1], res, xc0);   // down: sweep s+1 of nu, up: sweep s
                     if (s < NS) {
@@ -758,13 +762,15 @@ __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
                         win[s][sl][0] = __shfl_up_sync(KB_FULL, val, 1);
                         win[s][sl][2] = __shfl_down_sync(KB_FULL, val, 1);
                     }
-                    if (DOWN && s == NS - 1 && store) a.x_out[js * pitch + c] = val;
+                    if (DOWN && s == NS - 1 && store) a.x_out[offs] = val;
                     if (!DOWN && s == NS && store) {
                         if (L0) { if (fhh[sl] >= 0) a.z[fhh[sl]] = (double)val; }
-                        else a.x_out[js * pitch + c] = val;
+                        else a.x_out[offs] = val;
                     }
                 }
             }
+            off += pitch; ++tj; pcf += 8 * pitch;
+            if (pf_run != nullptr) pf_run += pf_stride;
         }
     }
 }
