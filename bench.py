@@ -490,6 +490,14 @@ def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier
                "note": "every rank uploads its strip (points, int64 connectivity, velocity, flags) from pinned host memory, "
                        "calls FEMSolver(partition='rows').Solve and reads its owned solution back, inside the timed "
                        "region; bytes are summed over the ranks"}
+    # ---- BASELINE config 5 beside the headline, measured in the same run (bounded: `--config5-time-steps` time steps of
+    # the theta = 0 loop on the same 4000 x 4000 N mesh; the stand-alone form is `--workload transient`)
+    config5 = None
+    if args.config5_time_steps > 0 and args.maxiter is None:
+        KD.close_peer_regions([fs._psys])
+        fs._psys = None
+        tl = measure_transient(args, K, torch, dist, lib, rank, world, local, barrier, 1, 1, args.config5_time_steps, 0.0)
+        config5 = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "time_loop", "verify", "t_setup_ms")}
     if rank == 0:
         cfg = gpu_config(nps, world, args.rtol, True)
         peer = info.get("exchange") == "peer"
@@ -507,17 +515,25 @@ def run_partitioned(args, K, torch, dist, lib, _lib, rank, world, local, barrier
                            "ms_per_iteration": float(solve_ms.item()) / max(1, info["iterations"])},
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "verify": verify, "t_setup_ms": t_setup * 1e3, "roofline": None, "cpu_baseline": None, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "config5_transient": config5}
         emit(line)
-    KD.close_peer_regions([fs._psys])
+    if fs._psys is not None:
+        KD.close_peer_regions([fs._psys])
 
 
 # ------------------------------------------------------------------------------------------------ config 5: transient
 def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, barrier):
+    line = measure_transient(args, K, torch, dist, lib, rank, world, local, barrier, args.steps, args.warmup, args.time_steps,
+                             args.theta)
+    if rank == 0:
+        emit(line)
+
+
+def measure_transient(args, K, torch, dist, lib, rank, world, local, barrier, steps, warmup, nt, theta):
     """BASELINE configs[4] / SURVEY 8(d) config 5: 4000 x (4000 N) nodes (128 M DOF at N = 8), theta-method time loop
     (theta = 0: the reference's intended forward Euler with a consistent-mass solve per step, FEMSolver.py:253-297),
-    row-block partitioned, through FEMSolver(analysis_type='transient', partition='rows').  A bench "step" = `--time-steps`
-    time steps of the loop; value = DOF * time steps / s."""
+    row-block partitioned, through FEMSolver(analysis_type='transient', partition='rows').  A bench "step" = `nt` time
+    steps of the loop; value = DOF * time steps / s.  Returns the JSON line (every rank; rank 0 emits or embeds it)."""
     from kiltro_b200 import distributed as KD
     nps = args.nodes_per_side
     nxn, nyn = nps, nps * world
@@ -534,9 +550,8 @@ def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, 
     form = K.HeatAdvectionDiffusion(mesh, velocity=vel)
     bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags); bc.SetInitialConditions(lambda: T0)
     dt = 0.1 * h * h / 2.0                                    # FEMSolver.py:138-144 on the uniform mesh (rho c_v = k = 1)
-    nt = args.time_steps
     fs = K.FEMSolver(analysis_type="transient", partition="rows", exchange=args.exchange, number_of_increments=nt + 1,
-                     theta=args.theta, time_step=dt, verbose=False)
+                     theta=theta, time_step=dt, verbose=False)
     solver = K.LinearSolver(tol=args.rtol, maxiter=2000)
 
     def step():
@@ -545,7 +560,7 @@ def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, 
     torch.cuda.synchronize(); t0 = time.perf_counter()
     out = step()
     torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(0, warmup - 1)):
         out = step()
     sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -553,7 +568,7 @@ def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, 
     launches0 = lib.kb_launch_count()
     e0.record()
     loop_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = step()
         loop_ms += fs.timings["solve_ms"]
     e1.record()
@@ -572,30 +587,31 @@ def run_transient_workload(args, K, torch, dist, lib, _lib, rank, world, local, 
     if world > 1:
         dist.all_reduce(rng, op=dist.ReduceOp.MIN)
     ndof = nxn * nyn
-    if rank == 0:
-        line = {"metric": "transient DOF*steps/s, 2D conv-diff theta-method (config 5)", "value": ndof * nt * args.steps / (ms * 1e-3),
-                "unit": "DOF*steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = None
+    if True:
+        line = {"metric": "transient DOF*steps/s, 2D conv-diff theta-method (config 5)", "value": ndof * nt * steps / (ms * 1e-3),
+                "unit": "DOF*steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "config 5: synthetic 2D structured quad mesh %dx%d nodes (%d DOF), transient "
                                        "convection-diffusion, theta = %g, %d time steps per bench step (assembly of K and M + "
                                        "boundary conditions + the whole time loop), inner Jacobi-%s rtol %.0e" % (
-                                           nxn, nyn, ndof, args.theta, nt, info["method"].upper(), args.rtol),
-                           "ndof": ndof, "ndof_per_gpu": nxn * nps, "theta": args.theta, "time_steps": nt, "dt": dt,
+                                           nxn, nyn, ndof, theta, nt, info["method"].upper(), args.rtol),
+                           "ndof": ndof, "ndof_per_gpu": nxn * nps, "theta": theta, "time_steps": nt, "dt": dt,
                            "l2_policy": "operators (2 x 1.15 GB + vectors per GPU) far larger than the 126 MB L2"},
-                "time_loop": {"ms_per_time_step": loop_ms / args.steps / nt, "krylov_iterations_per_time_step":
+                "time_loop": {"ms_per_time_step": loop_ms / steps / nt, "krylov_iterations_per_time_step":
                               info["iterations"] / nt, "method": info["method"], "exchange": info.get("exchange"),
                               "worst_relative_residual": info["worst_relative_residual"], "status": info["status"],
-                              "dof_steps_per_s_loop_only": ndof * nt / (loop_ms / args.steps * 1e-3)},
+                              "dof_steps_per_s_loop_only": ndof * nt / (loop_ms / steps * 1e-3)},
                 "verify": {"T_min": float(rng[0].item()), "T_max": float(-rng[1].item()),
                            "note": "bounded by the initial / boundary data up to the explicit scheme's small overshoot; parity "
                                    "of the partitioned loop against the single-GPU loop: tests/test_gpu_parity.py::"
                                    "test_peer_partitioned_transient_matches_single_gpu"},
                 "t_setup_ms": t_setup * 1e3, "roofline": None, "cpu_baseline": None, "e2e": None,
                 "gpu_launches": int(launches), "clocks": clocks}
-        emit(line)
     if getattr(fs, "_psys", None) is not None:
         KD.close_peer_regions([fs._psys])
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -609,6 +625,9 @@ def main():
                     help="steady: the headline metric (BASELINE configs[3]); transient: config 5 (theta-method time loop)")
     ap.add_argument("--theta", type=float, default=0.0, help="--workload transient: theta of the time scheme")
     ap.add_argument("--time-steps", type=int, default=50, help="--workload transient: time steps per bench step")
+    ap.add_argument("--config5-time-steps", type=int, default=20,
+                    help="steady workload: time steps of the bounded config-5 (transient) record embedded in the line "
+                         "(0 = skip)")
     ap.add_argument("--nodes-per-side", type=int, default=4000)
     ap.add_argument("--rtol", type=float, default=1.0e-10)
     ap.add_argument("--check-every", type=int, default=100)
@@ -965,6 +984,13 @@ def main():
         raise SystemExit("bench.py: the timed solve did not converge (status %d, relative residual %.3e) -- no throughput "
                          "record is emitted for a failed solve" % (info["status"], info["relative_residual"]))
 
+    # ---- BASELINE config 5 beside the headline (bounded: `--config5-time-steps` time steps of the theta = 0 loop on the same
+    # mesh through FEMSolver(analysis_type='transient', partition='rows') with one strip; stand-alone: `--workload transient`)
+    config5 = None
+    if args.config5_time_steps > 0 and not profiling_run:
+        tl = measure_transient(args, K, torch, dist, lib, rank, world, local, barrier, 1, 1, args.config5_time_steps, 0.0)
+        config5 = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "time_loop", "verify", "t_setup_ms")}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_block(args.ref_nodes_per_side, args.cpu_baseline_steps, args.ref_stubbed_nodes_per_side)
@@ -983,7 +1009,7 @@ def main():
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "t_symbolic_ms": t_symbolic * 1e3,
                 "roofline": roof, "roofline_assembly": roof_asm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "value_multigrid": mgleg}
+                "value_multigrid": mgleg, "config5_transient": config5}
         if profiling_run:
             line["profiling_run"] = "--maxiter %d: iterations capped for a profiler, `value` withheld unless the solve converged" % args.maxiter
         emit(line)
