@@ -478,7 +478,7 @@ int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps);
 void kb_mg_set_fused(int on);
 void kb_mg_set_tail(int on);               /* the coarsest levels as one shared-memory kernel (bit-identical; default on) */
 void kb_mg_set_aggressive(int nodes);      /* plans made afterwards coarsen levels with <= nodes per direction by 4 (default 0: off) */
-void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0) */
+void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0; set it before kb_mg_setup, which then computes the weights) */
 void kb_mg_set_overweight(double eta);        /* residual over-weighting factor of the restriction (default 1) */
 void kb_mg_set_rows_per_task(int rows);
 void kb_mg_set_min_rows(int rows);        /* shortest task (rows) the per-level choice may pick */

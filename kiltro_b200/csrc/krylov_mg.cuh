@@ -113,7 +113,7 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
     int total_iters = 0, status = KB_ENOTCONV, restarts = 0;
     const double rtol2 = rtol * rtol;
     double prev_true = INFINITY;
-    bool recurrence_converged = false, attainable = false;
+    bool recurrence_converged = false, attainable = false, verdict_known = false;
     for (int restart = 0; restart < 8 && total_iters < maxiter; ++restart) {
         restarts = restart;
         // (re)start from the TRUE residual: r = b - A x ; p = r ; rhat = r ; rho = <r,r>
@@ -121,7 +121,7 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
         if ((rc = launch_vec<1>(n, BodyResidual{b, m.v, m.r, m.p, m.rhat}, FinInit{w.sc, w.done, rtol2}, w, nullptr, s))) return rc;
         if ((rc = read_state(w, &hs, s))) return rc;
         const double true_rr = hs.sc[S_RES2], tol2 = rtol2 * hs.sc[S_AUX0];
-        if (hs.done[0] == 1) { status = 0; break; }
+        if (hs.done[0] == 1) { status = 0; verdict_known = true; break; }     // hs holds the true residual of the returned x
         if (hs.done[0] == 2) { status = KB_EBREAKDOWN; break; }
         if (restart > 0 && !(true_rr < 0.25 * prev_true) && true_rr <= 100.0 * tol2) { attainable = true; break; }
         if (recurrence_converged && !(true_rr < 0.25 * prev_true) && true_rr <= 1.0e6 * tol2) { attainable = true; break; }
@@ -153,10 +153,12 @@ int mg_bicgstab(kb_mg *mg, int64_t n, int64_t nnz, const int32_t *indptr, const 
         k_clear_done<<<1, 1, 0, s>>>(w.done);
         KB_LAUNCH_CHECK();
     }
-    // verdict on the true residual of the returned x
-    if ((rc = launch_spmv<0>(n, nnz, indptr, indices, vals, w, x, m.v, nullptr, nullptr, NoFinal{}, s))) return rc;
-    if ((rc = launch_vec<1>(n, BodyResidual{b, m.v, m.r, m.p, nullptr}, FinInit{w.sc, w.iter + 2, rtol2}, w, nullptr, s))) return rc;
-    if ((rc = read_state(w, &hs, s))) return rc;
+    // verdict on the true residual of the returned x (already at hand when the loop ended on its own true-residual test)
+    if (!verdict_known) {
+        if ((rc = launch_spmv<0>(n, nnz, indptr, indices, vals, w, x, m.v, nullptr, nullptr, NoFinal{}, s))) return rc;
+        if ((rc = launch_vec<1>(n, BodyResidual{b, m.v, m.r, m.p, nullptr}, FinInit{w.sc, w.iter + 2, rtol2}, w, nullptr, s))) return rc;
+        if ((rc = read_state(w, &hs, s))) return rc;
+    }
     const double res2 = hs.sc[S_RES2], b2 = hs.sc[S_AUX0];
     info->iterations = total_iters;
     info->residual = sqrt(res2);

@@ -1269,8 +1269,10 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         KB_CUDA(cudaMemsetAsync(L.cf - padded_origin(L, 8), 0, sizeof(float) * padded_elems(L, 8), s));
         KB_CUDA(cudaMemsetAsync(L.d - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
         KB_CUDA(cudaMemsetAsync(L.dinv - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
-        KB_CUDA(cudaMemsetAsync(L.cbx - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
-        KB_CUDA(cudaMemsetAsync(L.cby - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+        if (g_mg_upwind) {                                  // only the Petrov-Galerkin restriction switch reads them
+            KB_CUDA(cudaMemsetAsync(L.cbx - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+            KB_CUDA(cudaMemsetAsync(L.cby - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
+        }
         if (first) {
             float *v[4] = {L.bh, L.xa, L.xb, L.r};
             for (int k = 0; k < 4; ++k) KB_CUDA(cudaMemsetAsync(v[k] - padded_origin(L, 1), 0, sizeof(float) * padded_elems(L, 1), s));
@@ -1301,7 +1303,7 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
         const double *pf = l == 1 ? d_points : F.pts, *vf = d_velocity == nullptr ? nullptr : (l == 1 ? d_velocity : F.vel);
         k_mg_sample<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, F.nx, F.ny, pf, vf, F.fixed, L.pts, L.vel, L.fixed);
         KB_LAUNCH_CHECK();
-        if (d_velocity != nullptr) {
+        if (d_velocity != nullptr && g_mg_upwind) {
             k_mg_pg_weights<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, o.k, L.cbx, L.cby);
             KB_LAUNCH_CHECK();
         }
