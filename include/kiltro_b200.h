@@ -476,6 +476,7 @@ int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps);
 /* development switches: fused legs of the cycle (one kernel per leg and level instead of one per sweep; bit-identical
  * results) on / off, and the node rows per warp task of the fused kernels */
 void kb_mg_set_fused(int on);
+void kb_mg_set_assemble_tiled(int on);     /* coarse operators: every element evaluated once per CTA tile (bit-identical; default on) */
 void kb_mg_set_tail(int on);               /* the coarsest levels as one shared-memory kernel (bit-identical; default on) */
 void kb_mg_set_aggressive(int nodes);      /* plans made afterwards coarsen levels with <= nodes per direction by 4 (default 0: off) */
 void kb_mg_set_upwind_restriction(int on);   /* 1: residuals are restricted with the coarse Petrov-Galerkin test functions (default 0; set it before kb_mg_setup, which then computes the weights) */

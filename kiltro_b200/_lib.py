@@ -163,6 +163,7 @@ SIGNATURES = {
     "kb_mg_set_cycle": (I32, [c_vp, I32, ctypes.POINTER(ctypes.c_int32)]),
     "kb_mg_set_fused": (None, [I32]),
     "kb_mg_set_tail": (None, [I32]),
+    "kb_mg_set_assemble_tiled": (None, [I32]),
     "kb_mg_set_aggressive": (None, [I32]),
     "kb_mg_set_upwind_restriction": (None, [I32]),
     "kb_mg_set_overweight": (None, [F64]),

@@ -299,6 +299,77 @@ __global__ void __launch_bounds__(256) k_mg_pg_weights(int nx, int ny, int pitch
     }
 }
 
+// The same operator, tiled: a CTA owns AT_X x AT_Y nodes, evaluates the (AT_X + 1) x (AT_Y + 1) elements around them ONCE
+// each into shared memory (k_mg_assemble_dia evaluates every element four times, once per node: the fp64 element routine
+// is what that kernel costs), then every node gathers row `a` of its <= 4 elements in the same order -- bit-identical
+// results (test_coarse_assembly_tiled_bitwise).
+constexpr int AT_X = 32, AT_Y = 8, AT_EX = AT_X + 1, AT_EY = AT_Y + 1;
+template <bool VEL>
+__global__ void __launch_bounds__(AT_X * AT_Y) k_mg_assemble_dia_tile(int nx, int ny, int pitch, const double *__restrict__ pts,
+                                                                     const double *__restrict__ vel,
+                                                                     const uint8_t *__restrict__ fixed, ElemOpts o,
+                                                                     float *__restrict__ cf, float *__restrict__ d,
+                                                                     float *__restrict__ dinv) {
+    extern __shared__ double s_ke[];                         // [AT_EX * AT_EY][16]
+    const int i0 = blockIdx.x * AT_X, j0 = blockIdx.y * AT_Y;
+    for (int e = threadIdx.x; e < AT_EX * AT_EY; e += AT_X * AT_Y) {
+        const int ex = i0 - 1 + e % AT_EX, ey = j0 - 1 + e / AT_EX;
+        if (ex < 0 || ey < 0 || ex >= nx - 1 || ey >= ny - 1) continue;
+        const int64_t n0 = (int64_t)ey * nx + ex;
+        const int64_t nd[4] = {n0, n0 + 1, n0 + nx + 1, n0 + nx};
+        double X[4][2], U[4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            X[a][0] = pts[2 * nd[a]]; X[a][1] = pts[2 * nd[a] + 1];
+            U[a][0] = VEL ? vel[2 * nd[a]] : 0.0; U[a][1] = VEL ? vel[2 * nd[a] + 1] : 0.0;
+        }
+        double Ke[16], Fe[4], Me[16];
+        quad4(X, U, o, Ke, Fe, Me);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_ke[e * 16 + k] = Ke[k];
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x % AT_X, j = j0 + threadIdx.x / AT_X;
+    if (i >= nx || j >= ny) return;
+    const int64_t p = (int64_t)j * nx + i, pp = (int64_t)j * pitch + i;
+    if (fixed[p]) return;                                    // d and c stay 0 (memset by the caller)
+    double st[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st[k] = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int ex = i - 1 + (e & 1), ey = j - 1 + (e >> 1);
+        if (ex < 0 || ey < 0 || ex >= nx - 1 || ey >= ny - 1) continue;
+        const double *Ke = s_ke + ((ey - (j0 - 1)) * AT_EX + (ex - (i0 - 1))) * 16;
+        const int lx = i - ex, ly = j - ey, a = ly == 0 ? lx : 3 - lx;
+        const int bx[4] = {ex, ex + 1, ex + 1, ex}, by[4] = {ey, ey, ey + 1, ey + 1};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double v = Ke[4 * a + b];
+            const int slot = (by[b] - j + 1) * 3 + (bx[b] - i + 1);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st[k] += (k == slot) ? v : 0.0;
+        }
+    }
+    double dg = st[4];
+    if (!(dg != 0.0) || !isfinite(dg)) dg = 1.0;
+    const double inv = 1.0 / dg;
+    d[pp] = (float)dg;
+    dinv[pp] = (float)inv;
+    float out[8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (k == 4) continue;
+        const int qi = i + (k % 3) - 1, qj = j + (k / 3) - 1;
+        float cv = 0.f;
+        if (qi >= 0 && qj >= 0 && qi < nx && qj < ny && !fixed[(int64_t)qj * nx + qi]) cv = (float)(st[k] * inv);
+        out[k > 4 ? k - 1 : k] = cv;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(cf + 8 * pp);
+    dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
 // coarsest level: dense [Ahat | I] (fp64, n x 2n) from the stencil; rows of non-unknowns are identity rows
 __global__ void __launch_bounds__(256) k_mg_dense_build(int nx, int ny, int pitch, const float *__restrict__ cf,
                                                         const float *__restrict__ d, double *__restrict__ W) {
@@ -1030,6 +1101,7 @@ int launch_prolong(const MgLevel &L, const MgLevel &Cn, const float *xc, float *
 }
 
 int g_mg_tail = 1;            // 1: the coarsest levels run as one shared-memory kernel (kb_mg_set_tail)
+int g_mg_assemble_tiled = 1;  // 1: coarse operators by k_mg_assemble_dia_tile (each element evaluated once per tile)
 
 size_t tail_smem_bytes(const kb_mg *mg, int first) {
     size_t f = 0;
@@ -1307,7 +1379,19 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
             k_mg_pg_weights<<<kb_grid(nn, 256, 8), 256, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, o.k, L.cbx, L.cby);
             KB_LAUNCH_CHECK();
         }
-        if (d_velocity != nullptr)
+        if (g_mg_assemble_tiled && kb_cdiv(L.ny, AT_Y) <= 65535) {
+            const dim3 tg((unsigned)kb_cdiv(L.nx, AT_X), (unsigned)kb_cdiv(L.ny, AT_Y));
+            const size_t sm = sizeof(double) * AT_EX * AT_EY * 16;
+            static KbOncePerDevice configured;
+            if (configured.need()) {
+                KB_CUDA(cudaFuncSetAttribute(k_mg_assemble_dia_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                KB_CUDA(cudaFuncSetAttribute(k_mg_assemble_dia_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            }
+            if (d_velocity != nullptr)
+                k_mg_assemble_dia_tile<true><<<tg, AT_X * AT_Y, sm, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
+            else
+                k_mg_assemble_dia_tile<false><<<tg, AT_X * AT_Y, sm, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
+        } else if (d_velocity != nullptr)
             k_mg_assemble_dia<true><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
         else
             k_mg_assemble_dia<false><<<kb_grid(nn, 128, 16), 128, 0, s>>>(L.nx, L.ny, L.pitch, L.pts, L.vel, L.fixed, o, L.cf, L.d, L.dinv);
@@ -1348,6 +1432,7 @@ extern "C" int kb_mg_apply(kb_mg *mg, const double *d_v, double *d_z, void *stre
  * (0 = chosen per level), their L2 prefetch distance */
 extern "C" void kb_mg_set_fused(int on) { g_mg_fused = on; }
 extern "C" void kb_mg_set_tail(int on) { g_mg_tail = on; }
+extern "C" void kb_mg_set_assemble_tiled(int on) { g_mg_assemble_tiled = on; }
 /* cycle schedule: h_reps[l] = coarse-grid corrections per visit of level l (levels beyond n keep 1 = V-cycle) */
 extern "C" int kb_mg_set_cycle(kb_mg *mg, int n, const int32_t *h_reps) {
     if (!mg || !h_reps || n < 0 || n > MG_MAXLEV) return KB_EINVAL;

@@ -175,6 +175,43 @@ def test_fused_legs_bitwise(nps, nu, omega, cycle):
         lib.kb_mg_set_fused(1); lib.kb_mg_set_rows_per_task(0); lib.kb_mg_set_tail(1)
 
 
+@pytest.mark.parametrize("nps,peclet_scale", [(301, 1.0), (130, 0.0), (517, 2.0)])
+def test_coarse_assembly_tiled_matches_per_node(nps, peclet_scale):
+    """The tiled rediscretisation of the coarse operators (every element evaluated once per CTA tile, gathered from shared
+    memory) against the per-node form (every element evaluated by each of its four nodes): same sums in the same order;
+    the cycles built on them agree to fp32 rounding (the element routine is inlined into two kernels, whose FMA
+    contraction may differ in the last bit of a coefficient)."""
+    import bench
+    import kiltro_b200 as K
+    from kiltro_b200 import _lib
+    from kiltro_b200.multigrid import GridMultigrid
+    lib = _lib.load()
+    mesh, vel, flags, mat = bench.make_problem(K, torch, nps)
+    form = K.HeatAdvectionDiffusion(mesh, velocity=vel * peclet_scale) if peclet_scale > 0 else K.HeatDiffusion(mesh)
+    bc = K.BoundaryCondition(); bc.SetDirichletCriteria(lambda: flags)
+    fs = K.FEMSolver(verbose=False)
+    Kc = K.Assemble(fs, form.function_spaces, form, mesh, mat, bc)[0]
+    bc.GetDirichletBoundaryConditions(form, mesh, mat, fs)
+    F = torch.zeros((mesh.nnodes, 1), dtype=torch.float64, device="cuda")
+    Kb, Fb = bc.ApplyDirichletGetReducedMatrices(Kc, F, bc.applied_dirichlet_device)[:2]
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    r = torch.randn(Kb.shape[0], dtype=torch.float64, device="cuda", generator=g)
+    mg = GridMultigrid(mesh, form, mat, bc)
+    try:
+        lib.kb_mg_set_assemble_tiled(0)
+        mg.setup(Kb)
+        ref = mg.apply(r)
+        lib.kb_mg_set_assemble_tiled(1)
+        mg.setup(Kb)
+        got = mg.apply(r)
+    finally:
+        lib.kb_mg_set_assemble_tiled(1)
+    err = float(torch.linalg.vector_norm(got - ref) / torch.linalg.vector_norm(ref))
+    print("tiled vs per-node coarse assembly, %d^2 nodes: relative difference of one cycle %.2e (%s)" % (
+        nps, err, "bit-identical" if torch.equal(got, ref) else "rounding"))
+    assert err < 1e-5, err
+
+
 def test_multigrid_rejects_what_it_cannot_precondition():
     import kiltro_b200 as K
     from kiltro_b200.multigrid import GridMultigrid
