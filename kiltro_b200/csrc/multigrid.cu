@@ -66,14 +66,13 @@ struct kb_mg {
     float omega[4] = {0.67f, 0.67f, 0.67f, 0.67f};   // damping of sweep 1..nu (pre- and post-smoothing alike)
     int64_t nfree = 0;
     int reps[MG_MAXLEV];            // coarse-grid corrections per visit of level l (1 everywhere: V-cycle); kb_mg_set_cycle
-    int *free2pp = nullptr, *free2node = nullptr;
+    int *free2pp = nullptr;
     int *n2f = nullptr;             // level 0, padded like the vectors: unknown of a node, -1 elsewhere
     int tail_first = -1;            // first level of the shared-memory tail (k_mg_tail), -1: none
     int ncoarse = 0;
     double *dense = nullptr;
     float *ainv = nullptr;
     int *flag = nullptr;
-    bool has_velocity = false;
     bool ready = false;
     void *ws_base = nullptr;        // workspace the device pointers above were carved from
     KbMgSolveCache solve_cache = {nullptr, nullptr, nullptr, 0, 0, 0};
@@ -131,9 +130,9 @@ size_t carve(kb_mg *mg, char *base, bool assign) {
     const MgLevel &L0 = mg->L[0];
     const size_t nn0 = (size_t)L0.nx * L0.ny;
     {
-        int *p = (int *)take(sizeof(int) * nn0), *q = (int *)take(sizeof(int) * nn0);
+        int *p = (int *)take(sizeof(int) * nn0);
         int *r = (int *)take(sizeof(int) * padded_elems(L0, 1)) + padded_origin(L0, 1);
-        if (assign) { mg->free2pp = p; mg->free2node = q; mg->n2f = r; }
+        if (assign) { mg->free2pp = p; mg->n2f = r; }
     }
     const size_t nc = (size_t)mg->ncoarse;
     { double *p = (double *)take(sizeof(double) * nc * 2 * nc); if (assign) mg->dense = p; }
@@ -146,18 +145,18 @@ __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast
 __device__ __forceinline__ float4 ld4s(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
 
 // ------------------------------------------------------------------------------------------------ set-up kernels
-// reduced DOF -> compact node / padded index (level 0), the padded node -> unknown map and the fixed-node mask, from the
+// reduced DOF -> padded index (level 0), the padded node -> unknown map and the fixed-node mask, from the
 // renumbering of kb_dirichlet_split (n2f is pre-filled with -1)
 __global__ void __launch_bounds__(256) k_mg_free_map(int64_t nn, int nx, int pitch, const int32_t *__restrict__ renum,
-                                                     int *__restrict__ free2node, int *__restrict__ free2pp,
-                                                     int *__restrict__ n2f, uint8_t *__restrict__ fixed) {
+                                                     int *__restrict__ free2pp, int *__restrict__ n2f,
+                                                     uint8_t *__restrict__ fixed) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nn; p += stride) {
         const int f = renum[p];
         const int pp = (int)(p / nx) * pitch + (int)(p % nx);
         fixed[p] = f < 0;
         n2f[pp] = f >= 0 ? f : -1;
-        if (f >= 0) { free2node[f] = (int)p; free2pp[f] = pp; }
+        if (f >= 0) free2pp[f] = pp;
     }
 }
 
@@ -1331,7 +1330,7 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
     mg->ws_base = d_workspace;
     if (nu > 4 && !(omega > 0.0)) return KB_EINVAL;
     mg->nu = nu; mg->nfree = nfree;
-    if (omega > 0.0) for (int k = 0; k < 4; ++k) mg->omega[k] = (float)omega;      // omega <= 0: keep kb_mg_set_smoother's factors mg->has_velocity = d_velocity != nullptr;
+    if (omega > 0.0) for (int k = 0; k < 4; ++k) mg->omega[k] = (float)omega;      // omega <= 0: keep kb_mg_set_smoother's factors
     MgLevel &L0 = mg->L[0];
     const int64_t nn0 = (int64_t)L0.nx * L0.ny;
     if (nfree > nn0) return KB_EINVAL;
@@ -1361,7 +1360,7 @@ extern "C" int kb_mg_setup(kb_mg *mg, const double *d_points, const double *d_ve
     }
     KB_CUDA(cudaMemsetAsync(mg->n2f - padded_origin(L0, 1), 0xff, sizeof(int) * padded_elems(L0, 1), s));   // -1
     KB_CUDA(cudaMemsetAsync(mg->flag, 0, sizeof(int) * 8, s));
-    k_mg_free_map<<<kb_grid(nn0, 256, 8), 256, 0, s>>>(nn0, L0.nx, L0.pitch, d_renum, mg->free2node, mg->free2pp, mg->n2f,
+    k_mg_free_map<<<kb_grid(nn0, 256, 8), 256, 0, s>>>(nn0, L0.nx, L0.pitch, d_renum, mg->free2pp, mg->n2f,
                                                        L0.fixed);
     KB_LAUNCH_CHECK();
     k_mg_dia_from_csr<<<kb_grid(nfree, 256, 8), 256, 0, s>>>(nfree, d_indptr, d_indices, d_vals, mg->free2pp, mg->n2f,
