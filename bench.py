@@ -625,7 +625,7 @@ def main():
                     help="steady: the headline metric (BASELINE configs[3]); transient: config 5 (theta-method time loop)")
     ap.add_argument("--theta", type=float, default=0.0, help="--workload transient: theta of the time scheme")
     ap.add_argument("--time-steps", type=int, default=50, help="--workload transient: time steps per bench step")
-    ap.add_argument("--config5-time-steps", type=int, default=20,
+    ap.add_argument("--config5-time-steps", type=int, default=50,
                     help="steady workload: time steps of the bounded config-5 (transient) record embedded in the line "
                          "(0 = skip)")
     ap.add_argument("--nodes-per-side", type=int, default=4000)
