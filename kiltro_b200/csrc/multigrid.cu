@@ -666,7 +666,8 @@ struct LegArgs {
     const int *done;
 };
 
-// (two CTAs per SM: nu = 3 needs ~120 registers; capping it at 85 for a third CTA spills and ran 16 % slower)
+// (two CTAs of 8 warps per SM: nu = 3 needs ~120 registers; capping it at 85 for a third CTA spills and ran 16 % slower,
+// 10-warp CTAs at a cap of 96 registers 5 % slower)
 template <int NS, bool DOWN, bool L0, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_mg_leg(const LegArgs a) {
     kb_pdl_wait();
