@@ -46,3 +46,38 @@ def test_grid_entry_mapping_matches_scatter(nx, ny):
     got = grid_rows(Ke, nxn, nyn)
     assert got.shape[0] == A.nnz == (3 * nxn - 2) * (3 * nyn - 2)
     assert np.allclose(got, A.data, rtol=0, atol=1e-14)
+
+
+def grid_pattern(nxn, nyn):
+    """CPU restatement of kb_pattern_grid (kiltro_b200/csrc/pattern.cu): indptr / indices / diagonal positions of a mesh
+    numbered like Mesh.Rectangle, written down from the shape with the kernel's closed-form row offsets."""
+    nn = nxn * nyn
+    rowlen = 3 * nxn - 2
+    indptr = np.zeros(nn + 1, np.int64); indices = []; diag = np.zeros(nn, np.int64)
+    for p in range(nn):
+        i, j = p % nxn, p // nxn
+        cy = (j > 0) + 1 + (j < nyn - 1)
+        q = rowlen * (3 * j - 1 if j > 0 else 0) + cy * (3 * i - 1 if i > 0 else 0)
+        assert q == len(indices)                             # the closed form IS the running count
+        indptr[p] = q
+        for dj in range(-1 if j > 0 else 0, (1 if j < nyn - 1 else 0) + 1):
+            for di in range(-1 if i > 0 else 0, (1 if i < nxn - 1 else 0) + 1):
+                if dj == 0 and di == 0:
+                    diag[p] = len(indices)
+                indices.append(p + dj * nxn + di)
+    indptr[nn] = len(indices)
+    return indptr, np.array(indices), diag
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 1), (1, 4), (7, 5), (33, 4), (20, 31)])
+def test_grid_pattern_formula_matches_the_oracle(nx, ny):
+    """The shape-only pattern equals the oracle's restatement of the reference's sort + unique (ComputeSparsityPattern.h:22-62),
+    and nnz = (3 nxn - 2)(3 nyn - 2)."""
+    from oracle import kiltro_oracle as O
+    el = O.mesh_rectangle((0.0, 0.0), (1.0, 1.0), nx, ny)[1]
+    nxn, nyn = nx + 1, ny + 1
+    ind, ptr = O.sparsity_pattern_fast(el, nxn * nyn)
+    indptr, indices, diag = grid_pattern(nxn, nyn)
+    assert indptr[-1] == (3 * nxn - 2) * (3 * nyn - 2) == len(ind)
+    assert np.array_equal(indptr, ptr) and np.array_equal(indices, ind)
+    assert np.array_equal(indices[diag], np.arange(nxn * nyn))
