@@ -423,7 +423,7 @@ int launch_spmv_raw(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t
             KB_CUDA(cudaFuncSetAttribute(k_spmv_pat<DOTS, Final>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         }
         KB_CUDA(kb_launch_pdl(k_spmv_pat<DOTS, Final>, dim3(tma_grid(nblk)), dim3(P_THREADS), bytes, s, pdl, nblk, indptr,
-                              row_pat, pat_tab, vals, rowblk, x, y, dotw, partials, ticket, done, fin, dotw2, pwait, EpiNone{}));
+                              row_pat, pat_tab, vals, rowblk, x, y, dotw, partials, ticket, done, fin, dotw2, pwait));
         KB_LAUNCH_CHECK();
         return 0;
     }

@@ -36,18 +36,13 @@ constexpr size_t pat_smem_bytes() {
     return sizeof(StageP) * P_STAGES + 2 * P_STAGES * sizeof(uint64_t) + 512 + sizeof(pat_off_t) * P_SLOTS * P_MAXLEN;
 }
 
-// Row epilogues (the multigrid kernels of multigrid.cu reuse this SpMV): what is stored to y[r] -- and enters the fused dot
-// products -- as a function of the row's sum.  EpiNone: y = A x.
-struct EpiNone { __device__ __forceinline__ double operator()(int, double sum) const { return sum; } };
-
-template <int DOTS, class Final, class Epi = EpiNone>
+template <int DOTS, class Final>
 __global__ void __launch_bounds__(P_THREADS, 2)
 k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__restrict__ row_pat,
            const pat_off_t *__restrict__ pat_tab, const double *__restrict__ vals, const int32_t *__restrict__ rowblk,
            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
            double *__restrict__ partials, unsigned int *__restrict__ ticket, const int *__restrict__ done, Final fin,
-           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0},
-           Epi epi = Epi{}) {
+           const double *__restrict__ w2 = nullptr, kbpeer::Wait pwait = kbpeer::Wait{nullptr, nullptr, 0ull, nullptr, 0}) {
     // pwait: halo flags raised by the neighbouring ranks (peer.cuh); the kernel does not touch x before they are up
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GRAN = 2;                                // values per 16 bytes (bulk-copy granule)
@@ -173,7 +168,6 @@ k_spmv_pat(int64_t nblk, const int32_t *__restrict__ indptr, const uint8_t *__re
                     sum = fma(st.vals[q], __ldg(x + (r + (int)po[q - a])), sum);
                 for (int q = (bs > a ? bs : a); q < b; ++q)      // unstaged tail (last block of the matrix only)
                     sum = fma(__ldg(vals + m.pa + q), __ldg(x + (r + (int)po[q - a])), sum);
-                sum = epi(r, sum);
                 y[r] = sum;
                 if (DOTS) { d0 += wv * sum; d1 += sum * sum; }
                 if (DOTS == 2) { d2 += w2v * sum; d3 += w2v * wv; }
